@@ -1,0 +1,47 @@
+"""Pins the CPU oracle on the reference's committed golden vectors.
+
+The assertions are the reference's own (examples/Line1d_Cuspy_Laplace.py:64-67): S exact,
+x_frame and f_frame np.allclose. By default the expensive examples are run over a prefix of
+the protocol so the CPU suite stays within minutes; FQSB_FULL_GOLDEN=1 runs all of them to the
+end (all six pass in full: see DESIGN.md "Oracle").
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import protocol
+
+FULL = os.environ.get("FQSB_FULL_GOLDEN", "0") == "1"
+
+CASES = {
+    # name: (steps by default, steps in the golden)
+    "Line1d_Cuspy_Laplace": (120, 1000),
+    "Line1d_Cuspy_Laplace_Nopassing": (1000, 1000),
+    "Line1d_Cuspy_Quartic": (120, 1000),
+    "Line1d_SemiSmooth_Laplace": (300, 1000),
+    "Line1d_Cuspy_Laplace_LongRange": (12, 200),
+    "Line2d_Cuspy_Laplace": (40, 1000),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_reproduces_golden(name, golden_dir):
+    nstep = CASES[name][1] if FULL else CASES[name][0]
+    golden = np.load(golden_dir / f"{name}.npz")
+    system = protocol.make(orc.Line1d, orc.Line2d, name)
+    protocol.check(golden, *protocol.run(system, nstep))
+
+
+def test_pcg32_known_answer():
+    """pcg32 reference vector: the PCG paper's demo seeding (42, 54) gives 0xa15c02b7 first."""
+    import ctypes as C
+
+    # next_double = (uint32 << 20 | 0x3ff...) - 1  ==  uint32 / 2^32 exactly
+    d = orc.pcg32_draws(42, 6, initseq=54)
+    u32 = (d * 2.0**32).astype(np.uint64)
+    assert [hex(int(i)) for i in u32] == [
+        "0xa15c02b7", "0x7b47f409", "0xba1d3330", "0x83d2f293", "0xbfa4784b", "0xcbed606e"]
+    assert C.sizeof(orc.Params) == 160
