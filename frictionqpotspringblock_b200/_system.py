@@ -1,0 +1,354 @@
+"""Host-side mirror of the reference's system classes over the C ABI.
+
+``System`` reproduces the Python surface bound in /root/reference/python/main.cpp:46-226
+(``mySystemNd`` + ``mySystemNdAthermal`` + ``mySystemNdDynamics``) for one realisation;
+``Ensemble`` is the same surface over ``nrealisations`` independent realisations in one handle
+(new: the reference has no batch class). No arithmetic happens here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import lib, check
+
+
+def _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1, k2, k_frame, dt,
+            seed, distribution, parameters, offset, nchunk, nrealisations, seed_stride, device,
+            kernel):
+    if distribution not in _capi.DIST:
+        raise RuntimeError("Unknown distribution: " + str(distribution))  # detail.h:65
+    p = _capi.Params()
+    p.potential = _capi.POT[potential]
+    p.interactions = _capi.INT[interactions]
+    p.minimisation = int(minimisation)
+    shape = [int(i) for i in shape]
+    p.rank = len(shape)
+    p.shape[0] = shape[0]
+    p.shape[1] = shape[1] if len(shape) == 2 else 1
+    p.m, p.eta, p.mu, p.kappa = float(m), float(eta), float(mu), float(kappa)
+    p.k1, p.k2, p.k_frame, p.dt = float(k1), float(k2), float(k_frame), float(dt)
+    p.seed = int(seed)
+    p.distribution = _capi.DIST[distribution]
+    parameters = [float(i) for i in parameters]
+    p.nparameters = len(parameters)
+    for k, val in enumerate(parameters[:4]):
+        p.parameters[k] = val
+    p.offset = float(offset)
+    p.nchunk = int(nchunk)
+    p.nrealisations = int(nrealisations)
+    p.seed_stride = int(seed_stride)
+    p.device = int(device)
+    p.kernel = int(kernel)
+    return p
+
+
+class _Chunk:
+    """``system.chunk``: the python-prrng ``pcg32_tensor_cumsum`` surface the reference exposes
+    (main.cpp:65-70) as exercised by tests/test_Line1d.py:83-86,309-326. The device keeps no
+    chunk (only the current well and the generator state), so ``data`` / ``start`` are a window
+    of ``nchunk`` yield positions regenerated on demand."""
+
+    _MARGIN = 30  # prrng::alignment(buffer=2, margin=30, ...), Line1d.h:154
+    _BUFFER = 2
+
+    def __init__(self, owner):
+        self._o = owner
+        self._start = np.zeros(owner._full_shape, dtype=np.int64)
+
+    def _arr(self, fn, dtype):
+        o = self._o
+        out = np.empty(o._full_shape, dtype=dtype)
+        check(fn(o._h, out.ctypes.data, out.size))
+        return o._squeeze(out)
+
+    @property
+    def index_at_align(self):
+        return self._arr(lib.fqsb_chunk_index_at_align, np.int64)
+
+    @property
+    def left_of_align(self):
+        return self._arr(lib.fqsb_chunk_left_of_align, np.float64)
+
+    @property
+    def right_of_align(self):
+        return self._arr(lib.fqsb_chunk_right_of_align, np.float64)
+
+    def _update_start(self):
+        o = self._o
+        i = np.empty(o._full_shape, dtype=np.int64)
+        check(lib.fqsb_chunk_index_at_align(o._h, i.ctypes.data, i.size))
+        loc = i - self._start
+        move = (loc < self._BUFFER) | (loc >= o._nchunk - 1 - self._BUFFER)
+        self._start = np.where(move, np.maximum(i - self._MARGIN, 0), self._start)
+        return i
+
+    @property
+    def start(self):
+        self._update_start()
+        return self._o._squeeze(self._start.copy())
+
+    @property
+    def chunk_index_at_align(self):
+        i = self._update_start()
+        return self._o._squeeze(i - self._start)
+
+    @property
+    def chunk_size(self):
+        return self._o._nchunk
+
+    @property
+    def data(self):
+        o = self._o
+        self._update_start()
+        first = np.ascontiguousarray(self._start, dtype=np.int64)
+        out = np.empty(o._full_shape + (o._nchunk,), dtype=np.float64)
+        check(lib.fqsb_chunk_data(o._h, first.ctypes.data, o._nchunk, out.ctypes.data))
+        return o._squeeze(out)
+
+    def state_at(self, index):
+        o = self._o
+        index = np.ascontiguousarray(np.broadcast_to(index, o._user_shape).reshape(o._full_shape),
+                                     dtype=np.int64)
+        out = np.empty(o._full_shape, dtype=np.uint64)
+        check(lib.fqsb_chunk_state_at(o._h, index.ctypes.data, out.ctypes.data, out.size))
+        return o._squeeze(out)
+
+    def restore(self, state, value, index):
+        o = self._o
+        state = np.ascontiguousarray(np.asarray(state, dtype=np.uint64).reshape(o._full_shape))
+        value = np.ascontiguousarray(np.asarray(value, dtype=np.float64).reshape(o._full_shape))
+        index = np.ascontiguousarray(np.asarray(index, dtype=np.int64).reshape(o._full_shape))
+        check(lib.fqsb_chunk_restore(o._h, state.ctypes.data, value.ctypes.data,
+                                     index.ctypes.data, state.size))
+        self._start = index.copy()
+
+
+class Ensemble:
+    """``nrealisations`` independent systems in one device-resident handle.
+
+    Realisation ``r`` is the reference system constructed with ``seed + r * seed_stride``
+    (``seed_stride`` defaults to the number of blocks, so the pcg32 initstates are disjoint).
+    Array properties have shape ``[nrealisations, *shape]``, scalar properties ``[nrealisations]``.
+    """
+
+    _squeeze_realisation = False
+
+    def __init__(self, potential, interactions, shape, *, m=1.0, eta=0.0, mu=1.0, kappa=0.0,
+                 k1=0.0, k2=0.0, k_frame=1.0, dt=0.0, seed=0, distribution="random",
+                 parameters=(), offset=-100.0, nchunk=5000, minimisation=0, nrealisations=1,
+                 seed_stride=0, device=-1, kernel=0):
+        self._h = C.c_void_p()
+        self._par = _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
+                            k2, k_frame, dt, seed, distribution, parameters, offset, nchunk,
+                            nrealisations, seed_stride, device, kernel)
+        self._shape = tuple(int(i) for i in shape)
+        self._R = int(nrealisations)
+        self._nchunk = int(nchunk)
+        self._full_shape = (self._R,) + self._shape
+        self._user_shape = self._shape if self._squeeze_realisation else self._full_shape
+        self._kind = (potential, interactions, int(minimisation))
+        check(lib.fqsb_create(C.byref(self._par), C.byref(self._h)))
+        self._chunk = _Chunk(self)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.fqsb_destroy(h)
+            self._h = None
+
+    # ---- helpers
+    def _squeeze(self, arr):
+        return arr[0] if self._squeeze_realisation else arr
+
+    def _scalar(self, arr):
+        return arr[0].item() if self._squeeze_realisation else arr
+
+    def _get_array(self, name):
+        out = np.empty(self._full_shape, dtype=np.float64)
+        check(lib.fqsb_get(self._h, _capi.ARRAY[name], out.ctypes.data, out.size))
+        return self._squeeze(out)
+
+    def _set_array(self, fn, arg):
+        arg = np.ascontiguousarray(arg, dtype=np.float64)
+        if arg.shape != self._user_shape:
+            # detail.h:1278 FRICTIONQPOTSPRINGBLOCK_ASSERT(xt::has_shape(arg, m_u.shape()))
+            raise RuntimeError("assertion failed (xt::has_shape(arg, m_u.shape()))")
+        check(fn(self._h, arg.ctypes.data, arg.size))
+
+    def _get_scalars(self, fn, dtype=np.float64):
+        out = np.empty(self._R, dtype=dtype)
+        check(fn(self._h, out.ctypes.data))
+        return self._scalar(out)
+
+    def _set_scalars(self, fn, arg, dtype=np.float64):
+        arg = np.ascontiguousarray(np.broadcast_to(np.asarray(arg, dtype=dtype), (self._R,)))
+        check(fn(self._h, arg.ctypes.data))
+
+    # ---- deprecated names (main.cpp:49-63)
+    @property
+    def x(self):
+        raise RuntimeError("Deprecated, use 'u'")
+
+    @property
+    def x_frame(self):
+        raise RuntimeError("Deprecated, use 'u_frame'")
+
+    @property
+    def f_neighbours(self):
+        raise RuntimeError("Deprecated, use 'f_interactions'")
+
+    # ---- parameters (main.cpp:65-79)
+    chunk = property(lambda self: self._chunk, doc="Chunk of random numbers")
+    size = property(lambda self: int(np.prod(self._shape)), doc="Number of particles")
+    shape = property(lambda self: list(self._shape), doc="Shape of the system")
+    nrealisations = property(lambda self: self._R)
+    dt = property(lambda self: self._par.dt, doc="Time step (parameter)")
+    mu = property(lambda self: self._par.mu, doc="Curvature of each well (parameter)")
+    eta = property(lambda self: self._par.eta, doc="Damping coefficient (parameter)")
+    m = property(lambda self: self._par.m, doc="Mass of each particle (parameter)")
+    k_frame = property(lambda self: self._par.k_frame, doc="Loading frame stiffness (parameter)")
+
+    # ---- state (main.cpp:80-129)
+    u = property(lambda self: self._get_array("u"),
+                 lambda self, x: self._set_array(lib.fqsb_set_u, x), doc="Particle slip.")
+    v = property(lambda self: self._get_array("v"),
+                 lambda self, x: self._set_array(lib.fqsb_set_v, x), doc="Particle velocities.")
+    a = property(lambda self: self._get_array("a"),
+                 lambda self, x: self._set_array(lib.fqsb_set_a, x), doc="Particle accelerations.")
+    inc = property(lambda self: self._get_scalars(lib.fqsb_get_inc, np.int64),
+                   lambda self, x: self._set_scalars(lib.fqsb_set_inc, x, np.int64))
+    t = property(lambda self: self._get_scalars(lib.fqsb_get_t),
+                 lambda self, x: self._set_scalars(lib.fqsb_set_t, x))
+    u_frame = property(lambda self: self._get_scalars(lib.fqsb_get_u_frame),
+                       lambda self, x: self._set_scalars(lib.fqsb_set_u_frame, x))
+    f = property(lambda self: self._get_array("f"), doc="Residual forces")
+    f_potential = property(lambda self: self._get_array("f_potential"), doc="Elastic forces")
+    f_frame = property(lambda self: self._get_array("f_frame"), doc="Frame forces")
+    f_interactions = property(lambda self: self._get_array("f_interactions"))
+    f_damping = property(lambda self: self._get_array("f_damping"))
+    temperature = property(lambda self: self._get_scalars(lib.fqsb_temperature))
+    residual = property(lambda self: self._get_scalars(lib.fqsb_residual))
+    mean_f_frame = property(lambda self: self._get_scalars(lib.fqsb_mean_f_frame),
+                            doc="np.mean(f_frame) per realisation, reduced on the device")
+
+    @property
+    def quasistaticActivityFirst(self):
+        first = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_qs_activity(self._h, first.ctypes.data, None))
+        return self._scalar(first)
+
+    @property
+    def quasistaticActivityLast(self):
+        last = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_qs_activity(self._h, None, last.ctypes.data))
+        return self._scalar(last)
+
+    def refresh(self):
+        check(lib.fqsb_refresh(self._h))
+
+    def quench(self):
+        check(lib.fqsb_quench(self._h))
+
+    def maxUniformDisplacement(self, direction=1):
+        out = np.empty(self._R, dtype=np.float64)
+        check(lib.fqsb_max_uniform_displacement(self._h, int(direction), out.ctypes.data))
+        return self._scalar(out)
+
+    def trigger(self, p, eps, direction=1, realisation=0):
+        check(lib.fqsb_trigger(self._h, int(realisation), int(p), float(eps), int(direction)))
+
+    def advanceToFixedForce(self, f_frame, allow_plastic=False):
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(f_frame, dtype=np.float64),
+                                                 (self._R,)))
+        check(lib.fqsb_advance_to_fixed_force(self._h, f.ctypes.data, int(allow_plastic)))
+
+    # ---- athermal protocol (main.cpp:153-203)
+    def minimise(self, tol=1e-5, niter_tol=10, max_iter=int(1e9), time_activity=False,
+                 max_iter_is_error=True):
+        ret = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_minimise(self._h, float(tol), int(niter_tol), int(max_iter),
+                                int(time_activity), int(max_iter_is_error), ret.ctypes.data))
+        return self._scalar(ret)
+
+    def minimise_truncate(self, i_n, A_truncate=0, S_truncate=0, tol=1e-5, niter_tol=10,
+                          max_iter=int(1e9), time_activity=True, max_iter_is_error=True):
+        i_n = np.ascontiguousarray(i_n, dtype=np.int64)
+        if i_n.shape != self._user_shape:
+            raise RuntimeError("assertion failed (xt::has_shape(i_n, m_u.shape()))")
+        ret = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_minimise_truncate(
+            self._h, i_n.ctypes.data, int(A_truncate), int(S_truncate), float(tol),
+            int(niter_tol), int(max_iter), int(time_activity), int(max_iter_is_error),
+            ret.ctypes.data))
+        return self._scalar(ret)
+
+    def eventDrivenStep(self, eps, kick, direction=1):
+        out = np.empty(self._R, dtype=np.float64)
+        check(lib.fqsb_event_driven_step(self._h, float(eps), int(bool(kick)), int(direction),
+                                         out.ctypes.data))
+        return self._scalar(out)
+
+    def avalanche(self, i_n):
+        """(S, A) per realisation since ``i_n``: S = sum(i - i_n), A = #(i != i_n), reduced on
+        the device (what examples/Line1d_Cuspy_Laplace.py:61 computes on the host)."""
+        i_n = np.ascontiguousarray(i_n, dtype=np.int64)
+        S = np.empty(self._R, dtype=np.int64)
+        A = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_avalanche(self._h, i_n.ctypes.data, S.ctypes.data, A.ctypes.data))
+        return self._scalar(S), self._scalar(A)
+
+    # ---- dynamics (main.cpp:205-226)
+    def _no_dynamics(self):
+        if self._kind[2] == 1:  # Line1d.h:231-234
+            raise AttributeError("the no-passing system has no dynamics")
+
+    def timeStep(self):
+        self._no_dynamics()
+        check(lib.fqsb_time_steps(self._h, 1))
+
+    def timeSteps(self, n):
+        self._no_dynamics()
+        check(lib.fqsb_time_steps(self._h, int(n)))
+
+    def timeStepsUntilEvent(self, tol=1e-5, niter_tol=10, max_iter=int(1e9)):
+        self._no_dynamics()
+        ret = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_time_steps_until_event(self._h, float(tol), int(niter_tol), int(max_iter),
+                                              ret.ctypes.data))
+        return self._scalar(ret)
+
+    def flowSteps(self, n, v_frame):
+        self._no_dynamics()
+        check(lib.fqsb_flow_steps(self._h, int(n), float(v_frame)))
+
+    # ---- instrumentation
+    @property
+    def launch_count(self):
+        return int(lib.fqsb_launch_count(self._h))
+
+    @property
+    def step_count(self):
+        return int(lib.fqsb_step_count(self._h))
+
+    @property
+    def last_kernel(self):
+        return lib.fqsb_last_kernel(self._h).decode()
+
+    def set_stream(self, cuda_stream: int):
+        check(lib.fqsb_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def __repr__(self):
+        pot, inter, mini = self._kind
+        return (f"<frictionqpotspringblock_b200 {pot}/{inter}"
+                f"{'/Nopassing' if mini else ''} shape={list(self._shape)} "
+                f"nrealisations={self._R}>")
+
+
+class System(Ensemble):
+    """One realisation with the reference's exact (unbatched) Python surface."""
+
+    _squeeze_realisation = True

@@ -1,0 +1,1279 @@
+// fqsb_api.cu -- implementation of the C ABI declared in include/fqsb.h.
+// Host-side orchestration only: every number is produced by the kernels in fqsb_kernels.cuh.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/fqsb.h"
+#include "fqsb_host.h"
+#include "fqsb_aux_kernels.cuh"
+
+using namespace fqsb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(FQSB_ECUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what);
+}
+
+#define CU(x) \
+    do { \
+        cudaError_t e_ = (x); \
+        if (e_ != cudaSuccess) { \
+            return cuda_fail(e_, #x); \
+        } \
+    } while (0)
+
+#define TRY(x) \
+    do { \
+        int rc_ = (x); \
+        if (rc_ != FQSB_OK) { \
+            return rc_; \
+        } \
+    } while (0)
+
+// the reference's assertion text (config.h:19-24)
+#define ASSERT_MSG(expr) (std::string("fqsb: assertion failed (") + expr + ") \n\t")
+
+struct fqsb_system {
+    fqsb_params par;
+    Par P;
+    State S;
+    ForceArrays F;
+    cudaStream_t stream;
+    bool own_stream;
+    int device;
+    i64 N, R, n;
+    bool forces_valid;  // F holds the forces of the current state
+    bool forces_frozen; // F is kept as is (stale after trigger(), detail.h:1975-1976)
+    double* d_red;      // [R][tiles][8] partial sums
+    double* d_out;      // [R][4]
+    double* d_du;       // [R]
+    i64* d_in;          // [R*N] i_n scratch
+    void* d_scratch;    // generic staging
+    size_t scratch_bytes;
+    double* h_out;      // pinned [R][4]
+    Ctl* h_ctl;         // pinned [R]
+    int* h_err;         // pinned [2]
+    double* d_pref;
+    i64 launches, steps;
+    const char* last_kernel;
+    std::vector<void*> allocs;
+};
+
+static unsigned grid_for(i64 n)
+{
+    i64 g = (n + 255) / 256;
+    const i64 cap = 148 * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <class T>
+static int dev_alloc(fqsb_system* s, T** p, size_t count)
+{
+    void* q = nullptr;
+    CU(cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 1));
+    s->allocs.push_back(q);
+    *p = (T*)q;
+    return FQSB_OK;
+}
+
+static int scratch(fqsb_system* s, size_t bytes)
+{
+    if (bytes > s->scratch_bytes) {
+        if (s->d_scratch) {
+            CU(cudaStreamSynchronize(s->stream));
+            CU(cudaFree(s->d_scratch));
+            s->d_scratch = nullptr;
+            s->scratch_bytes = 0;
+        }
+        CU(cudaMalloc(&s->d_scratch, bytes));
+        s->scratch_bytes = bytes;
+    }
+    return FQSB_OK;
+}
+
+static int enter(fqsb_system* s)
+{
+    if (!s) {
+        return fail(FQSB_EASSERT, "null handle");
+    }
+    CU(cudaSetDevice(s->device));
+    return FQSB_OK;
+}
+
+static int check_flags(fqsb_system* s)
+{
+    CU(cudaMemcpyAsync(s->h_err, s->S.err, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->h_err[0] || s->h_err[1]) {
+        int e0 = s->h_err[0], e1 = s->h_err[1];
+        CU(cudaMemsetAsync(s->S.err, 0, 2 * sizeof(int), s->stream));
+        if (e1) {
+            return fail(FQSB_ENAN, "NaN entries found"); // detail.h:1568
+        }
+        if (e0) {
+            return fail(FQSB_EASSERT,
+                        "yield landscape exhausted below its first entry (lower the offset)");
+        }
+    }
+    return FQSB_OK;
+}
+
+static void invalidate_forces(fqsb_system* s)
+{
+    s->forces_valid = false;
+    s->forces_frozen = false;
+}
+
+static int ensure_forces(fqsb_system* s)
+{
+    if (!s->F.f) {
+        TRY(dev_alloc(s, &s->F.f, (size_t)s->n));
+        TRY(dev_alloc(s, &s->F.f_pot, (size_t)s->n));
+        TRY(dev_alloc(s, &s->F.f_int, (size_t)s->n));
+        TRY(dev_alloc(s, &s->F.f_frame, (size_t)s->n));
+        TRY(dev_alloc(s, &s->F.f_damp, (size_t)s->n));
+        s->forces_valid = false;
+        s->forces_frozen = false;
+    }
+    if (!s->forces_valid && !s->forces_frozen) {
+        k_forces<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, s->F, 15);
+        CU(cudaGetLastError());
+        s->launches++;
+        s->forces_valid = true;
+    }
+    return FQSB_OK;
+}
+
+// recompute one component inside a frozen (possibly stale) force set
+static int frozen_update(fqsb_system* s, int mask)
+{
+    k_forces<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, s->F, mask);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FQSB_OK;
+}
+
+static int reduce(fqsb_system* s, int what, int direction, const i64* i_n_dev)
+{
+    dim3 grid((unsigned)s->S.tiles, (unsigned)s->R);
+    k_reduce<<<grid, 256, 0, s->stream>>>(s->P, s->S, s->F, what, direction, i_n_dev, s->d_red);
+    k_reduce_final<<<(unsigned)s->R, 32, 0, s->stream>>>(s->d_red, s->S.tiles, s->d_out);
+    CU(cudaGetLastError());
+    s->launches += 2;
+    return FQSB_OK;
+}
+
+static int reduce_to_host(fqsb_system* s, int what, int direction, const i64* i_n_dev)
+{
+    TRY(reduce(s, what, direction, i_n_dev));
+    CU(cudaMemcpyAsync(s->h_out, s->d_out, (size_t)s->R * 4 * sizeof(double),
+                       cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+static int align(fqsb_system* s, const double* du_dev)
+{
+    k_align<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, du_dev);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FQSB_OK;
+}
+
+static int pull_ctl(fqsb_system* s)
+{
+    CU(cudaMemcpyAsync(s->h_ctl, s->S.ctl, (size_t)s->R * sizeof(Ctl), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+static int push_ctl(fqsb_system* s)
+{
+    CU(cudaMemcpyAsync(s->S.ctl, s->h_ctl, (size_t)s->R * sizeof(Ctl), cudaMemcpyHostToDevice,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* fqsb_last_error(void) { return g_err.c_str(); }
+int fqsb_abi_version(void) { return FQSB_ABI_VERSION; }
+const char* fqsb_version(void) { return "0.1.0"; }
+
+int fqsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void* fqsb_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void fqsb_host_free(void* p)
+{
+    if (p) {
+        cudaFreeHost(p);
+    }
+}
+
+int fqsb_create(const fqsb_params* par, fqsb_system** out)
+{
+    if (!par || !out) {
+        return fail(FQSB_EASSERT, "null argument");
+    }
+    *out = nullptr;
+    if (par->rank != 1 && par->rank != 2) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("rank == 1 || rank == 2"));
+    }
+    if (par->shape[0] < 1 || (par->rank == 2 && par->shape[1] < 1)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("shape > 0"));
+    }
+    switch (par->distribution) {
+    case FQSB_DIST_RANDOM:
+    case FQSB_DIST_DELTA:
+    case FQSB_DIST_EXPONENTIAL:
+    case FQSB_DIST_POWER:
+    case FQSB_DIST_PARETO:
+    case FQSB_DIST_WEIBULL:
+        break;
+    case FQSB_DIST_GAMMA:
+    case FQSB_DIST_NORMAL:
+        return fail(FQSB_EUNSUPPORTED,
+                    "distribution not supported on the device (needs boost special functions)");
+    default:
+        return fail(FQSB_EASSERT, "Unknown distribution: " + std::to_string(par->distribution));
+    }
+    if (!combination_supported(par->potential, par->interactions)) {
+        return fail(FQSB_EUNSUPPORTED, "potential x interactions combination not available");
+    }
+    const bool two_d = par->interactions == FQSB_INT_LAPLACE2D ||
+                       par->interactions == FQSB_INT_QUARTICGRADIENT2D;
+    if (two_d != (par->rank == 2)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("rank matches interactions"));
+    }
+    if (par->minimisation == FQSB_MIN_OVERDAMPED &&
+        !(par->potential == FQSB_POT_CUSPY && (par->interactions == FQSB_INT_LAPLACE1D ||
+                                               par->interactions == FQSB_INT_LAPLACE2D))) {
+        return fail(FQSB_EUNSUPPORTED, "Minimisation not implementated"); // detail.h:1692,1695
+    }
+    int ndev = fqsb_device_count();
+    if (ndev < 1) {
+        return fail(FQSB_ECUDA, "no CUDA device: this library has no CPU fallback");
+    }
+    int device = par->device;
+    if (device < 0) {
+        CU(cudaGetDevice(&device));
+    }
+    if (device >= ndev) {
+        return fail(FQSB_ECUDA, "CUDA device ordinal out of range");
+    }
+    CU(cudaSetDevice(device));
+
+    fqsb_system* s = new fqsb_system();
+    s->par = *par;
+    s->device = device;
+    s->own_stream = true;
+    s->stream = nullptr;
+    s->forces_valid = false;
+    s->forces_frozen = false;
+    s->d_scratch = nullptr;
+    s->scratch_bytes = 0;
+    s->launches = 0;
+    s->steps = 0;
+    s->last_kernel = "";
+    memset(&s->F, 0, sizeof s->F);
+    memset(&s->S, 0, sizeof s->S);
+
+    Par& P = s->P;
+    memset(&P, 0, sizeof P);
+    P.pot = par->potential;
+    P.inter = par->interactions;
+    P.rank = par->rank;
+    P.dist = par->distribution;
+    P.rows = (int)par->shape[0];
+    P.cols = par->rank == 2 ? (int)par->shape[1] : 1;
+    P.N = (i64)P.rows * P.cols;
+    P.R = par->nrealisations > 0 ? par->nrealisations : 1;
+    P.consumes = par->distribution != FQSB_DIST_DELTA;
+    P.m = par->m;
+    P.inv_m = 1.0 / par->m; // detail.h:1110
+    P.eta = par->eta;
+    P.mu = par->mu;
+    P.kappa = par->kappa;
+    P.k1 = par->k1;
+    P.k2 = par->k2;
+    P.k_frame = par->k_frame;
+    P.dt = par->dt;
+    {
+        // prrng defaults for omitted parameters
+        double def[4] = {1.0, 0.0, 0.0, 0.0};
+        if (par->distribution == FQSB_DIST_PARETO || par->distribution == FQSB_DIST_WEIBULL) {
+            def[1] = 1.0;
+        }
+        for (int k = 0; k < 4; ++k) {
+            P.dpar[k] = k < par->nparameters ? par->parameters[k] : def[k];
+        }
+    }
+    P.offset = par->offset;
+    P.seed = par->seed;
+    P.seed_stride = par->seed_stride > 0 ? (u64)par->seed_stride : (u64)P.N;
+    s->N = P.N;
+    s->R = P.R;
+    s->n = P.N * P.R;
+    s->par.nrealisations = P.R;
+    s->par.seed_stride = (int64_t)P.seed_stride;
+    s->par.device = device;
+    if (P.N >= (i64)1 << 31 || P.R >= 65535) {
+        delete s;
+        return fail(FQSB_EASSERT, ASSERT_MSG("size < 2^31 && nrealisations < 65535"));
+    }
+
+    int rc = FQSB_OK;
+    auto build = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        State& S = s->S;
+        const size_t n = (size_t)s->n;
+        TRY(dev_alloc(s, &S.u, n));
+        TRY(dev_alloc(s, &S.v, n));
+        TRY(dev_alloc(s, &S.a, n));
+        TRY(dev_alloc(s, &S.yl, n));
+        TRY(dev_alloc(s, &S.yr, n));
+        TRY(dev_alloc(s, &S.idx, n));
+        TRY(dev_alloc(s, &S.rng, n));
+        TRY(dev_alloc(s, &S.u_frame, (size_t)s->R));
+        TRY(dev_alloc(s, &S.ctl, (size_t)s->R));
+        TRY(dev_alloc(s, &S.err, 2));
+        S.tiles = (int)grid_for(s->N);
+        TRY(dev_alloc(s, &s->d_red, (size_t)s->R * S.tiles * FQSB_NPART));
+        S.part = s->d_red;
+        TRY(dev_alloc(s, &s->d_out, (size_t)s->R * 4));
+        TRY(dev_alloc(s, &s->d_du, (size_t)s->R));
+        s->d_in = nullptr;
+        s->d_pref = nullptr;
+        CU(cudaHostAlloc((void**)&s->h_out, (size_t)s->R * 4 * sizeof(double), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&s->h_ctl, (size_t)s->R * sizeof(Ctl), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&s->h_err, 2 * sizeof(int), cudaHostAllocDefault));
+        CU(cudaMemsetAsync(S.err, 0, 2 * sizeof(int), s->stream));
+        CU(cudaMemsetAsync(S.u_frame, 0, (size_t)s->R * sizeof(double), s->stream));
+        CU(cudaMemsetAsync(S.ctl, 0, (size_t)s->R * sizeof(Ctl), s->stream));
+        if (P.inter == INT_LONGRANGE1D) { // detail.h:829-844 (host pow, as the reference)
+            std::vector<double> pref((size_t)P.N, 0.0);
+            for (i64 d = 1; d < P.N; ++d) {
+                pref[(size_t)d] = P.k1 / std::pow((double)d, P.k2 + 1.0);
+            }
+            TRY(dev_alloc(s, &s->d_pref, (size_t)P.N));
+            CU(cudaMemcpyAsync(s->d_pref, pref.data(), (size_t)P.N * sizeof(double),
+                               cudaMemcpyHostToDevice, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            S.pref = s->d_pref;
+        }
+        k_init<<<grid_for(s->n), 256, 0, s->stream>>>(P, S);
+        CU(cudaGetLastError());
+        s->launches++;
+        return check_flags(s);
+    };
+    rc = build();
+    if (rc != FQSB_OK) {
+        std::string keep = g_err;
+        fqsb_destroy(s);
+        if (rc == FQSB_EASSERT && keep.find("yield landscape") != std::string::npos) {
+            keep = "u = 0 lies below the first yield position: lower the offset";
+        }
+        g_err = keep;
+        return rc;
+    }
+    *out = s;
+    return FQSB_OK;
+}
+
+void fqsb_destroy(fqsb_system* s)
+{
+    if (!s) {
+        return;
+    }
+    cudaSetDevice(s->device);
+    if (s->stream) {
+        cudaStreamSynchronize(s->stream);
+    }
+    for (void* p : s->allocs) {
+        cudaFree(p);
+    }
+    if (s->d_scratch) {
+        cudaFree(s->d_scratch);
+    }
+    if (s->h_out) {
+        cudaFreeHost(s->h_out);
+    }
+    if (s->h_ctl) {
+        cudaFreeHost(s->h_ctl);
+    }
+    if (s->h_err) {
+        cudaFreeHost(s->h_err);
+    }
+    if (s->own_stream && s->stream) {
+        cudaStreamDestroy(s->stream);
+    }
+    cudaGetLastError();
+    delete s;
+}
+
+int fqsb_get_params(const fqsb_system* s, fqsb_params* out)
+{
+    if (!s || !out) {
+        return fail(FQSB_EASSERT, "null argument");
+    }
+    *out = s->par;
+    return FQSB_OK;
+}
+
+int64_t fqsb_size(const fqsb_system* s) { return s ? s->N : 0; }
+int64_t fqsb_nrealisations(const fqsb_system* s) { return s ? s->R : 0; }
+
+int fqsb_set_stream(fqsb_system* s, void* cuda_stream)
+{
+    TRY(enter(s));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) {
+        CU(cudaStreamDestroy(s->stream));
+    }
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return FQSB_OK;
+}
+
+void* fqsb_get_stream(const fqsb_system* s) { return s ? (void*)s->stream : nullptr; }
+int64_t fqsb_launch_count(const fqsb_system* s) { return s ? s->launches : 0; }
+int64_t fqsb_step_count(const fqsb_system* s) { return s ? s->steps : 0; }
+const char* fqsb_last_kernel(const fqsb_system* s) { return s ? s->last_kernel : ""; }
+
+// ---- state in ---------------------------------------------------------------------------------
+static int upload(fqsb_system* s, double* dst, const double* src, int64_t n)
+{
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(arg, m_u.shape())")); // detail.h:1278
+    }
+    CU(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_set_u(fqsb_system* s, const double* u, int64_t n)
+{
+    TRY(enter(s));
+    TRY(upload(s, s->S.u, u, n));
+    TRY(align(s, nullptr)); // updated_u(), detail.h:1280
+    invalidate_forces(s);
+    return check_flags(s);
+}
+
+int fqsb_set_v(fqsb_system* s, const double* v, int64_t n)
+{
+    TRY(enter(s));
+    TRY(upload(s, s->S.v, v, n));
+    if (s->forces_frozen) {
+        TRY(frozen_update(s, 8)); // updated_v(), detail.h:1294
+    }
+    else {
+        s->forces_valid = false;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_set_a(fqsb_system* s, const double* a, int64_t n)
+{
+    TRY(enter(s));
+    TRY(upload(s, s->S.a, a, n));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_set_u_frame(fqsb_system* s, const double* u_frame)
+{
+    TRY(enter(s));
+    CU(cudaMemcpyAsync(s->S.u_frame, u_frame, (size_t)s->R * sizeof(double),
+                       cudaMemcpyHostToDevice, s->stream));
+    if (s->forces_frozen) {
+        TRY(frozen_update(s, 4)); // computeForceFrame + computeForce, detail.h:1256-1257
+    }
+    else {
+        s->forces_valid = false;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_set_inc(fqsb_system* s, const int64_t* inc)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) { // detail.h:1241-1247
+        s->h_ctl[r].inc = inc[r];
+        s->h_ctl[r].qs_first = inc[r];
+        s->h_ctl[r].qs_last = inc[r];
+    }
+    return push_ctl(s);
+}
+
+int fqsb_set_t(fqsb_system* s, const double* t)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) { // detail.h:1231-1235 (quirk Q5: qs_* untouched)
+        i64 inc = (i64)std::round(t[r] / s->P.dt);
+        double tt = (double)inc * s->P.dt;
+        if (!(std::fabs(tt - t[r]) <= 1e-8 + 1e-5 * std::fabs(t[r]))) {
+            return fail(FQSB_EASSERT, ASSERT_MSG("xt::allclose(this->t(), arg)"));
+        }
+        s->h_ctl[r].inc = inc;
+    }
+    return push_ctl(s);
+}
+
+int fqsb_refresh(fqsb_system* s)
+{
+    TRY(enter(s));
+    TRY(align(s, nullptr));
+    invalidate_forces(s);
+    return check_flags(s);
+}
+
+int fqsb_quench(fqsb_system* s)
+{
+    TRY(enter(s));
+    k_zero_va<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S);
+    CU(cudaGetLastError());
+    s->launches++;
+    if (s->forces_frozen) {
+        TRY(frozen_update(s, 8));
+    }
+    else {
+        s->forces_valid = false;
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+// ---- state out --------------------------------------------------------------------------------
+static int array_ptr(fqsb_system* s, int which, const double** p)
+{
+    switch (which) {
+    case FQSB_U:
+        *p = s->S.u;
+        return FQSB_OK;
+    case FQSB_V:
+        *p = s->S.v;
+        return FQSB_OK;
+    case FQSB_A:
+        *p = s->S.a;
+        return FQSB_OK;
+    default:
+        break;
+    }
+    if (which < FQSB_F || which > FQSB_F_DAMPING) {
+        return fail(FQSB_EASSERT, "unknown array id");
+    }
+    TRY(ensure_forces(s));
+    const double* f[] = {s->F.f, s->F.f_pot, s->F.f_frame, s->F.f_int, s->F.f_damp};
+    *p = f[which - FQSB_F];
+    return FQSB_OK;
+}
+
+int fqsb_get(fqsb_system* s, int which, double* out, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the output buffer"));
+    }
+    const double* src = nullptr;
+    TRY(array_ptr(s, which, &src));
+    CU(cudaMemcpyAsync(out, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_get_device(fqsb_system* s, int which, const double** out_device)
+{
+    TRY(enter(s));
+    TRY(array_ptr(s, which, out_device));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_get_u_frame(fqsb_system* s, double* out)
+{
+    TRY(enter(s));
+    CU(cudaMemcpyAsync(out, s->S.u_frame, (size_t)s->R * sizeof(double), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_get_inc(fqsb_system* s, int64_t* out)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) {
+        out[r] = s->h_ctl[r].inc;
+    }
+    return FQSB_OK;
+}
+
+int fqsb_get_t(fqsb_system* s, double* out)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) {
+        out[r] = (double)s->h_ctl[r].inc * s->P.dt; // detail.h:1479
+    }
+    return FQSB_OK;
+}
+
+int fqsb_qs_activity(fqsb_system* s, int64_t* first, int64_t* last)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) {
+        if (first) {
+            first[r] = s->h_ctl[r].qs_first;
+        }
+        if (last) {
+            last[r] = s->h_ctl[r].qs_last;
+        }
+    }
+    return FQSB_OK;
+}
+
+int fqsb_residual(fqsb_system* s, double* out)
+{
+    TRY(enter(s));
+    // frozen forces are reduced as stored; otherwise they are derived on the fly
+    TRY(reduce_to_host(s, s->forces_frozen ? 0 : 1, 1, nullptr));
+    for (i64 r = 0; r < s->R; ++r) { // detail.h:1512-1520
+        double r_fres = std::sqrt(s->h_out[4 * r]);
+        double r_fext = std::sqrt(s->h_out[4 * r + 1]);
+        out[r] = r_fext != 0.0 ? r_fres / r_fext : r_fres;
+    }
+    return FQSB_OK;
+}
+
+int fqsb_temperature(fqsb_system* s, double* out)
+{
+    TRY(enter(s));
+    TRY(reduce_to_host(s, 2, 1, nullptr));
+    for (i64 r = 0; r < s->R; ++r) { // detail.h:1502
+        out[r] = 0.5 * s->P.m * s->h_out[4 * r] / (double)s->N;
+    }
+    return FQSB_OK;
+}
+
+int fqsb_mean_f_frame(fqsb_system* s, double* out)
+{
+    TRY(enter(s));
+    TRY(reduce_to_host(s, 2, 1, nullptr));
+    for (i64 r = 0; r < s->R; ++r) {
+        out[r] = s->h_out[4 * r + 1] / (double)s->N;
+    }
+    return FQSB_OK;
+}
+
+// ---- dynamics ---------------------------------------------------------------------------------
+__global__ void k_ctl_begin(const Par P, const State S, int track_user, int overdamped,
+                            const double* red_out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.R) {
+        return;
+    }
+    Ctl& c = S.ctl[r];
+    c.status = ST_RUNNING;
+    c.init = 1;
+    c.steps = 0;
+    c.S = track_user ? (i64)red_out[4 * r + 2] : 0;
+    c.A = track_user ? (i64)red_out[4 * r + 1] : 0;
+    c.s_n = 0;
+    c.count = 0u;
+    c.flip = 0;
+    c.residual = 0.0;
+    for (int k = 0; k < FQSB_RING; ++k) {
+        c.ring[k] = __longlong_as_double(0x7ff0000000000000LL); // +inf (App. A.4)
+    }
+    if (overdamped) { // detail.h:1704-1705
+        c.qs_first = c.inc;
+        c.qs_last = c.inc;
+    }
+}
+
+static bool use_resident(const fqsb_system* s, ResidentCfg* cfg)
+{
+    *cfg = resident_cfg(s->N);
+    if (s->par.kernel == 2 || cfg->B == 0) {
+        return false;
+    }
+    return resident_smem(s->P, *cfg) <= 227 * 1024;
+}
+
+static int ensure_stream_buffers(fqsb_system* s)
+{
+    if (!s->S.u2) {
+        TRY(dev_alloc(s, &s->S.u2, (size_t)s->n));
+        if (s->par.minimisation != FQSB_MIN_OVERDAMPED) {
+            TRY(dev_alloc(s, &s->S.v2, (size_t)s->n));
+            TRY(dev_alloc(s, &s->S.a2, (size_t)s->n));
+        }
+    }
+    return FQSB_OK;
+}
+
+// Runs one dynamics call to completion. On return h_ctl holds the final control blocks.
+static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
+{
+    if (A.mode != MODE_FIXED && (A.niter_tol < 1 || A.niter_tol > FQSB_RING)) {
+        return fail(FQSB_EUNSUPPORTED, "niter_tol must be in [1, 32]");
+    }
+    const unsigned rg = (unsigned)((s->R + 127) / 128);
+    k_ctl_begin<<<rg, 128, 0, s->stream>>>(s->P, s->S, track_user ? 1 : 0, overdamped ? 1 : 0,
+                                           s->d_out);
+    CU(cudaGetLastError());
+    s->launches++;
+    invalidate_forces(s);
+    if (A.max_steps <= 0) {
+        TRY(pull_ctl(s));
+        for (i64 r = 0; r < s->R; ++r) {
+            s->h_ctl[r].status = ST_EXHAUSTED;
+        }
+        return FQSB_OK;
+    }
+
+    ResidentCfg cfg;
+    if (use_resident(s, &cfg)) {
+        s->last_kernel = overdamped ? "resident_nopassing" : "resident";
+        const i64 chunk = (i64)1 << 20;
+        for (;;) {
+            A.launch_steps = A.max_steps < chunk ? A.max_steps : chunk;
+            cudaError_t e = overdamped ? launch_resident_nopassing(cfg, s->P, s->S, A, s->stream)
+                                       : launch_resident(cfg, s->P, s->S, A, s->stream);
+            if (e != cudaSuccess) {
+                return cuda_fail(e, "resident kernel launch");
+            }
+            s->launches++;
+            TRY(pull_ctl(s));
+            bool running = false;
+            for (i64 r = 0; r < s->R; ++r) {
+                running |= s->h_ctl[r].status == ST_RUNNING;
+            }
+            if (!running) {
+                break;
+            }
+        }
+    }
+    else {
+        if (s->par.kernel == 1) {
+            return fail(FQSB_EUNSUPPORTED, "system too large for the resident kernel");
+        }
+        TRY(ensure_stream_buffers(s));
+        s->last_kernel = overdamped ? "stream_nopassing" : "stream";
+        i64 remaining = A.max_steps; // upper bound on launches still useful
+        i64 batch = 16;
+        for (;;) {
+            i64 nb = A.mode == MODE_FIXED ? (remaining < 2048 ? remaining : 2048)
+                                          : (remaining < batch ? remaining : batch);
+            for (i64 b = 0; b < nb; ++b) {
+                cudaError_t e = overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream)
+                                           : launch_stream_step(s->P, s->S, A, s->stream);
+                if (e != cudaSuccess) {
+                    return cuda_fail(e, "stream kernel launch");
+                }
+            }
+            s->launches += overdamped ? 2 * nb : nb;
+            remaining -= nb;
+            TRY(pull_ctl(s));
+            bool running = false;
+            for (i64 r = 0; r < s->R; ++r) {
+                running |= s->h_ctl[r].status == ST_RUNNING;
+            }
+            if (!running || remaining <= 0) {
+                break;
+            }
+            if (batch < 256) {
+                batch *= 2;
+            }
+        }
+        dim3 grid((unsigned)s->S.tiles, (unsigned)s->R);
+        k_stream_settle<<<grid, 256, 0, s->stream>>>(s->P, s->S, overdamped ? 0 : 1);
+        k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
+        CU(cudaGetLastError());
+        s->launches += 2;
+    }
+    for (i64 r = 0; r < s->R; ++r) {
+        s->steps += s->h_ctl[r].steps;
+    }
+    TRY(check_flags(s));
+    for (i64 r = 0; r < s->R; ++r) {
+        if (s->h_ctl[r].status == ST_NAN) {
+            return fail(FQSB_ENAN, "NaN entries found");
+        }
+    }
+    return FQSB_OK;
+}
+
+static void fill_ret(const fqsb_system* s, int64_t* ret)
+{
+    if (!ret) {
+        return;
+    }
+    for (i64 r = 0; r < s->R; ++r) {
+        const Ctl& c = s->h_ctl[r];
+        switch (c.status) {
+        case ST_CONVERGED:
+            ret[r] = 0;
+            break;
+        case ST_EVENT:
+        case ST_TRUNCATED:
+            ret[r] = c.steps;
+            break;
+        default:
+            ret[r] = c.steps + 1; // detail.h:1621,1791 (quirk Q4)
+            break;
+        }
+    }
+}
+
+static int require_dynamic(const fqsb_system* s)
+{
+    if (s->par.minimisation == FQSB_MIN_OVERDAMPED) {
+        // Line1d.h:231-234: the no-passing system hides the dynamics
+        return fail(FQSB_EUNSUPPORTED, "no dynamics available for an overdamped system");
+    }
+    return FQSB_OK;
+}
+
+static RunArgs make_args(int mode, i64 max_steps)
+{
+    RunArgs A;
+    memset(&A, 0, sizeof A);
+    A.mode = mode;
+    A.max_steps = max_steps;
+    A.niter_tol = 1;
+    return A;
+}
+
+int fqsb_time_steps(fqsb_system* s, int64_t n)
+{
+    TRY(enter(s));
+    TRY(require_dynamic(s));
+    if (n < 0) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("n + 1 < std::numeric_limits<long>::max()"));
+    }
+    return run(s, make_args(MODE_FIXED, n), false, false);
+}
+
+int fqsb_flow_steps(fqsb_system* s, int64_t n, double v_frame)
+{
+    TRY(enter(s));
+    TRY(require_dynamic(s));
+    if (n < 0) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("n + 1 < std::numeric_limits<long>::max()"));
+    }
+    RunArgs A = make_args(MODE_FIXED, n);
+    A.flow = 1;
+    A.v_frame = v_frame;
+    return run(s, A, false, false);
+}
+
+int fqsb_time_steps_until_event(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_iter,
+                                int64_t* ret)
+{
+    TRY(enter(s));
+    TRY(require_dynamic(s));
+    if (!(tol < 1.0)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("tol < 1.0")); // detail.h:1597
+    }
+    RunArgs A = make_args(MODE_UNTIL_EVENT, max_iter);
+    A.tol = tol;
+    A.tol2 = tol * tol;
+    A.niter_tol = (int)niter_tol;
+    TRY(run(s, A, false, false));
+    fill_ret(s, ret);
+    return FQSB_OK;
+}
+
+static int snapshot_index(fqsb_system* s)
+{
+    if (!s->d_in) {
+        TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
+    }
+    CU(cudaMemcpyAsync(s->d_in, s->S.idx, (size_t)s->n * sizeof(i64), cudaMemcpyDeviceToDevice,
+                       s->stream));
+    return FQSB_OK;
+}
+
+static int no_convergence(const fqsb_system* s, int max_iter_is_error)
+{
+    if (!max_iter_is_error) {
+        return FQSB_OK;
+    }
+    for (i64 r = 0; r < s->R; ++r) {
+        if (s->h_ctl[r].status == ST_EXHAUSTED) {
+            return fail(FQSB_ENOCONV, "No convergence found"); // detail.h:1788,1889
+        }
+    }
+    return FQSB_OK;
+}
+
+int fqsb_minimise(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_iter,
+                  int time_activity, int max_iter_is_error, int64_t* ret)
+{
+    TRY(enter(s));
+    if (!(tol < 1.0)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("tol < 1.0")); // detail.h:1684
+    }
+    const bool overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
+    if (overdamped && time_activity) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("!time_activity")); // detail.h:1696
+    }
+    RunArgs A = make_args(MODE_MINIMISE, max_iter);
+    A.tol = tol;
+    A.tol2 = tol * tol;
+    A.niter_tol = (int)niter_tol;
+    if (time_activity) {
+        TRY(snapshot_index(s)); // detail.h:1760-1762
+        A.track = 1;
+        A.i_n = s->d_in;
+    }
+    TRY(run(s, A, overdamped, false));
+    fill_ret(s, ret);
+    return no_convergence(s, max_iter_is_error);
+}
+
+int fqsb_minimise_truncate(fqsb_system* s, const int64_t* i_n, int64_t A_truncate,
+                           int64_t S_truncate, double tol, int64_t niter_tol, int64_t max_iter,
+                           int time_activity, int max_iter_is_error, int64_t* ret)
+{
+    TRY(enter(s));
+    TRY(require_dynamic(s));
+    if (!(tol < 1.0)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("tol < 1.0")); // detail.h:1844
+    }
+    if (!time_activity) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("time_activity")); // detail.h:1847
+    }
+    if (!s->d_in) {
+        TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
+    }
+    CU(cudaMemcpyAsync(s->d_in, i_n, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
+                       s->stream));
+    TRY(reduce(s, 4, 1, s->d_in)); // initial S, A against the caller's i_n
+    RunArgs A = make_args(MODE_TRUNCATE, max_iter);
+    A.tol = tol;
+    A.tol2 = tol * tol;
+    A.niter_tol = (int)niter_tol;
+    A.track = 1;
+    A.i_n = s->d_in;
+    A.A_truncate = A_truncate;
+    A.S_truncate = S_truncate;
+    TRY(run(s, A, false, true));
+    fill_ret(s, ret);
+    return no_convergence(s, max_iter_is_error);
+}
+
+// ---- event-driven protocol --------------------------------------------------------------------
+int fqsb_max_uniform_displacement(fqsb_system* s, int direction, double* out)
+{
+    TRY(enter(s));
+    if (direction != 1 && direction != -1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("direction == 1 || direction == -1"));
+    }
+    if (s->par.potential == FQSB_POT_SMOOTH) {
+        return fail(FQSB_EUNSUPPORTED, "Operation not possible."); // detail.h:420
+    }
+    TRY(align(s, nullptr)); // m_chunk->align(u), detail.h:180,286
+    TRY(reduce_to_host(s, 3, direction, nullptr));
+    for (i64 r = 0; r < s->R; ++r) {
+        out[r] = s->h_out[4 * r + 1] > 0.0 ? 0.0 : s->h_out[4 * r + 3];
+    }
+    return check_flags(s);
+}
+
+// eventDrivenStep (detail.h:1933-1960) + advanceUniformly(du, false) (detail.h:2027-2050) for
+// every realisation: du[r] particle shift, u_frame[r] += du * (k_frame + mu) / k_frame
+__global__ void k_event_prepare(const Par P, const State S, double eps, int kick, int direction,
+                                const double* red_out, double* du, double* ret)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.R) {
+        return;
+    }
+    double dup;
+    if (!kick) {
+        double d = red_out[4 * r + 1] > 0.0 ? 0.0 : red_out[4 * r + 3];
+        if (d < 0.5 * eps) {
+            du[r] = 0.0;
+            ret[r] = 0.0;
+            return;
+        }
+        dup = direction > 0 ? d - 0.5 * eps : 0.5 * eps - d;
+    }
+    else {
+        dup = direction > 0 ? eps : -eps;
+    }
+    double duf = dup * (P.k_frame + P.mu) / P.k_frame;
+    du[r] = dup;
+    S.u_frame[r] += duf;
+    ret[r] = duf;
+}
+
+static int advance(fqsb_system* s)
+{
+    // u += du[r]; updated_u()
+    TRY(align(s, s->d_du));
+    invalidate_forces(s);
+    return FQSB_OK;
+}
+
+int fqsb_event_driven_step(fqsb_system* s, double eps, int kick, int direction, double* du_frame)
+{
+    TRY(enter(s));
+    if (direction != 1 && direction != -1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("direction == 1 || direction == -1"));
+    }
+    if (!kick) {
+        if (s->par.potential == FQSB_POT_SMOOTH) {
+            return fail(FQSB_EUNSUPPORTED, "Operation not possible.");
+        }
+        TRY(align(s, nullptr));
+        TRY(reduce(s, 3, direction, nullptr));
+    }
+    const unsigned rg = (unsigned)((s->R + 127) / 128);
+    TRY(scratch(s, (size_t)s->R * sizeof(double)));
+    double* d_ret = (double*)s->d_scratch;
+    k_event_prepare<<<rg, 128, 0, s->stream>>>(s->P, s->S, eps, kick, direction, s->d_out,
+                                               s->d_du, d_ret);
+    CU(cudaGetLastError());
+    s->launches++;
+    TRY(advance(s));
+    CU(cudaMemcpyAsync(s->h_out, d_ret, (size_t)s->R * sizeof(double), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (du_frame) {
+        memcpy(du_frame, s->h_out, (size_t)s->R * sizeof(double));
+    }
+    return check_flags(s);
+}
+
+int fqsb_trigger(fqsb_system* s, int64_t r, int64_t p, double eps, int direction)
+{
+    TRY(enter(s));
+    if (r < 0 || r >= s->R || p < 0 || p >= s->N) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("(size_type)p < m_N")); // detail.h:1974
+    }
+    // quirk Q1 (detail.h:1975-1976): u changes, forces and (for non-Cuspy) the well do not
+    TRY(ensure_forces(s));
+    if (s->par.potential == FQSB_POT_CUSPY) {
+        TRY(align(s, nullptr)); // Cuspy::trigger aligns first, detail.h:197
+    }
+    const i64 g = r * s->N + p;
+    double y = 0.0;
+    CU(cudaMemcpyAsync(&y, (direction > 0 ? s->S.yr : s->S.yl) + g, sizeof(double),
+                       cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    double u = direction > 0 ? y + 0.5 * eps : y - 0.5 * eps; // detail.h:199-204
+    CU(cudaMemcpyAsync(s->S.u + g, &u, sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->forces_frozen = true;
+    return check_flags(s);
+}
+
+__global__ void k_fixed_force_prepare(const Par P, const State S, const double* target,
+                                      const double* red_out, double* du)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.R) {
+        return;
+    }
+    double mean = red_out[4 * r + 1] / (double)P.N;
+    double dup = (target[r] - mean) / P.mu; // detail.h:1991 (quirk Q10: divides by mu)
+    du[r] = dup;
+    S.u_frame[r] += dup * (P.k_frame + P.mu) / P.k_frame;
+}
+
+int fqsb_advance_to_fixed_force(fqsb_system* s, const double* f_frame, int allow_plastic)
+{
+    TRY(enter(s));
+    TRY(snapshot_index(s)); // detail.h:1990
+    TRY(reduce(s, 2, 1, nullptr));
+    TRY(scratch(s, (size_t)s->R * sizeof(double)));
+    CU(cudaMemcpyAsync(s->d_scratch, f_frame, (size_t)s->R * sizeof(double),
+                       cudaMemcpyHostToDevice, s->stream));
+    const unsigned rg = (unsigned)((s->R + 127) / 128);
+    k_fixed_force_prepare<<<rg, 128, 0, s->stream>>>(s->P, s->S, (const double*)s->d_scratch,
+                                                     s->d_out, s->d_du);
+    CU(cudaGetLastError());
+    s->launches++;
+    TRY(advance(s));
+    TRY(reduce_to_host(s, 4, 1, s->d_in));
+    TRY(check_flags(s));
+    if (!allow_plastic) {
+        for (i64 r = 0; r < s->R; ++r) {
+            if (s->h_out[4 * r + 1] != 0.0) {
+                return fail(FQSB_EASSERT,
+                            ASSERT_MSG("allow_plastic || xt::all(xt::equal(m_chunk->index_at_align(), i_n))"));
+            }
+        }
+    }
+    return FQSB_OK;
+}
+
+// ---- yield landscape ----------------------------------------------------------------------------
+int fqsb_chunk_index_at_align(fqsb_system* s, int64_t* out, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the output buffer"));
+    }
+    CU(cudaMemcpyAsync(out, s->S.idx, (size_t)n * sizeof(i64), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_chunk_left_of_align(fqsb_system* s, double* out, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the output buffer"));
+    }
+    CU(cudaMemcpyAsync(out, s->S.yl, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_chunk_right_of_align(fqsb_system* s, double* out, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the output buffer"));
+    }
+    CU(cudaMemcpyAsync(out, s->S.yr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_chunk_data(fqsb_system* s, const int64_t* first, int64_t nyield, double* out)
+{
+    TRY(enter(s));
+    if (nyield < 1 || nyield > (1 << 24)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("0 < nyield"));
+    }
+    for (i64 g = 0; g < s->n; ++g) {
+        if (first[g] < 0) {
+            return fail(FQSB_EASSERT, ASSERT_MSG("first >= 0"));
+        }
+    }
+    const size_t nb_first = (size_t)s->n * sizeof(i64);
+    const size_t nb_out = (size_t)s->n * (size_t)nyield * sizeof(double);
+    TRY(scratch(s, nb_first + nb_out));
+    i64* d_first = (i64*)s->d_scratch;
+    double* d_o = (double*)((char*)s->d_scratch + nb_first);
+    CU(cudaMemcpyAsync(d_first, first, nb_first, cudaMemcpyHostToDevice, s->stream));
+    k_chunk_data<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, d_first, (int)nyield, d_o);
+    CU(cudaGetLastError());
+    s->launches++;
+    CU(cudaMemcpyAsync(out, d_o, nb_out, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_chunk_state_at(fqsb_system* s, const int64_t* index, uint64_t* state, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the output buffer"));
+    }
+    std::vector<u64> rng((size_t)n);
+    std::vector<i64> idx((size_t)n);
+    CU(cudaMemcpyAsync(rng.data(), s->S.rng, (size_t)n * sizeof(u64), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaMemcpyAsync(idx.data(), s->S.idx, (size_t)n * sizeof(i64), cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (i64 g = 0; g < n; ++g) {
+        // the stored state's next draw is d_{i+2}
+        state[g] = s->P.consumes ? pcg_advance(rng[(size_t)g], index[g] - (idx[(size_t)g] + 2))
+                                 : rng[(size_t)g];
+    }
+    return FQSB_OK;
+}
+
+int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* value,
+                       const int64_t* index, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("size of the input buffers"));
+    }
+    for (i64 g = 0; g < n; ++g) {
+        if (index[g] < 0) {
+            return fail(FQSB_EASSERT, ASSERT_MSG("index >= 0"));
+        }
+    }
+    const size_t nb = (size_t)n * 8;
+    TRY(scratch(s, 3 * nb));
+    char* base = (char*)s->d_scratch;
+    CU(cudaMemcpyAsync(base, state, nb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(base + nb, value, nb, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(base + 2 * nb, index, nb, cudaMemcpyHostToDevice, s->stream));
+    k_chunk_restore<<<grid_for(s->n), 256, 0, s->stream>>>(
+        s->P, s->S, (const u64*)base, (const double*)(base + nb), (const i64*)(base + 2 * nb));
+    CU(cudaGetLastError());
+    s->launches++;
+    TRY(align(s, nullptr));
+    invalidate_forces(s);
+    return check_flags(s);
+}
+
+int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A)
+{
+    TRY(enter(s));
+    if (!s->d_in) {
+        TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
+    }
+    CU(cudaMemcpyAsync(s->d_in, i_n, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
+                       s->stream));
+    TRY(reduce_to_host(s, 4, 1, s->d_in));
+    for (i64 r = 0; r < s->R; ++r) {
+        if (out_S) {
+            out_S[r] = (int64_t)s->h_out[4 * r];
+        }
+        if (out_A) {
+            out_A[r] = (int64_t)s->h_out[4 * r + 1];
+        }
+    }
+    return FQSB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,320 @@
+// fqsb_aux_kernels.cuh -- non-template helper kernels (construction, well alignment K4, force
+// materialisation K8, reductions K3/K5, chunk views, streaming settle). Included by fqsb_api.cu
+// only.
+#pragma once
+
+#include "fqsb_kernels.cuh"
+
+namespace fqsb {
+
+// after a streaming call: realisations whose current state sits in the second buffer set are
+// copied back (and quenched when they converged, detail.h:1527-1532)
+__global__ void k_stream_settle(const Par P, const State S, int with_va)
+{
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    const int flip = ctl.flip;
+    const bool quench = ctl.status == ST_CONVERGED;
+    if (!flip && !quench) {
+        return;
+    }
+    const i64 base = (i64)r * P.N;
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < P.N;
+         p += (i64)gridDim.x * blockDim.x) {
+        if (flip) {
+            S.u[base + p] = S.u2[base + p];
+        }
+        if (quench) {
+            S.v[base + p] = 0.0;
+            S.a[base + p] = 0.0;
+        }
+        else if (flip && with_va) {
+            S.v[base + p] = S.v2[base + p];
+            S.a[base + p] = S.a2[base + p];
+        }
+    }
+}
+
+__global__ void k_stream_settle_flags(const Par P, const State S)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P.R) {
+        S.ctl[r].flip = 0;
+    }
+}
+
+// =============================================================================================
+// construction, alignment, forces, reductions, chunk views
+// =============================================================================================
+
+// Line1d.h:148-157 / Line2d.h:28-34: initstate = seed + flat index, y = cumsum + offset; then
+// detail.h:1127-1138: u = v = a = 0 and the first align.
+__global__ void k_init(const Par P, const State S)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        const i64 r = g / P.N, p = g - r * P.N;
+        u64 st = pcg_seed(P.seed + (u64)r * P.seed_stride + (u64)p);
+        double d0 = spacing_peek(P, st);
+        if (P.consumes) {
+            st = pcg_next(st);
+        }
+        // virtual well i = -1: (y[-1], y[0]] = (offset, offset + d_0]
+        double yl = P.offset, yr = P.offset + d0;
+        int underflow = 0;
+        int moved = well_align(P, 0.0, yl, yr, st, -1, &underflow);
+        if (-1 + moved < 0) {
+            S.err[0] = 1;
+        }
+        S.u[g] = 0.0;
+        S.v[g] = 0.0;
+        S.a[g] = 0.0;
+        S.yl[g] = yl;
+        S.yr[g] = yr;
+        S.idx[g] = -1 + moved;
+        S.rng[g] = st;
+    }
+}
+
+// updated_u()'s m_chunk->align(u) for every block (detail.h:144); optional uniform shift
+// u += du[r] first (advanceUniformly, detail.h:2041)
+__global__ void k_align(const Par P, const State S, const double* du)
+{
+    const i64 n = P.N * P.R;
+    int underflow = 0;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        double u = S.u[g];
+        if (du) {
+            u += du[g / P.N];
+            S.u[g] = u;
+        }
+        double yl = S.yl[g], yr = S.yr[g];
+        if (u > yr || !(u > yl)) {
+            u64 st = S.rng[g];
+            i64 i0 = S.idx[g];
+            int moved = well_align(P, u, yl, yr, st, i0, &underflow);
+            S.rng[g] = st;
+            S.idx[g] = i0 + moved;
+            S.yl[g] = yl;
+            S.yr[g] = yr;
+        }
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+}
+
+// K8: materialise force arrays on demand (getters, detail.h:1429-1468).
+// mask bits: 1 potential, 2 interactions, 4 frame, 8 damping; f is always re-summed
+// (detail.h:1324) from the stored components.
+struct ForceArrays {
+    double *f, *f_pot, *f_int, *f_frame, *f_damp;
+};
+
+__global__ void k_forces(const Par P, const State S, const ForceArrays F, int mask)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        const i64 r = g / P.N;
+        const int p = (int)(g - r * P.N);
+        const double* ur = S.u + r * P.N;
+        const double uc = ur[p];
+        if (mask & 1) {
+            F.f_pot[g] = f_potential_rt(P, uc, S.yl[g], S.yr[g]);
+        }
+        if (mask & 2) {
+            int i = 0, j = 0;
+            if (P.rank == 2) {
+                i = p / P.cols;
+                j = p - i * P.cols;
+            }
+            auto U = [&](int q) { return ur[q]; };
+            F.f_int[g] = f_interactions_rt(P, U, S.pref, p, i, j, uc);
+        }
+        if (mask & 4) {
+            F.f_frame[g] = P.k_frame * (S.u_frame[r] - uc);
+        }
+        if (mask & 8) {
+            F.f_damp[g] = -P.eta * S.v[g];
+        }
+        F.f[g] = F.f_frame[g] + F.f_pot[g] + F.f_int[g] + F.f_damp[g];
+    }
+}
+
+// per-realisation reductions, two stages with fixed order.
+// what: 0 residual sums from stored arrays {sum f^2, sum f_frame^2}
+//       1 residual sums derived on the fly from the state
+//       2 {sum v^2, sum f_frame} (temperature, mean frame force)
+//       3 {min displacement, off-branch flag} (maxUniformDisplacement, detail.h:176-187,282-334)
+//       4 {sum (i - i_n), #(i != i_n)} and part[2] = sum |i - i_n|
+__global__ void __launch_bounds__(256) k_reduce(const Par P, const State S, const ForceArrays F,
+                                                int what, int direction, const i64* i_n,
+                                                double* part /* [R][tiles][4] */)
+{
+    __shared__ double scratch[32 * 3];
+    const int r = blockIdx.y;
+    const i64 base = (i64)r * P.N;
+    const int N = (int)P.N;
+    double acc[3] = {0.0, 0.0, 0.0};
+    double mn = 1.7976931348623157e308;
+    const double uf = S.u_frame[r];
+    const double* ur = S.u + base;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+        const i64 g = base + p;
+        if (what == 0) {
+            acc[0] += F.f[g] * F.f[g];
+            acc[1] += F.f_frame[g] * F.f_frame[g];
+        }
+        else if (what == 1) {
+            const double uc = ur[p];
+            int i = 0, j = 0;
+            if (P.rank == 2) {
+                i = p / P.cols;
+                j = p - i * P.cols;
+            }
+            auto U = [&](int q) { return ur[q]; };
+            double fi = f_interactions_rt(P, U, S.pref, p, i, j, uc);
+            double fp = f_potential_rt(P, uc, S.yl[g], S.yr[g]);
+            double ff = P.k_frame * (uf - uc);
+            double f = ff + fp + fi + (-P.eta * S.v[g]);
+            acc[0] += f * f;
+            acc[1] += ff * ff;
+        }
+        else if (what == 2) {
+            acc[0] += S.v[g] * S.v[g];
+            acc[1] += P.k_frame * (uf - ur[p]);
+        }
+        else if (what == 3) {
+            const double uc = ur[p], yl = S.yl[g], yr = S.yr[g];
+            if (P.pot == POT_CUSPY) {
+                mn = fmin(mn, direction > 0 ? yr - uc : uc - yl);
+            }
+            else {
+                double xi = 0.5 * (yl + yr);
+                double u_r = (P.mu * xi + P.kappa * yr) / (P.mu + P.kappa);
+                double u_l = (P.mu * xi + P.kappa * yl) / (P.mu + P.kappa);
+                if (uc < u_l || !(uc <= u_r)) {
+                    acc[1] += 1.0;
+                }
+                else {
+                    mn = fmin(mn, direction > 0 ? u_r - uc : uc - u_l);
+                }
+            }
+        }
+        else {
+            i64 d = S.idx[g] - i_n[g];
+            acc[0] += (double)d;
+            acc[1] += d != 0 ? 1.0 : 0.0;
+            acc[2] += (double)(d < 0 ? -d : d);
+        }
+    }
+    block_sum<3>(acc, scratch);
+    mn = warp_min(mn);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        scratch[threadIdx.x >> 5] = mn;
+    }
+    __syncthreads();
+    mn = warp_min((threadIdx.x & 31) < (blockDim.x >> 5) ? scratch[threadIdx.x & 31]
+                                                         : 1.7976931348623157e308);
+    if (threadIdx.x == 0) {
+        double* o = part + ((size_t)r * gridDim.x + blockIdx.x) * 4;
+        o[0] = acc[0];
+        o[1] = acc[1];
+        o[2] = acc[2];
+        o[3] = mn;
+    }
+}
+
+__global__ void k_reduce_final(const double* part, int tiles, double* out /* [R][4] */)
+{
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, mn = 1.7976931348623157e308;
+    for (int c = lane; c < tiles; c += 32) {
+        const double* o = part + ((size_t)r * tiles + c) * 4;
+        a0 += o[0];
+        a1 += o[1];
+        a2 += o[2];
+        mn = fmin(mn, o[3]);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    mn = warp_min(mn);
+    if (lane == 0) {
+        out[4 * r] = a0;
+        out[4 * r + 1] = a1;
+        out[4 * r + 2] = a2;
+        out[4 * r + 3] = mn;
+    }
+}
+
+// quench(): v = a = 0 (detail.h:1527-1532)
+__global__ void k_zero_va(const Par P, const State S)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        S.v[g] = 0.0;
+        S.a[g] = 0.0;
+    }
+}
+
+// `system.chunk.data`: y[p, first[p] .. first[p]+ny) regenerated from the current well
+__global__ void k_chunk_data(const Par P, const State S, const i64* first, int ny, double* out)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        double yl = S.yl[g], yr = S.yr[g];
+        u64 st = S.rng[g];
+        i64 i = S.idx[g];
+        const i64 f0 = first[g];
+        double* o = out + g * (i64)ny;
+        // walk the window (yl = y[i], yr = y[i+1]) so that i == f0
+        while (i > f0) {
+            u64 sb = st;
+            if (P.consumes) {
+                st = pcg_prev(st);
+                sb = pcg_prev(st);
+            }
+            yr = yl;
+            yl = yl - spacing_peek(P, sb);
+            --i;
+        }
+        while (i < f0) {
+            double d = spacing_peek(P, st);
+            if (P.consumes) {
+                st = pcg_next(st);
+            }
+            yl = yr;
+            yr = yr + d;
+            ++i;
+        }
+        for (int k = 0; k < ny; ++k) {
+            o[k] = yl;
+            double d = spacing_peek(P, st);
+            if (P.consumes) {
+                st = pcg_next(st);
+            }
+            yl = yr;
+            yr = yr + d;
+        }
+    }
+}
+
+// `system.chunk.restore(state, value, index)`: y[index] = value, generator as state_at(index)
+__global__ void k_chunk_restore(const Par P, const State S, const u64* state, const double* value,
+                                const i64* index)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        u64 st = state[g];
+        double d = spacing_peek(P, st); // d_index
+        S.yr[g] = value[g];
+        S.yl[g] = value[g] - d;
+        S.idx[g] = index[g] - 1;
+        S.rng[g] = P.consumes ? pcg_next(st) : st;
+    }
+}
+
+} // namespace fqsb

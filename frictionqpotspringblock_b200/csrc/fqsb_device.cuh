@@ -1,0 +1,423 @@
+// fqsb_device.cuh -- device-side building blocks of the B200-native integrator.
+//
+// Arithmetic contract: every per-block expression keeps the evaluation order of the
+// reference (include/FrictionQPotSpringBlock/detail.h, cited per function as detail.h:LINE)
+// and this translation unit is compiled with -fmad=false, so u, v, a and the forces are a
+// deterministic IEEE-754 function of the inputs -- bit-identical to the CPU oracle
+// (oracle/fqsb_oracle.c, -ffp-contract=off). Only reductions (residual norms) and libm
+// functions (sin, log, pow) may differ in the last bits.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fqsb {
+
+typedef long long i64;
+typedef unsigned long long u64;
+
+// ---- parameters shared by all realisations of a handle (kernel argument, by value) --------
+struct Par {
+    int pot, inter, rank, dist;
+    int rows, cols;
+    int consumes; // distribution consumes pcg32 draws (everything but delta)
+    int pad0;
+    i64 N; // blocks per realisation
+    i64 R; // realisations
+    double m, inv_m, eta, mu, kappa, k1, k2, k_frame, dt;
+    double dpar[4];
+    double offset;
+    u64 seed, seed_stride;
+};
+
+// ---- per-realisation control block (device global memory) ---------------------------------
+enum Status : int {
+    ST_RUNNING = 0,
+    ST_CONVERGED = 1, // StopList criterion met -> quenched, returns 0
+    ST_EVENT = 2,     // timeStepsUntilEvent: a well index changed -> returns step
+    ST_TRUNCATED = 3, // minimise_truncate: A or S reached -> returns step
+    ST_EXHAUSTED = 4, // max_iter reached -> returns max_iter + 1
+    ST_NAN = 5,
+    ST_IDLE = 6
+};
+
+enum Mode : int { MODE_FIXED = 0, MODE_MINIMISE = 1, MODE_UNTIL_EVENT = 2, MODE_TRUNCATE = 3 };
+
+#define FQSB_RING 32
+
+struct Ctl {
+    int status;
+    int init; // "first plastic event not seen yet" (detail.h:1758,1771)
+    i64 steps; // steps done so far in the current call
+    i64 S, A;  // sum |i - i_n|, #(i != i_n) (detail.h:1863-1864)
+    i64 s_n;   // detail.h:1757,1777
+    i64 inc;   // increment number m_inc (detail.h:1067)
+    i64 qs_first, qs_last; // detail.h:1068-1069
+    double residual;       // last residual inserted
+    double ring[FQSB_RING]; // GooseFEM::Iterate::StopList
+    unsigned int count;     // streaming path: CTAs of this realisation that finished the step
+    int flip;               // streaming path: which of the two u/v/a buffer sets is current
+};
+
+struct RunArgs {
+    int mode;
+    int track; // maintain S, A against i_n (time_activity / truncate)
+    int flow;  // flowSteps: move the frame before every step
+    int niter_tol;
+    i64 max_steps; // total step budget of the call (max_iter, or n for fixed)
+    i64 launch_steps; // resident path: upper bound of steps in this launch
+    i64 A_truncate, S_truncate;
+    double tol, tol2, v_frame;
+    const i64* i_n; // device [R*N] or nullptr
+};
+
+struct State {
+    double *u, *v, *a;    // current state [R*N]
+    double *u2, *v2, *a2; // ping-pong set of the streaming kernels
+    double *yl, *yr;      // y[i], y[i+1] of the current well
+    i64* idx;             // global well index i
+    u64* rng;             // pcg32 state whose next draw is d_{i+2}
+    double* u_frame;      // [R]
+    Ctl* ctl;             // [R]
+    int* err;             // [0] landscape underflow, [1] NaN
+    const double* pref;   // LongRange prefactor table [N] (detail.h:829-844)
+    double* part;         // streaming path: per-CTA partial sums
+    int tiles;            // streaming path: CTAs per realisation
+};
+
+// ---- prrng::pcg32 ------------------------------------------------------
+#define FQSB_PCG_MULT 0x5851f42d4c957f2dULL
+#define FQSB_PCG_MULT_INV 0xc097ef87329e28a5ULL
+#define FQSB_PCG_INC 1ULL // initseq = 0 for every block (Line1d.h:151)
+
+__host__ __device__ __forceinline__ u64 pcg_next(u64 s) { return s * FQSB_PCG_MULT + FQSB_PCG_INC; }
+__host__ __device__ __forceinline__ u64 pcg_prev(u64 s)
+{
+    return (s - FQSB_PCG_INC) * FQSB_PCG_MULT_INV;
+}
+
+__host__ __device__ __forceinline__ u64 pcg_seed(u64 initstate)
+{
+    u64 s = 0ULL;
+    s = pcg_next(s);
+    s += initstate;
+    s = pcg_next(s);
+    return s;
+}
+
+// the [0,1) double the generator emits from state `old` (32 random mantissa bits)
+__host__ __device__ __forceinline__ double pcg_double(u64 old)
+{
+    unsigned int xs = (unsigned int)(((old >> 18u) ^ old) >> 27u);
+    unsigned int rot = (unsigned int)(old >> 59u);
+    unsigned int out = (xs >> rot) | (xs << ((0u - rot) & 31u));
+    u64 bits = ((u64)out << 20) | 0x3ff0000000000000ULL;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((i64)bits) - 1.0;
+#else
+    double d;
+    memcpy(&d, &bits, sizeof d);
+    return d - 1.0;
+#endif
+}
+
+// O(log n) jump (host side: state_at)
+__host__ __device__ inline u64 pcg_advance(u64 s, i64 distance)
+{
+    u64 delta = (u64)distance;
+    u64 cur_mult = FQSB_PCG_MULT, cur_plus = FQSB_PCG_INC, acc_mult = 1ULL, acc_plus = 0ULL;
+    while (delta > 0) {
+        if (delta & 1ULL) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1ULL) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1ULL;
+    }
+    return acc_mult * s + acc_plus;
+}
+
+// ---- distributions -> yield spacing ------------------------------------
+enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DIST_GAMMA = 4,
+       DIST_PARETO = 5, DIST_WEIBULL = 6, DIST_NORMAL = 7 };
+
+__host__ __device__ __forceinline__ double spacing_from_draw(const Par& P, double r)
+{
+    if (P.dist == DIST_RANDOM) {
+        return r * P.dpar[0] + P.dpar[1];
+    }
+    switch (P.dist) {
+    case DIST_DELTA:
+        return P.dpar[0] + P.dpar[1];
+    case DIST_EXPONENTIAL:
+        return -log(1.0 - r) * P.dpar[0] + P.dpar[1];
+    case DIST_POWER:
+        return pow(1.0 - r, 1.0 / (P.dpar[0] + 1.0)) + P.dpar[1];
+    case DIST_PARETO:
+        return P.dpar[1] * pow(1.0 - r, -1.0 / P.dpar[0]) + P.dpar[2];
+    default: // DIST_WEIBULL
+        return P.dpar[1] * pow(-log(1.0 - r), 1.0 / P.dpar[0]) + P.dpar[2];
+    }
+}
+
+// spacing the generator draws next from state st; st itself is not advanced
+__host__ __device__ __forceinline__ double spacing_peek(const Par& P, u64 st)
+{
+    return spacing_from_draw(P, P.consumes ? pcg_double(st) : 0.0);
+}
+
+// ---- the yield landscape: prrng::pcg32_tensor_cumsum without a chunk ------------------------
+// A block keeps only its current well: yl = y[i], yr = y[i+1], the global index i and the
+// generator state st whose next draw is d_{i+2}. Leaving the well regenerates the neighbouring
+// yield position from the pcg32 stream (forward: one LCG step; backward: one inverse-LCG step),
+// so y[j] = y[j-1] + d_j exactly as a sequential cumsum. This replaces
+// m_chunk->align(u) (detail.h:144,180,197) and align(p,u) (detail.h:1732).
+// Returns the signed number of wells moved; sets *underflow when i would drop below 0.
+__host__ __device__ __forceinline__ int well_align(const Par& P, double u, double& yl, double& yr,
+                                          u64& st, i64 i_now, int* underflow)
+{
+    int moved = 0;
+    if (!(fabs(u) <= 1.7976931348623157e308)) { // NaN / inf: reported by the NaN check
+        return 0;
+    }
+    while (u > yr) {
+        double d = spacing_peek(P, st);
+        if (P.consumes) {
+            st = pcg_next(st);
+        }
+        yl = yr;
+        yr = yr + d;
+        ++moved;
+    }
+    while (!(u > yl)) {
+        if (i_now + moved <= 0) {
+            *underflow = 1;
+            break;
+        }
+        // y[i-1] = y[i] - d_i ; d_i is the draw two positions behind st
+        u64 sb = st;
+        if (P.consumes) {
+            st = pcg_prev(st);
+            sb = pcg_prev(st);
+        }
+        double d = spacing_peek(P, sb);
+        yr = yl;
+        yl = yl - d;
+        --moved;
+    }
+    return moved;
+}
+
+// ---- potentials -----------------------------------------------------------------------------
+enum { POT_CUSPY = 0, POT_SEMISMOOTH = 1, POT_SMOOTH = 2 };
+
+template <int POT>
+__device__ __forceinline__ double f_potential(const Par& P, double u, double yl, double yr)
+{
+    if (POT == POT_CUSPY) { // detail.h:164-169
+        return (0.5 * (yl + yr) - u) * P.mu;
+    }
+    else if (POT == POT_SEMISMOOTH) { // detail.h:261-276
+        double xi = 0.5 * (yl + yr);
+        double u_r = (P.mu * xi + P.kappa * yr) / (P.mu + P.kappa);
+        double u_l = (P.mu * xi + P.kappa * yl) / (P.mu + P.kappa);
+        if (u < u_l) {
+            return P.kappa * (u - yl);
+        }
+        else if (u <= u_r) {
+            return P.mu * (0.5 * (yl + yr) - u);
+        }
+        return P.kappa * (u - yr);
+    }
+    else { // detail.h:402-408
+        double umin = 0.5 * (yr + yl);
+        double dy = 0.5 * (yr - yl);
+        return -P.mu * dy / 3.14159265358979323846 *
+               sin(3.14159265358979323846 * (u - umin) / dy);
+    }
+}
+
+__device__ __forceinline__ double f_potential_rt(const Par& P, double u, double yl, double yr)
+{
+    switch (P.pot) {
+    case POT_CUSPY:
+        return f_potential<POT_CUSPY>(P, u, yl, yr);
+    case POT_SEMISMOOTH:
+        return f_potential<POT_SEMISMOOTH>(P, u, yl, yr);
+    default:
+        return f_potential<POT_SMOOTH>(P, u, yl, yr);
+    }
+}
+
+// ---- interactions ---------------------------------------------------------------------------
+enum { INT_NONE = 0, INT_LAPLACE1D = 1, INT_QUARTIC1D = 2, INT_QUARTICGRADIENT1D = 3,
+       INT_LONGRANGE1D = 4, INT_LAPLACE2D = 5, INT_QUARTICGRADIENT2D = 6 };
+
+// U(q): slip of the block with flat index q of the same realisation (shared memory, or
+// recomputed from global memory). p = own flat index, (i, j) = its row/col for rank 2.
+template <int INT, class UF>
+__device__ __forceinline__ double f_interactions(const Par& P, UF&& U, const double* pref, int p,
+                                                 int i, int j, double uc)
+{
+    const int N = (int)P.N;
+    if (INT == INT_NONE) {
+        return 0.0;
+    }
+    else if (INT == INT_LAPLACE1D) { // detail.h:480-486
+        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
+        return (U(l) - 2 * uc + U(r)) * P.k1;
+    }
+    else if (INT == INT_QUARTIC1D) { // detail.h:784-803
+        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
+        double um = U(l), up = U(r);
+        double dup = up - uc;
+        double dun = um - uc;
+        return P.k1 * (um - 2 * uc + up) + P.k2 * (dup * dup * dup + dun * dun * dun);
+    }
+    else if (INT == INT_QUARTICGRADIENT1D) { // detail.h:642-651
+        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
+        double um = U(l), up = U(r);
+        double du = up - um;
+        return (um - 2 * uc + up) * (P.k1 + (0.25 * P.k2) * du * du);
+    }
+    else if (INT == INT_LONGRANGE1D) { // detail.h:852-866 (same summation order)
+        const int m = (N - N % 2) / 2;
+        double fp = 0.0;
+        for (int q = 0; q < N; ++q) {
+            if (q == p) {
+                continue;
+            }
+            int d = q > p ? q - p : p - q;
+            if (d > m) {
+                d = N - d;
+            }
+            fp += (U(q) - uc) * pref[d];
+        }
+        return fp;
+    }
+    else if (INT == INT_LAPLACE2D) { // detail.h:557-582
+        const int R = P.rows, C = P.cols;
+        int im = (i == 0 ? R - 1 : i - 1) * C, ip = (i == R - 1 ? 0 : i + 1) * C, ic = i * C;
+        int jm = j == 0 ? C - 1 : j - 1, jp = j == C - 1 ? 0 : j + 1;
+        return (U(im + j) + U(ip + j) + U(ic + jm) + U(ic + jp) - 4 * uc) * P.k1;
+    }
+    else { // QuarticGradient2d, detail.h:700-711
+        const int R = P.rows, C = P.cols;
+        int im = (i == 0 ? R - 1 : i - 1) * C, ip = (i == R - 1 ? 0 : i + 1) * C, ic = i * C;
+        int jm = j == 0 ? C - 1 : j - 1, jp = j == C - 1 ? 0 : j + 1;
+        double mk4_3 = P.k2 / 3.0;
+        double mk4_23 = 2.0 * mk4_3;
+        double u_pj = U(ip + j), u_mj = U(im + j), u_cp = U(ic + jp), u_cm = U(ic + jm);
+        double l = u_pj + u_mj + u_cp + u_cm - 4 * uc;
+        double dudx = 0.5 * (u_pj - u_mj);
+        double dudy = 0.5 * (u_cp - u_cm);
+        double d2udxdy = 0.25 * (U(ip + jp) - U(ip + jm) - U(im + jp) + U(im + jm));
+        double d2udx2 = u_pj - 2 * uc + u_mj;
+        double d2udy2 = u_cp - 2 * uc + u_cm;
+        return l * (P.k1 + mk4_3) + mk4_23 * (dudx * dudx * d2udx2 + dudy * dudy * d2udy2 +
+                                              2.0 * dudx * dudy * d2udxdy);
+    }
+}
+
+template <class UF>
+__device__ __forceinline__ double f_interactions_rt(const Par& P, UF&& U, const double* pref,
+                                                    int p, int i, int j, double uc)
+{
+    switch (P.inter) {
+    case INT_NONE:
+        return 0.0;
+    case INT_LAPLACE1D:
+        return f_interactions<INT_LAPLACE1D>(P, U, pref, p, i, j, uc);
+    case INT_QUARTIC1D:
+        return f_interactions<INT_QUARTIC1D>(P, U, pref, p, i, j, uc);
+    case INT_QUARTICGRADIENT1D:
+        return f_interactions<INT_QUARTICGRADIENT1D>(P, U, pref, p, i, j, uc);
+    case INT_LONGRANGE1D:
+        return f_interactions<INT_LONGRANGE1D>(P, U, pref, p, i, j, uc);
+    case INT_LAPLACE2D:
+        return f_interactions<INT_LAPLACE2D>(P, U, pref, p, i, j, uc);
+    default:
+        return f_interactions<INT_QUARTICGRADIENT2D>(P, U, pref, p, i, j, uc);
+    }
+}
+
+// ---- velocity-Verlet tail of timeStep (detail.h:1552-1565) -----------------------------------
+// F = (f_frame + f_potential) + f_interactions at the new u; returns the final residual force
+// f = F + f_damping and updates v, a in place (v_n, a_n are the values on entry).
+__device__ __forceinline__ double verlet_tail(const Par& P, double F, double& v, double& a)
+{
+    const double vn = v, an = a;
+    const double hdt = 0.5 * P.dt;
+    const double meta = -P.eta;
+    double vv = vn + P.dt * an; // 1552
+    double f = F + meta * vv;   // 1553: updated_v() -> f = f_frame+f_pot+f_int+f_damp
+    double aa = f * P.inv_m;    // 1555
+    vv = vn + hdt * (an + aa);  // 1557
+    f = F + meta * vv;          // 1558
+    aa = f * P.inv_m;           // 1560
+    vv = vn + hdt * (an + aa);  // 1562
+    f = F + meta * vv;          // 1563
+    aa = f * P.inv_m;           // 1565
+    v = vv;
+    a = aa;
+    return f;
+}
+
+// ---- GooseFEM::Iterate::StopList held in the lanes of a warp -----------
+// lane l < n holds entry l; entries start at +inf.
+__device__ __forceinline__ double ring_roll_insert(double ring, double x, int n, int lane)
+{
+    double nxt = __shfl_down_sync(0xffffffffu, ring, 1);
+    return lane == n - 1 ? x : nxt;
+}
+
+__device__ __forceinline__ bool ring_stop(double ring, int n, int lane, double tol, double tol2)
+{
+    double nxt = __shfl_down_sync(0xffffffffu, ring, 1);
+    bool desc = (lane >= n - 1) || !(nxt > ring);       // std::is_sorted(..., greater)
+    bool less1 = (lane >= n) || (ring < tol);           // all_less(tol): strict
+    bool less2 = (lane >= n) || (ring < tol2);
+    bool descending = __all_sync(0xffffffffu, desc);
+    bool all1 = __all_sync(0xffffffffu, less1);
+    bool all2 = __all_sync(0xffffffffu, less2);
+    return (descending && all1) || all2; // detail.h:1615,1748,1780,1874
+}
+
+// ---- warp reductions (fixed butterfly order -> deterministic) --------------------------------
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    return x;
+}
+
+__device__ __forceinline__ int warp_sum(int x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    return x;
+}
+
+__device__ __forceinline__ double warp_min(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
+    }
+    return x;
+}
+
+// residual() of detail.h:1512-1520 from the two sums of squares
+__device__ __forceinline__ double residual_from_sums(double sf, double sff)
+{
+    double r_fres = sqrt(sf);
+    double r_fext = sqrt(sff);
+    return r_fext != 0.0 ? r_fres / r_fext : r_fres;
+}
+
+} // namespace fqsb

@@ -1,0 +1,125 @@
+// fqsb_resident.cu -- instantiation unit of the resident (one CTA = one realisation) kernels.
+// Compiled once per potential x interaction combination (-DFQSB_COMBO=k) so the objects build
+// in parallel; combination 9 holds the no-passing kernels.
+#include "fqsb_host.h"
+#include "fqsb_kernels.cuh"
+
+#ifndef FQSB_COMBO
+#error "compile with -DFQSB_COMBO=<0..9>"
+#endif
+
+namespace fqsb {
+
+#if FQSB_COMBO == 0
+#define C_POT POT_CUSPY
+#define C_INT INT_LAPLACE1D
+#elif FQSB_COMBO == 1
+#define C_POT POT_CUSPY
+#define C_INT INT_QUARTIC1D
+#elif FQSB_COMBO == 2
+#define C_POT POT_CUSPY
+#define C_INT INT_QUARTICGRADIENT1D
+#elif FQSB_COMBO == 3
+#define C_POT POT_CUSPY
+#define C_INT INT_LONGRANGE1D
+#elif FQSB_COMBO == 4
+#define C_POT POT_CUSPY
+#define C_INT INT_LAPLACE2D
+#elif FQSB_COMBO == 5
+#define C_POT POT_CUSPY
+#define C_INT INT_QUARTICGRADIENT2D
+#elif FQSB_COMBO == 6
+#define C_POT POT_SEMISMOOTH
+#define C_INT INT_LAPLACE1D
+#elif FQSB_COMBO == 7
+#define C_POT POT_SMOOTH
+#define C_INT INT_LAPLACE1D
+#elif FQSB_COMBO == 8
+#define C_POT POT_CUSPY
+#define C_INT INT_NONE
+#endif
+
+template <class K>
+static cudaError_t launch(K kernel, int T, size_t smem, const Par& P, const State& S,
+                          const RunArgs& A, cudaStream_t stream)
+{
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    kernel<<<(unsigned)P.R, T, smem, stream>>>(P, S, A);
+    return cudaGetLastError();
+}
+
+#if FQSB_COMBO < 9
+
+#define FQSB_CAT2(a, b) a##b
+#define FQSB_CAT(a, b) FQSB_CAT2(a, b)
+
+cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const Par& P,
+                                                   const State& S, const RunArgs& A,
+                                                   cudaStream_t stream)
+{
+    const size_t smem = resident_smem(P, c);
+    if (c.B == 1 && c.T == 256) {
+        return launch(k_resident<C_POT, C_INT, 1, 256>, 256, smem, P, S, A, stream);
+    }
+    if (c.B == 1 && c.T == 1024) {
+        return launch(k_resident<C_POT, C_INT, 1, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 2 && c.T == 1024) {
+        return launch(k_resident<C_POT, C_INT, 2, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 4 && c.T == 1024) {
+        return launch(k_resident<C_POT, C_INT, 4, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 8 && c.T == 512) {
+        return launch(k_resident<C_POT, C_INT, 8, 512>, 512, smem, P, S, A, stream);
+    }
+    if (c.B == 8 && c.T == 1024) {
+        return launch(k_resident<C_POT, C_INT, 8, 1024>, 1024, smem, P, S, A, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+#else // no-passing
+
+template <int INT>
+static cudaError_t launch_np(const ResidentCfg& c, const Par& P, const State& S,
+                             const RunArgs& A, cudaStream_t stream)
+{
+    const size_t smem = resident_smem(P, c);
+    if (c.B == 1 && c.T == 256) {
+        return launch(k_resident_nopassing<INT, 1, 256>, 256, smem, P, S, A, stream);
+    }
+    if (c.B == 1 && c.T == 1024) {
+        return launch(k_resident_nopassing<INT, 1, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 2 && c.T == 1024) {
+        return launch(k_resident_nopassing<INT, 2, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 4 && c.T == 1024) {
+        return launch(k_resident_nopassing<INT, 4, 1024>, 1024, smem, P, S, A, stream);
+    }
+    if (c.B == 8 && c.T == 512) {
+        return launch(k_resident_nopassing<INT, 8, 512>, 512, smem, P, S, A, stream);
+    }
+    if (c.B == 8 && c.T == 1024) {
+        return launch(k_resident_nopassing<INT, 8, 1024>, 1024, smem, P, S, A, stream);
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+cudaError_t launch_resident_nopassing(const ResidentCfg& c, const Par& P, const State& S,
+                                      const RunArgs& A, cudaStream_t stream)
+{
+    if (P.inter == INT_LAPLACE2D) {
+        return launch_np<INT_LAPLACE2D>(c, P, S, A, stream);
+    }
+    return launch_np<INT_LAPLACE1D>(c, P, S, A, stream);
+}
+
+#endif
+
+} // namespace fqsb

@@ -1,0 +1,92 @@
+// fqsb_stream.cu -- instantiation unit of the streaming kernels + kernel dispatch tables.
+#include "fqsb_host.h"
+#include "fqsb_kernels.cuh"
+
+namespace fqsb {
+
+#define FQSB_DECL(k) \
+    cudaError_t launch_resident_##k(const ResidentCfg&, const Par&, const State&, \
+                                    const RunArgs&, cudaStream_t);
+FQSB_DECL(0) FQSB_DECL(1) FQSB_DECL(2) FQSB_DECL(3) FQSB_DECL(4)
+FQSB_DECL(5) FQSB_DECL(6) FQSB_DECL(7) FQSB_DECL(8)
+
+// the systems of Line1d.h:112-677 and Line2d.h:77-162 (+ interaction-free, Particles.h)
+static int combo_of(int pot, int inter)
+{
+    if (pot == POT_CUSPY) {
+        switch (inter) {
+        case INT_LAPLACE1D: return 0;
+        case INT_QUARTIC1D: return 1;
+        case INT_QUARTICGRADIENT1D: return 2;
+        case INT_LONGRANGE1D: return 3;
+        case INT_LAPLACE2D: return 4;
+        case INT_QUARTICGRADIENT2D: return 5;
+        case INT_NONE: return 8;
+        }
+    }
+    if (pot == POT_SEMISMOOTH && inter == INT_LAPLACE1D) {
+        return 6;
+    }
+    if (pot == POT_SMOOTH && inter == INT_LAPLACE1D) {
+        return 7;
+    }
+    return -1;
+}
+
+bool combination_supported(int pot, int inter) { return combo_of(pot, inter) >= 0; }
+
+cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
+                            const RunArgs& A, cudaStream_t stream)
+{
+    switch (combo_of(P.pot, P.inter)) {
+    case 0: return launch_resident_0(c, P, S, A, stream);
+    case 1: return launch_resident_1(c, P, S, A, stream);
+    case 2: return launch_resident_2(c, P, S, A, stream);
+    case 3: return launch_resident_3(c, P, S, A, stream);
+    case 4: return launch_resident_4(c, P, S, A, stream);
+    case 5: return launch_resident_5(c, P, S, A, stream);
+    case 6: return launch_resident_6(c, P, S, A, stream);
+    case 7: return launch_resident_7(c, P, S, A, stream);
+    case 8: return launch_resident_8(c, P, S, A, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
+                               cudaStream_t stream)
+{
+    dim3 grid((unsigned)S.tiles, (unsigned)P.R);
+#define FQSB_STREAM(pot, inter) \
+    k_stream_step<pot, inter><<<grid, 256, 0, stream>>>(P, S, A); \
+    break;
+    switch (combo_of(P.pot, P.inter)) {
+    case 0: FQSB_STREAM(POT_CUSPY, INT_LAPLACE1D)
+    case 1: FQSB_STREAM(POT_CUSPY, INT_QUARTIC1D)
+    case 2: FQSB_STREAM(POT_CUSPY, INT_QUARTICGRADIENT1D)
+    case 3: FQSB_STREAM(POT_CUSPY, INT_LONGRANGE1D)
+    case 4: FQSB_STREAM(POT_CUSPY, INT_LAPLACE2D)
+    case 5: FQSB_STREAM(POT_CUSPY, INT_QUARTICGRADIENT2D)
+    case 6: FQSB_STREAM(POT_SEMISMOOTH, INT_LAPLACE1D)
+    case 7: FQSB_STREAM(POT_SMOOTH, INT_LAPLACE1D)
+    case 8: FQSB_STREAM(POT_CUSPY, INT_NONE)
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
+                                cudaStream_t stream)
+{
+    dim3 grid((unsigned)S.tiles, (unsigned)P.R);
+    if (P.inter == INT_LAPLACE2D) {
+        k_stream_sweep<INT_LAPLACE2D><<<grid, 256, 0, stream>>>(P, S, A);
+        k_stream_sweep_residual<INT_LAPLACE2D><<<grid, 256, 0, stream>>>(P, S, A);
+    }
+    else {
+        k_stream_sweep<INT_LAPLACE1D><<<grid, 256, 0, stream>>>(P, S, A);
+        k_stream_sweep_residual<INT_LAPLACE1D><<<grid, 256, 0, stream>>>(P, S, A);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace fqsb

@@ -1,0 +1,206 @@
+/*
+ * fqsb.h -- C ABI of the B200-native FrictionQPotSpringBlock integrator (libfqsb.so).
+ *
+ * This is the drop-in boundary of the hot path. The reference has no FFI of its own: it is a
+ * header-only C++ template library (include/FrictionQPotSpringBlock/detail.h) consumed
+ * directly by python/main.cpp. Each entry point below therefore names the reference
+ * member function it replaces ("ref:" = path:line under the reference tree); a C++ host class
+ * with the reference's names (include/fqsb.hpp) and the Python module
+ * (frictionqpotspringblock_b200) forward 1:1 to these calls, exactly as python/main.cpp:46-226
+ * forwards to detail::System.
+ *
+ * One handle = an ENSEMBLE of `nrealisations` >= 1 independent systems of identical
+ * parameters (a single reference `System_*` object is nrealisations == 1). Realisation r owns
+ * the pcg32 initstates  seed + r*seed_stride + p  (p = flat block index), so it equals the
+ * reference object constructed with seed = seed + r*seed_stride (ref: Line1d.h:148-151).
+ * Per-block arrays are row-major [nrealisations][size]; per-realisation scalars are arrays of
+ * length nrealisations.
+ *
+ * Conventions
+ *  - plain pointers are HOST pointers unless the name says `_device`;
+ *  - every function returns an fqsb_status; the message of the last failure on the calling
+ *    thread is fqsb_last_error() and equals the reference's exception text;
+ *  - one handle = one owner thread = one CUDA stream; calls are synchronous on return;
+ *  - there is no CPU fallback: without a CUDA device fqsb_create fails with FQSB_ECUDA.
+ */
+#ifndef FQSB_H
+#define FQSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQSB_ABI_VERSION 1
+
+typedef enum {
+    FQSB_OK = 0,
+    FQSB_ENAN = 1,         /* "NaN entries found"               ref: detail.h:1567-1569 */
+    FQSB_ENOCONV = 2,      /* "No convergence found"            ref: detail.h:1787-1789 */
+    FQSB_EASSERT = 3,      /* "...assertion failed (...)"       ref: config.h:19-24     */
+    FQSB_EUNSUPPORTED = 4, /* "Minimisation not implementated", "Operation not possible." */
+    FQSB_ECUDA = 5         /* CUDA runtime failure / no device */
+} fqsb_status;
+
+/* ref: detail.h:113-439 */
+typedef enum { FQSB_POT_CUSPY = 0, FQSB_POT_SEMISMOOTH = 1, FQSB_POT_SMOOTH = 2 } fqsb_potential;
+
+/* ref: detail.h:446-868 */
+typedef enum {
+    FQSB_INT_NONE = 0,
+    FQSB_INT_LAPLACE1D = 1,
+    FQSB_INT_QUARTIC1D = 2,
+    FQSB_INT_QUARTICGRADIENT1D = 3,
+    FQSB_INT_LONGRANGE1D = 4,
+    FQSB_INT_LAPLACE2D = 5,
+    FQSB_INT_QUARTICGRADIENT2D = 6
+} fqsb_interactions;
+
+/* ref: detail.h:1005-1020 (Overdamped = the "minimise_nopassing" of older releases) */
+typedef enum { FQSB_MIN_DYNAMIC = 0, FQSB_MIN_OVERDAMPED = 1 } fqsb_minimisation;
+
+/* ref: detail.h:31-66 (prrng::distribution) */
+typedef enum {
+    FQSB_DIST_RANDOM = 0,
+    FQSB_DIST_DELTA = 1,
+    FQSB_DIST_EXPONENTIAL = 2,
+    FQSB_DIST_POWER = 3,
+    FQSB_DIST_GAMMA = 4, /* unsupported: needs boost inverse incomplete gamma */
+    FQSB_DIST_PARETO = 5,
+    FQSB_DIST_WEIBULL = 6,
+    FQSB_DIST_NORMAL = 7 /* unsupported: needs boost erf_inv */
+} fqsb_distribution;
+
+/* Constructor arguments of every Line1d / Line2d System_* class
+ * (ref: Line1d.h:134-147,199-211,348-362,394-407,451-465,585-599,643-657; Line2d.h:88-101,133-147) */
+typedef struct {
+    int32_t potential;    /* fqsb_potential */
+    int32_t interactions; /* fqsb_interactions */
+    int32_t minimisation; /* fqsb_minimisation */
+    int32_t rank;         /* 1 (Line1d) or 2 (Line2d) */
+    int64_t shape[2];     /* [N, 1] or [rows, cols] */
+    double m, eta, mu, kappa;
+    double k1; /* k_interactions | a1 | k2 */
+    double k2; /* a2 | k4 | alpha */
+    double k_frame, dt;
+    uint64_t seed;
+    int32_t distribution; /* fqsb_distribution */
+    int32_t nparameters;
+    double parameters[4];
+    double offset;  /* default -100 in the reference */
+    int64_t nchunk; /* default 5000; only sizes fqsb_chunk_data (the device keeps no chunk) */
+    /* --- new surface (the reference has no ensemble class) --- */
+    int64_t nrealisations; /* 0 is read as 1 */
+    int64_t seed_stride;   /* 0 is read as prod(shape) */
+    int32_t device;        /* CUDA ordinal; -1 = current device */
+    int32_t kernel;        /* 0 auto, 1 force resident (one CTA per realisation), 2 force streaming */
+} fqsb_params;
+
+typedef struct fqsb_system fqsb_system;
+
+/* library ------------------------------------------------------------------------------- */
+const char* fqsb_last_error(void);
+int fqsb_abi_version(void);
+const char* fqsb_version(void); /* ref: config.h:209-212 */
+int fqsb_device_count(void);
+
+/* lifetime (ref: Line1d.h:134-161 ctor body + detail.h:1096-1139 initSystem) ------------- */
+int fqsb_create(const fqsb_params* params, fqsb_system** out);
+void fqsb_destroy(fqsb_system* s);
+int fqsb_get_params(const fqsb_system* s, fqsb_params* out);
+int64_t fqsb_size(const fqsb_system* s);          /* blocks per realisation, ref: detail.h:1155 */
+int64_t fqsb_nrealisations(const fqsb_system* s);
+/* run all later work of this handle on an existing cudaStream_t (e.g. torch's current one) */
+int fqsb_set_stream(fqsb_system* s, void* cuda_stream);
+void* fqsb_get_stream(const fqsb_system* s);
+
+/* state in (ref: detail.h:1231-1315) ---------------------------------------------------- */
+int fqsb_set_u(fqsb_system* s, const double* u, int64_t n);  /* + updated_u(),  ref: 1276-1281 */
+int fqsb_set_v(fqsb_system* s, const double* v, int64_t n);  /* + updated_v(),  ref: 1290-1295 */
+int fqsb_set_a(fqsb_system* s, const double* a, int64_t n);  /*                 ref: 1301-1305 */
+int fqsb_set_u_frame(fqsb_system* s, const double* u_frame); /* [R]             ref: 1253-1258 */
+int fqsb_set_inc(fqsb_system* s, const int64_t* inc);        /* [R]             ref: 1241-1247 */
+int fqsb_set_t(fqsb_system* s, const double* t);             /* [R]             ref: 1231-1235 */
+int fqsb_refresh(fqsb_system* s);                            /*                 ref: 1310-1315 */
+int fqsb_quench(fqsb_system* s);                             /*                 ref: 1527-1532 */
+
+/* state out (ref: detail.h:1402-1520) --------------------------------------------------- */
+typedef enum {
+    FQSB_U = 0,
+    FQSB_V = 1,
+    FQSB_A = 2,
+    FQSB_F = 3,
+    FQSB_F_POTENTIAL = 4,
+    FQSB_F_FRAME = 5,
+    FQSB_F_INTERACTIONS = 6,
+    FQSB_F_DAMPING = 7
+} fqsb_array;
+int fqsb_get(fqsb_system* s, int which, double* out, int64_t n); /* ref: 1402-1468 */
+/* device-resident view of the same arrays (valid until the next call on the handle) */
+int fqsb_get_device(fqsb_system* s, int which, const double** out_device);
+int fqsb_get_u_frame(fqsb_system* s, double* out);     /* [R]  ref: 1264-1267 */
+int fqsb_get_inc(fqsb_system* s, int64_t* out);        /* [R]  ref: 1486-1489 */
+int fqsb_get_t(fqsb_system* s, double* out);           /* [R]  ref: 1477-1480 */
+int fqsb_residual(fqsb_system* s, double* out);        /* [R]  ref: 1512-1520 */
+int fqsb_temperature(fqsb_system* s, double* out);     /* [R]  ref: 1500-1503 */
+int fqsb_mean_f_frame(fqsb_system* s, double* out);    /* [R]  np.mean(system.f_frame) of the examples */
+int fqsb_qs_activity(fqsb_system* s, int64_t* first, int64_t* last); /* [R] ref: 1802-1818 */
+
+/* dynamics (ref: detail.h:1539-1645) ---------------------------------------------------- */
+int fqsb_time_steps(fqsb_system* s, int64_t n);                  /* timeStep/timeSteps, ref: 1539-1583 */
+int fqsb_flow_steps(fqsb_system* s, int64_t n, double v_frame);  /* ref: 1637-1645 */
+/* ret [R]: step of the first well change, 0 if converged, max_iter+1 otherwise. ref: 1595-1622 */
+int fqsb_time_steps_until_event(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_iter,
+                                int64_t* ret);
+
+/* minimisation (ref: detail.h:1676-1893) ------------------------------------------------ */
+/* ret [R]: 0 if converged, max_iter+1 otherwise (only reachable with max_iter_is_error == 0).
+ * Dynamic systems: velocity-Verlet until the StopList criterion (ref: 1754-1785);
+ * Overdamped systems: no-passing Jacobi sweeps (ref: 1694-1753). */
+int fqsb_minimise(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_iter,
+                  int time_activity, int max_iter_is_error, int64_t* ret);
+/* i_n [R][size]; ret [R]. ref: 1833-1893 */
+int fqsb_minimise_truncate(fqsb_system* s, const int64_t* i_n, int64_t A_truncate,
+                           int64_t S_truncate, double tol, int64_t niter_tol, int64_t max_iter,
+                           int time_activity, int max_iter_is_error, int64_t* ret);
+
+/* event-driven protocol (ref: detail.h:1901-2050) --------------------------------------- */
+int fqsb_max_uniform_displacement(fqsb_system* s, int direction, double* out); /* [R] ref: 1901-1905 */
+int fqsb_event_driven_step(fqsb_system* s, double eps, int kick, int direction,
+                           double* du_frame);                                   /* [R] ref: 1933-1960 */
+int fqsb_trigger(fqsb_system* s, int64_t realisation, int64_t p, double eps, int direction); /* ref: 1972-1977 */
+int fqsb_advance_to_fixed_force(fqsb_system* s, const double* f_frame, int allow_plastic);   /* [R] ref: 1988-1995 */
+
+/* yield landscape = the prrng::pcg32_tensor_cumsum object `system.chunk`
+ * (absent third-party; call sites ref: detail.h:144-160,183-186,1602,1609,1725-1733,
+ *  tests/test_Line1d.py:83-86,309-326) -------------------------------------------------- */
+int fqsb_chunk_index_at_align(fqsb_system* s, int64_t* out, int64_t n); /* global well index i */
+int fqsb_chunk_left_of_align(fqsb_system* s, double* out, int64_t n);   /* y[i]   */
+int fqsb_chunk_right_of_align(fqsb_system* s, double* out, int64_t n);  /* y[i+1] */
+/* y[p, first[p] + j], j < nyield, row-major [R*size][nyield]; first [R*size] >= 0 */
+int fqsb_chunk_data(fqsb_system* s, const int64_t* first, int64_t nyield, double* out);
+/* pcg32 state positioned so that the next draw is global draw index[p] */
+int fqsb_chunk_state_at(fqsb_system* s, const int64_t* index, uint64_t* state, int64_t n);
+/* restart: y[index[p]] = value[p] with generator state[p] (as from state_at), then re-align */
+int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* value,
+                       const int64_t* index, int64_t n);
+/* signed well-index change since `i_n` summed per realisation (the examples' S) and the number
+ * of blocks that changed (A): out_S [R], out_A [R] (either may be NULL) */
+int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A);
+
+/* host staging helpers (pinned memory for the e2e path) ---------------------------------- */
+void* fqsb_host_alloc(size_t bytes);
+void fqsb_host_free(void* p);
+
+/* instrumentation: kernels launched / steps executed by this handle since creation */
+int64_t fqsb_launch_count(const fqsb_system* s);
+int64_t fqsb_step_count(const fqsb_system* s);
+/* name of the stepping kernel the last dynamics call used ("resident", "stream", ...) */
+const char* fqsb_last_kernel(const fqsb_system* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQSB_H */

@@ -1,0 +1,253 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeds.
+
+Bars: well indices, S, A bit-exact; u, v, a, forces over a fixed number
+of steps within 1e-12 relative -- and in fact bit-identical for every polynomial force law,
+because both sides evaluate the reference's expressions in the same order without FMA.
+"""
+
+import numpy as np
+import pytest
+
+from tests import protocol
+from tests.helpers import assert_same_state, pair, product
+
+pytestmark = pytest.mark.gpu
+
+PHYS = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, dt=0.1, seed=3, distribution="random",
+            parameters=[2.0], offset=-50)
+
+SYSTEMS_1D = [
+    ("System_Cuspy_Laplace", dict(k_interactions=1.0), True),
+    ("System_Cuspy_Quartic", dict(a1=1.0, a2=0.7), True),
+    ("System_Cuspy_QuarticGradient", dict(k2=1.0, k4=0.3), True),
+    ("System_Cuspy_LongRange", dict(k_interactions=1.0, alpha=1.5), True),
+    ("System_SemiSmooth_Laplace", dict(k_interactions=1.0, kappa=0.9), True),
+    ("System_Smooth_Laplace", dict(k_interactions=1.0), False),  # sin(): 1e-12, not bit-exact
+]
+
+
+def kicked(o, p):
+    """minimise, then kick: an avalanche is under way in both systems."""
+    for s in (o, p):
+        assert s.minimise() == 0
+        s.eventDrivenStep(1e-3, False)
+        s.eventDrivenStep(1e-3, True)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("cls,extra,exact", SYSTEMS_1D, ids=[s[0] for s in SYSTEMS_1D])
+@pytest.mark.parametrize("N", [7, 300, 1000])
+def test_fixed_steps_line1d(cls, extra, exact, N, kernel):
+    o, p = pair("Line1d", cls, shape=[N], k_frame=1.0 / N, kernel=kernel, **extra, **PHYS)
+    assert_same_state(o, p, exact)
+    if cls == "System_Smooth_Laplace":
+        for s in (o, p):  # no event-driven protocol for the smooth potential (detail.h:420)
+            s.u_frame = 3.0
+    else:
+        kicked(o, p)
+    for n in (1, 2, 37, 160):
+        o.timeSteps(n)
+        p.timeSteps(n)
+        assert_same_state(o, p, exact)
+    assert p.last_kernel == ("resident" if kernel == 1 else "stream")
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("cls,extra", [("System_Cuspy_Laplace", dict(k_interactions=1.0)),
+                                       ("System_Cuspy_QuarticGradient", dict(k2=1.0, k4=0.3))])
+@pytest.mark.parametrize("shape", [[5, 4], [50, 50], [37, 61]])
+def test_fixed_steps_line2d(cls, extra, shape, kernel):
+    n = shape[0] * shape[1]
+    o, p = pair("Line2d", cls, shape=shape, k_frame=1.0 / n, kernel=kernel, **extra, **PHYS)
+    kicked(o, p)
+    for nstep in (1, 50, 111):
+        o.timeSteps(nstep)
+        p.timeSteps(nstep)
+        assert_same_state(o, p)
+
+
+def test_large_resident_configurations():
+    """every blocks-per-thread configuration of the resident kernel (N up to 8192)."""
+    for N in (256, 257, 1024, 1025, 2048, 2049, 4096, 4097, 8192):
+        o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N,
+                    k_interactions=1.0, kernel=1, **PHYS)
+        for s in (o, p):
+            s.u_frame = 2.5
+            s.timeSteps(64)
+        assert_same_state(o, p)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+def test_minimise_and_event_driven_match_oracle(kernel):
+    N = 400
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
+                kernel=kernel, **PHYS)
+    for step in range(30):
+        i_n = o.chunk.index_at_align
+        if step > 0:
+            du_o = o.eventDrivenStep(1e-3, step % 2 == 0)
+            du_p = p.eventDrivenStep(1e-3, step % 2 == 0)
+            assert du_o == du_p
+        if step % 2 == 0:
+            assert o.minimise() == 0
+            assert p.minimise() == 0
+        # identical stopping step => identical state; a +-1 step difference of the stop test
+        # (different summation order of the residual) would show up in `inc`
+        assert o.inc == p.inc
+        assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+        assert np.array_equal(o.u, p.u)
+        assert o.u_frame == p.u_frame
+        S, A = p.avalanche(i_n)
+        assert S == np.sum(o.chunk.index_at_align - i_n)
+        assert A == np.sum(o.chunk.index_at_align != i_n)
+        assert np.isclose(o.residual, p.residual, rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+def test_time_steps_until_event(kernel):
+    N = 300
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
+                kernel=kernel, **PHYS)
+    kicked(o, p)
+    seen = set()
+    for _ in range(40):
+        ro = o.timeStepsUntilEvent()
+        rp = p.timeStepsUntilEvent()
+        assert ro == rp
+        seen.add(ro > 0)
+        assert_same_state(o, p)
+        if ro == 0:
+            for s in (o, p):
+                s.eventDrivenStep(1e-3, False)
+                s.eventDrivenStep(1e-3, True)
+    assert seen == {True, False}
+    # max_iter reached without event: returns max_iter + 1 (quirk Q4, detail.h:1621)
+    for s in (o, p):
+        s.eventDrivenStep(1e-3, False)
+    assert o.timeStepsUntilEvent(max_iter=3) == p.timeStepsUntilEvent(max_iter=3)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+def test_minimise_truncate_and_activity(kernel):
+    N = 500
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
+                kernel=kernel, **PHYS)
+    for s in (o, p):
+        assert s.minimise() == 0
+    for A_t, S_t in [(5, 0), (0, 12), (40, 100), (0, 0)]:
+        for s in (o, p):
+            s.eventDrivenStep(1e-3, False)
+            s.eventDrivenStep(1e-3, True)
+        i_n = o.chunk.index_at_align
+        ro = o.minimise_truncate(i_n=i_n, A_truncate=A_t, S_truncate=S_t)
+        rp = p.minimise_truncate(i_n=i_n, A_truncate=A_t, S_truncate=S_t)
+        assert ro == rp
+        assert o.quasistaticActivityFirst == p.quasistaticActivityFirst
+        assert o.quasistaticActivityLast == p.quasistaticActivityLast
+        assert_same_state(o, p)
+        ro = o.minimise(time_activity=True)
+        rp = p.minimise(time_activity=True)
+        assert ro == rp == 0
+        assert o.quasistaticActivityFirst == p.quasistaticActivityFirst
+        assert o.quasistaticActivityLast == p.quasistaticActivityLast
+        assert_same_state(o, p)
+
+
+def test_flow_steps_and_temperature():
+    N = 256
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0, k_interactions=1.0,
+                **{**PHYS, "eta": 0.1})
+    for v_frame in (0.1, 1.3):
+        o.flowSteps(200, v_frame)
+        p.flowSteps(200, v_frame)
+        assert_same_state(o, p)
+        assert np.isclose(o.temperature, p.temperature, rtol=1e-12)
+
+
+def test_no_convergence_and_nan_errors():
+    F = product()
+    N = 64
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, **PHYS)
+    p = F.Line1d.System_Cuspy_Laplace(**kw)
+    p.eventDrivenStep(1e-3, True)
+    with pytest.raises(RuntimeError, match="No convergence found"):  # detail.h:1788
+        p.minimise(max_iter=3)
+    assert p.minimise(max_iter=3, max_iter_is_error=False) == 4  # quirk Q4
+    with pytest.raises(RuntimeError, match="tol < 1.0"):
+        p.minimise(tol=2.0)
+    u = p.u
+    u[3] = np.nan
+    p.u = u
+    with pytest.raises(RuntimeError, match="NaN entries found"):  # detail.h:1568
+        p.timeStep()
+    s = F.Line1d.System_Smooth_Laplace(**kw)
+    with pytest.raises(RuntimeError, match="Operation not possible."):  # detail.h:420
+        s.eventDrivenStep(1e-3, False)
+    with pytest.raises(RuntimeError, match="has_shape"):
+        p.u = np.zeros(N + 1)
+    with pytest.raises(RuntimeError, match="Deprecated, use 'u'"):
+        p.x
+
+
+@pytest.mark.parametrize("name,nstep", [
+    ("Line1d_Cuspy_Laplace", 100),
+    ("Line1d_Cuspy_Laplace_Nopassing", 1000),
+    ("Line1d_Cuspy_Quartic", 100),
+    ("Line1d_SemiSmooth_Laplace", 400),
+    ("Line1d_Cuspy_Laplace_LongRange", 20),
+    ("Line2d_Cuspy_Laplace", 60),
+])
+def test_golden_protocol_on_gpu(name, nstep, golden_dir):
+    """The reference's own regression: examples/<name>.py against its committed .h5."""
+    F = product()
+    golden = np.load(golden_dir / f"{name}.npz")
+    system = protocol.make(F.Line1d, F.Line2d, name)
+    protocol.check(golden, *protocol.run(system, nstep))
+
+
+def test_nopassing_matches_oracle_1d_and_2d():
+    base = dict(mu=1.0, k_interactions=1.0, seed=11, distribution="random", parameters=[2.0],
+                offset=-50)
+    for module, shape, kernel in [("Line1d", [333], 1), ("Line1d", [333], 2),
+                                  ("Line2d", [24, 31], 1), ("Line2d", [24, 31], 2)]:
+        n = int(np.prod(shape))
+        o, p = pair(module, "System_Cuspy_Laplace_Nopassing", shape=shape, k_frame=1.0 / n,
+                    kernel=kernel, **base)
+        for step in range(60):
+            if step > 0:
+                assert o.eventDrivenStep(1e-3, step % 2 == 0) == \
+                    p.eventDrivenStep(1e-3, step % 2 == 0)
+            if step % 2 == 0:
+                assert o.minimise() == p.minimise() == 0
+            assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+            assert np.array_equal(o.u, p.u)
+        assert np.allclose(o.f, p.f, rtol=1e-12, atol=1e-15)
+        # fixed point of the full force balance
+        assert p.residual < 1e-5
+
+
+def test_ensemble_equals_independent_systems():
+    F = product()
+    N, R = 128, 5
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, **PHYS)
+    ens = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=R, **kw)
+    singles = [F.Line1d.System_Cuspy_Laplace(**{**kw, "seed": PHYS["seed"] + r * N})
+               for r in range(R)]
+    assert ens.minimise().tolist() == [0] * R
+    for s in singles:
+        assert s.minimise() == 0
+    ens.eventDrivenStep(1e-3, False)
+    du = ens.eventDrivenStep(1e-3, True)
+    for r, s in enumerate(singles):
+        s.eventDrivenStep(1e-3, False)
+        assert s.eventDrivenStep(1e-3, True) == du[r]
+    ens.timeSteps(77)
+    ret = ens.minimise()
+    for r, s in enumerate(singles):
+        s.timeSteps(77)
+        assert s.minimise() == ret[r] == 0
+        assert np.array_equal(ens.u[r], s.u)
+        assert np.array_equal(ens.chunk.index_at_align[r], s.chunk.index_at_align)
+        assert ens.inc[r] == s.inc
+        assert ens.u_frame[r] == s.u_frame
+    assert len(set(ens.inc.tolist())) > 1  # realisations stop at their own step
