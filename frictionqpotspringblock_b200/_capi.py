@@ -119,6 +119,8 @@ SIGNATURES = {
     "fqsb_launch_count": (C.c_int64, [_P]),
     "fqsb_step_count": (C.c_int64, [_P]),
     "fqsb_last_kernel": (C.c_char_p, [_P]),
+    "fqsb_last_kernel_seconds": (C.c_double, [_P]),
+    "fqsb_last_kernel_launches": (C.c_int64, [_P]),
 }
 
 

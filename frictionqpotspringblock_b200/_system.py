@@ -338,6 +338,14 @@ class Ensemble:
     def last_kernel(self):
         return lib.fqsb_last_kernel(self._h).decode()
 
+    @property
+    def last_kernel_seconds(self):
+        return float(lib.fqsb_last_kernel_seconds(self._h))
+
+    @property
+    def last_kernel_launches(self):
+        return int(lib.fqsb_last_kernel_launches(self._h))
+
     def set_stream(self, cuda_stream: int):
         check(lib.fqsb_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 

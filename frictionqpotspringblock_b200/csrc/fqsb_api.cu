@@ -68,6 +68,9 @@ struct fqsb_system {
     double* d_pref;
     i64 launches, steps;
     const char* last_kernel;
+    cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
+    double kernel_ms;        // device time between them, summed over the call's launches
+    i64 kernel_launches;     // stepping-kernel launches of the last dynamics call
     std::vector<void*> allocs;
 };
 
@@ -307,6 +310,9 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->launches = 0;
     s->steps = 0;
     s->last_kernel = "";
+    s->ev0 = s->ev1 = nullptr;
+    s->kernel_ms = 0.0;
+    s->kernel_launches = 0;
     memset(&s->F, 0, sizeof s->F);
     memset(&s->S, 0, sizeof s->S);
 
@@ -357,6 +363,8 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     int rc = FQSB_OK;
     auto build = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s->ev0));
+        CU(cudaEventCreate(&s->ev1));
         State& S = s->S;
         const size_t n = (size_t)s->n;
         TRY(dev_alloc(s, &S.u, n));
@@ -439,6 +447,12 @@ void fqsb_destroy(fqsb_system* s)
     if (s->own_stream && s->stream) {
         cudaStreamDestroy(s->stream);
     }
+    if (s->ev0) {
+        cudaEventDestroy(s->ev0);
+    }
+    if (s->ev1) {
+        cudaEventDestroy(s->ev1);
+    }
     cudaGetLastError();
     delete s;
 }
@@ -471,6 +485,8 @@ void* fqsb_get_stream(const fqsb_system* s) { return s ? (void*)s->stream : null
 int64_t fqsb_launch_count(const fqsb_system* s) { return s ? s->launches : 0; }
 int64_t fqsb_step_count(const fqsb_system* s) { return s ? s->steps : 0; }
 const char* fqsb_last_kernel(const fqsb_system* s) { return s ? s->last_kernel : ""; }
+double fqsb_last_kernel_seconds(const fqsb_system* s) { return s ? 1e-3 * s->kernel_ms : 0.0; }
+int64_t fqsb_last_kernel_launches(const fqsb_system* s) { return s ? s->kernel_launches : 0; }
 
 // ---- state in ---------------------------------------------------------------------------------
 static int upload(fqsb_system* s, double* dst, const double* src, int64_t n)
@@ -761,6 +777,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
                                            s->d_out);
     CU(cudaGetLastError());
     s->launches++;
+    s->kernel_ms = 0.0;
+    s->kernel_launches = 0;
     invalidate_forces(s);
     if (A.max_steps <= 0) {
         TRY(pull_ctl(s));
@@ -776,13 +794,21 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         const i64 chunk = (i64)1 << 20;
         for (;;) {
             A.launch_steps = A.max_steps < chunk ? A.max_steps : chunk;
+            CU(cudaEventRecord(s->ev0, s->stream));
             cudaError_t e = overdamped ? launch_resident_nopassing(cfg, s->P, s->S, A, s->stream)
                                        : launch_resident(cfg, s->P, s->S, A, s->stream);
             if (e != cudaSuccess) {
                 return cuda_fail(e, "resident kernel launch");
             }
+            CU(cudaEventRecord(s->ev1, s->stream));
             s->launches++;
+            s->kernel_launches++;
             TRY(pull_ctl(s));
+            {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                s->kernel_ms += ms;
+            }
             bool running = false;
             for (i64 r = 0; r < s->R; ++r) {
                 running |= s->h_ctl[r].status == ST_RUNNING;
@@ -803,6 +829,7 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         for (;;) {
             i64 nb = A.mode == MODE_FIXED ? (remaining < 2048 ? remaining : 2048)
                                           : (remaining < batch ? remaining : batch);
+            CU(cudaEventRecord(s->ev0, s->stream));
             for (i64 b = 0; b < nb; ++b) {
                 cudaError_t e = overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream)
                                            : launch_stream_step(s->P, s->S, A, s->stream);
@@ -810,9 +837,16 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
                     return cuda_fail(e, "stream kernel launch");
                 }
             }
+            CU(cudaEventRecord(s->ev1, s->stream));
             s->launches += overdamped ? 2 * nb : nb;
+            s->kernel_launches += overdamped ? 2 * nb : nb;
             remaining -= nb;
             TRY(pull_ctl(s));
+            {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                s->kernel_ms += ms;
+            }
             bool running = false;
             for (i64 r = 0; r < s->R; ++r) {
                 running |= s->h_ctl[r].status == ST_RUNNING;

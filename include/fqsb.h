@@ -199,6 +199,10 @@ int64_t fqsb_launch_count(const fqsb_system* s);
 int64_t fqsb_step_count(const fqsb_system* s);
 /* name of the stepping kernel the last dynamics call used ("resident", "stream", ...) */
 const char* fqsb_last_kernel(const fqsb_system* s);
+/* device time (CUDA events on the handle's stream) spent in the stepping-kernel launches of the
+ * last dynamics call, and how many launches that was */
+double fqsb_last_kernel_seconds(const fqsb_system* s);
+int64_t fqsb_last_kernel_launches(const fqsb_system* s);
 
 #ifdef __cplusplus
 }

@@ -1325,89 +1325,106 @@ int orc_chunk_restore(orc_system* s, const uint64_t* state, const double* value,
 }
 
 /* ------------------------------------------------------------------------------------------
- * bounded multi-threaded CPU arm (bench.py cpu_baseline / --impl reference)
+ * bounded multi-threaded CPU arm (bench.py cpu_baseline / --impl reference):
+ * `nsys` independent lines (seed = seed0 + r*N), one realisation per thread round-robin,
+ * prepared by minimise() + eventDrivenStep(kick) and then advanced by timeSteps(n).
  * ---------------------------------------------------------------------------------------- */
-typedef struct {
-    const orc_params* par;
-    int64_t nsys, nsteps;
-    int tid, nthreads;
+struct orc_ensemble {
+    orc_params par;
+    int64_t nsys;
+    int nthreads;
     orc_system** sys;
+};
+
+typedef struct {
+    orc_ensemble* e;
+    int tid;
+    int64_t nsteps;
+    int prepare;
     double checksum;
-} bench_arg;
+} ens_arg;
 
-static void* bench_prepare(void* vp)
+static void* ens_worker(void* vp)
 {
-    bench_arg* a = (bench_arg*)vp;
-    for (int64_t r = a->tid; r < a->nsys; r += a->nthreads) {
-        orc_params par = *a->par;
-        par.seed = a->par->seed + (uint64_t)(r * par.shape[0] * (par.rank == 2 ? par.shape[1] : 1));
-        orc_system* s = NULL;
-        if (orc_create(&par, &s) != ORC_OK) {
-            continue;
-        }
-        int64_t ret;
-        double du;
-        orc_minimise(s, 1e-5, 10, 1000000000LL, 0, 0, &ret);
-        orc_event_driven_step(s, 1e-3, 0, 1, &du);
-        orc_event_driven_step(s, 1e-3, 1, 1, &du);
-        a->sys[r] = s;
-    }
-    return NULL;
-}
-
-static void* bench_run(void* vp)
-{
-    bench_arg* a = (bench_arg*)vp;
+    ens_arg* a = (ens_arg*)vp;
+    orc_ensemble* e = a->e;
     double cs = 0.0;
-    for (int64_t r = a->tid; r < a->nsys; r += a->nthreads) {
-        orc_system* s = a->sys[r];
-        if (!s) {
-            continue;
+    for (int64_t r = a->tid; r < e->nsys; r += e->nthreads) {
+        if (a->prepare) {
+            orc_params par = e->par;
+            int64_t n = par.shape[0] * (par.rank == 2 ? par.shape[1] : 1);
+            par.seed = e->par.seed + (uint64_t)(r * n);
+            orc_system* s = NULL;
+            if (orc_create(&par, &s) != ORC_OK) {
+                continue;
+            }
+            int64_t ret;
+            double du;
+            orc_minimise(s, 1e-5, 10, 1000000000LL, 0, 0, &ret);
+            orc_event_driven_step(s, 1e-3, 0, 1, &du);
+            orc_event_driven_step(s, 1e-3, 1, 1, &du);
+            e->sys[r] = s;
         }
-        orc_time_steps(s, a->nsteps);
-        for (int64_t p = 0; p < s->N; ++p) {
-            cs += s->u[p];
+        else if (e->sys[r]) {
+            orc_system* s = e->sys[r];
+            orc_time_steps(s, a->nsteps);
+            for (int64_t p = 0; p < s->N; ++p) {
+                cs += s->u[p];
+            }
         }
     }
     a->checksum = cs;
     return NULL;
 }
 
-double orc_bench_ensemble(const orc_params* par, int64_t nsys, int64_t nsteps, int nthreads,
-                          double* checksum)
+static double ens_run(orc_ensemble* e, int prepare, int64_t nsteps, double* checksum)
 {
-    if (nthreads < 1) {
-        nthreads = 1;
-    }
-    orc_system** sys = (orc_system**)calloc((size_t)nsys, sizeof(orc_system*));
-    pthread_t* th = (pthread_t*)malloc((size_t)nthreads * sizeof(pthread_t));
-    bench_arg* args = (bench_arg*)calloc((size_t)nthreads, sizeof(bench_arg));
-    for (int t = 0; t < nthreads; ++t) {
-        args[t] = (bench_arg){par, nsys, nsteps, t, nthreads, sys, 0.0};
-        pthread_create(&th[t], NULL, bench_prepare, &args[t]);
-    }
-    for (int t = 0; t < nthreads; ++t) {
-        pthread_join(th[t], NULL);
-    }
+    pthread_t* th = (pthread_t*)malloc((size_t)e->nthreads * sizeof(pthread_t));
+    ens_arg* args = (ens_arg*)calloc((size_t)e->nthreads, sizeof(ens_arg));
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    for (int t = 0; t < nthreads; ++t) {
-        pthread_create(&th[t], NULL, bench_run, &args[t]);
+    for (int t = 0; t < e->nthreads; ++t) {
+        args[t] = (ens_arg){e, t, nsteps, prepare, 0.0};
+        pthread_create(&th[t], NULL, ens_worker, &args[t]);
     }
     double cs = 0.0;
-    for (int t = 0; t < nthreads; ++t) {
+    for (int t = 0; t < e->nthreads; ++t) {
         pthread_join(th[t], NULL);
         cs += args[t].checksum;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    for (int64_t r = 0; r < nsys; ++r) {
-        orc_destroy(sys[r]);
-    }
-    free(sys);
     free(th);
     free(args);
     if (checksum) {
         *checksum = cs;
     }
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+orc_ensemble* orc_ensemble_create(const orc_params* par, int64_t nsys, int nthreads)
+{
+    orc_ensemble* e = (orc_ensemble*)calloc(1, sizeof *e);
+    e->par = *par;
+    e->nsys = nsys;
+    e->nthreads = nthreads < 1 ? 1 : nthreads;
+    e->sys = (orc_system**)calloc((size_t)nsys, sizeof(orc_system*));
+    ens_run(e, 1, 0, NULL);
+    return e;
+}
+
+double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum)
+{
+    return ens_run(e, 0, nsteps, checksum);
+}
+
+void orc_ensemble_destroy(orc_ensemble* e)
+{
+    if (!e) {
+        return;
+    }
+    for (int64_t r = 0; r < e->nsys; ++r) {
+        orc_destroy(e->sys[r]);
+    }
+    free(e->sys);
+    free(e);
 }

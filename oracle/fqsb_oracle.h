@@ -140,12 +140,14 @@ int orc_chunk_restore(orc_system* s, const uint64_t* state, const double* value,
 void orc_pcg32_draws(uint64_t initstate, uint64_t initseq, int64_t n, double* out);
 double orc_draw_to_spacing(double r, int32_t distribution, const double* par);
 
-/* bounded multi-threaded CPU arm for bench.py: `nsys` independent System_Cuspy_Laplace
- * lines of N blocks (seed = seed0 + r*N), kicked once by eventDrivenStep(eps,true) after a
- * minimise(), then timeSteps(nsteps) each; one realisation per thread round-robin.
- * Returns wall seconds of the timeSteps phase only. */
-double orc_bench_ensemble(const orc_params* par, int64_t nsys, int64_t nsteps, int nthreads,
-                          double* checksum);
+/* bounded multi-threaded CPU arm for bench.py: `nsys` independent lines (seed = seed0 + r*N),
+ * one realisation per thread round-robin; create() prepares them with minimise() and one
+ * eventDrivenStep kick (untimed); time_steps() advances all of them by timeSteps(nsteps) and
+ * returns the wall seconds that took. */
+typedef struct orc_ensemble orc_ensemble;
+orc_ensemble* orc_ensemble_create(const orc_params* par, int64_t nsys, int nthreads);
+double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum);
+void orc_ensemble_destroy(orc_ensemble* e);
 
 #ifdef __cplusplus
 }

@@ -89,7 +89,11 @@ def lib():
         L.orc_qs_last.restype = C.c_int64
         L.orc_draw_to_spacing.restype = C.c_double
         L.orc_draw_to_spacing.argtypes = [C.c_double, C.c_int32, C.c_void_p]
-        L.orc_bench_ensemble.restype = C.c_double
+        L.orc_ensemble_create.restype = C.c_void_p
+        L.orc_ensemble_create.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        L.orc_ensemble_time_steps.restype = C.c_double
+        L.orc_ensemble_time_steps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_ensemble_destroy.argtypes = [C.c_void_p]
         L.orc_set_u_frame.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_t.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_inc.argtypes = [C.c_void_p, C.c_int64]
@@ -120,7 +124,6 @@ def lib():
                      "orc_qs_first", "orc_qs_last"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_create.argtypes = [C.c_void_p, C.c_void_p]
-        L.orc_bench_ensemble.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -395,7 +398,19 @@ Line2d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient2d", "k2", "k
 Line2d.System_Cuspy_Laplace_Nopassing = _mk("Cuspy", "Laplace2d", "k_interactions", minimisation=1)
 
 
-def bench_ensemble(par: Params, nsys: int, nsteps: int, nthreads: int):
-    cs = C.c_double()
-    sec = lib().orc_bench_ensemble(C.byref(par), nsys, nsteps, nthreads, C.byref(cs))
-    return sec, cs.value
+class CpuEnsemble:
+    """`nsys` independent oracle lines advanced by a thread pool (bench.py's CPU arm)."""
+
+    def __init__(self, par: Params, nsys: int, nthreads: int):
+        self.nsys, self.nthreads = int(nsys), int(nthreads)
+        self._e = lib().orc_ensemble_create(C.byref(par), self.nsys, self.nthreads)
+
+    def time_steps(self, nsteps: int):
+        cs = C.c_double()
+        sec = lib().orc_ensemble_time_steps(self._e, int(nsteps), C.byref(cs))
+        return sec, cs.value
+
+    def __del__(self):
+        if getattr(self, "_e", None):
+            lib().orc_ensemble_destroy(self._e)
+            self._e = None
