@@ -747,8 +747,8 @@ __global__ void k_ctl_begin(const Par P, const State S, int track_user, int over
 
 static bool use_resident(const fqsb_system* s, ResidentCfg* cfg)
 {
-    *cfg = resident_cfg(s->N);
-    if (s->par.kernel == 2 || cfg->B == 0) {
+    *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
+    if ((s->par.kernel & 15) == 2 || cfg->B == 0) {
         return false;
     }
     return resident_smem(s->P, *cfg) <= 227 * 1024;
@@ -819,28 +819,39 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         }
     }
     else {
-        if (s->par.kernel == 1) {
+        if ((s->par.kernel & 15) == 1) {
             return fail(FQSB_EUNSUPPORTED, "system too large for the resident kernel");
         }
         TRY(ensure_stream_buffers(s));
-        s->last_kernel = overdamped ? "stream_nopassing" : "stream";
+        s->last_kernel = overdamped ? "stream_nopassing" : stream_step_name(s->P);
+        // fixed-step calls without a moving frame need no per-step decision on the device
+        const int finalise = (A.mode != MODE_FIXED || A.flow) ? 1 : 0;
         i64 remaining = A.max_steps; // upper bound on launches still useful
+        i64 launched = 0;
         i64 batch = 16;
         for (;;) {
             i64 nb = A.mode == MODE_FIXED ? (remaining < 2048 ? remaining : 2048)
                                           : (remaining < batch ? remaining : batch);
             CU(cudaEventRecord(s->ev0, s->stream));
             for (i64 b = 0; b < nb; ++b) {
-                cudaError_t e = overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream)
-                                           : launch_stream_step(s->P, s->S, A, s->stream);
+                cudaError_t e = overdamped
+                                    ? launch_stream_sweep(s->P, s->S, A, s->stream)
+                                    : launch_stream_step(s->P, s->S, A, s->stream,
+                                                         (int)((launched + b) & 1), finalise);
                 if (e != cudaSuccess) {
                     return cuda_fail(e, "stream kernel launch");
                 }
             }
             CU(cudaEventRecord(s->ev1, s->stream));
+            launched += nb;
             s->launches += overdamped ? 2 * nb : nb;
             s->kernel_launches += overdamped ? 2 * nb : nb;
             remaining -= nb;
+            if (!finalise && !overdamped && remaining <= 0) {
+                k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, A.max_steps);
+                CU(cudaGetLastError());
+                s->launches++;
+            }
             TRY(pull_ctl(s));
             {
                 float ms = 0.f;

@@ -35,6 +35,19 @@ __global__ void k_stream_settle(const Par P, const State S, int with_va)
     }
 }
 
+// fixed-step streaming calls keep no per-step bookkeeping on the device: settle it at the end
+__global__ void k_stream_fixed_done(const Par P, const State S, i64 nsteps)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P.R) {
+        Ctl& c = S.ctl[r];
+        c.inc += nsteps; // detail.h:1541
+        c.steps = nsteps;
+        c.flip = (int)(nsteps & 1);
+        c.status = ST_EXHAUSTED;
+    }
+}
+
 __global__ void k_stream_settle_flags(const Par P, const State S)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -9,6 +9,8 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace fqsb {
@@ -212,11 +214,13 @@ __host__ __device__ __forceinline__ int well_align(const Par& P, double u, doubl
 // ---- potentials -----------------------------------------------------------------------------
 enum { POT_CUSPY = 0, POT_SEMISMOOTH = 1, POT_SMOOTH = 2 };
 
-template <int POT>
+// UNIT: the caller guarantees mu == 1, m == 1 and k1 == 1 exactly, so the multiplications by
+// those parameters (x * 1.0 == x in IEEE-754) are skipped without changing a single bit.
+template <int POT, bool UNIT = false>
 __device__ __forceinline__ double f_potential(const Par& P, double u, double yl, double yr)
 {
     if (POT == POT_CUSPY) { // detail.h:164-169
-        return (0.5 * (yl + yr) - u) * P.mu;
+        return UNIT ? (0.5 * (yl + yr) - u) : (0.5 * (yl + yr) - u) * P.mu;
     }
     else if (POT == POT_SEMISMOOTH) { // detail.h:261-276
         double xi = 0.5 * (yl + yr);
@@ -256,7 +260,8 @@ enum { INT_NONE = 0, INT_LAPLACE1D = 1, INT_QUARTIC1D = 2, INT_QUARTICGRADIENT1D
 
 // U(q): slip of the block with flat index q of the same realisation (shared memory, or
 // recomputed from global memory). p = own flat index, (i, j) = its row/col for rank 2.
-template <int INT, class UF>
+// WRAP = false: the caller's U() accepts q = -1 and q = N (ghost cells) for the 1-D stencils.
+template <int INT, bool WRAP = true, bool UNIT = false, class UF>
 __device__ __forceinline__ double f_interactions(const Par& P, UF&& U, const double* pref, int p,
                                                  int i, int j, double uc)
 {
@@ -265,18 +270,18 @@ __device__ __forceinline__ double f_interactions(const Par& P, UF&& U, const dou
         return 0.0;
     }
     else if (INT == INT_LAPLACE1D) { // detail.h:480-486
-        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
-        return (U(l) - 2 * uc + U(r)) * P.k1;
+        int l = (WRAP && p == 0) ? N - 1 : p - 1, r = (WRAP && p == N - 1) ? 0 : p + 1;
+        return UNIT ? (U(l) - 2 * uc + U(r)) : (U(l) - 2 * uc + U(r)) * P.k1;
     }
     else if (INT == INT_QUARTIC1D) { // detail.h:784-803
-        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
+        int l = (WRAP && p == 0) ? N - 1 : p - 1, r = (WRAP && p == N - 1) ? 0 : p + 1;
         double um = U(l), up = U(r);
         double dup = up - uc;
         double dun = um - uc;
         return P.k1 * (um - 2 * uc + up) + P.k2 * (dup * dup * dup + dun * dun * dun);
     }
     else if (INT == INT_QUARTICGRADIENT1D) { // detail.h:642-651
-        int l = p == 0 ? N - 1 : p - 1, r = p == N - 1 ? 0 : p + 1;
+        int l = (WRAP && p == 0) ? N - 1 : p - 1, r = (WRAP && p == N - 1) ? 0 : p + 1;
         double um = U(l), up = U(r);
         double du = up - um;
         return (um - 2 * uc + up) * (P.k1 + (0.25 * P.k2) * du * du);
@@ -300,7 +305,8 @@ __device__ __forceinline__ double f_interactions(const Par& P, UF&& U, const dou
         const int R = P.rows, C = P.cols;
         int im = (i == 0 ? R - 1 : i - 1) * C, ip = (i == R - 1 ? 0 : i + 1) * C, ic = i * C;
         int jm = j == 0 ? C - 1 : j - 1, jp = j == C - 1 ? 0 : j + 1;
-        return (U(im + j) + U(ip + j) + U(ic + jm) + U(ic + jp) - 4 * uc) * P.k1;
+        double lap = U(im + j) + U(ip + j) + U(ic + jm) + U(ic + jp) - 4 * uc;
+        return UNIT ? lap : lap * P.k1;
     }
     else { // QuarticGradient2d, detail.h:700-711
         const int R = P.rows, C = P.cols;
@@ -345,20 +351,21 @@ __device__ __forceinline__ double f_interactions_rt(const Par& P, UF&& U, const 
 // ---- velocity-Verlet tail of timeStep (detail.h:1552-1565) -----------------------------------
 // F = (f_frame + f_potential) + f_interactions at the new u; returns the final residual force
 // f = F + f_damping and updates v, a in place (v_n, a_n are the values on entry).
+template <bool UNIT = false>
 __device__ __forceinline__ double verlet_tail(const Par& P, double F, double& v, double& a)
 {
     const double vn = v, an = a;
     const double hdt = 0.5 * P.dt;
     const double meta = -P.eta;
-    double vv = vn + P.dt * an; // 1552
-    double f = F + meta * vv;   // 1553: updated_v() -> f = f_frame+f_pot+f_int+f_damp
-    double aa = f * P.inv_m;    // 1555
-    vv = vn + hdt * (an + aa);  // 1557
-    f = F + meta * vv;          // 1558
-    aa = f * P.inv_m;           // 1560
-    vv = vn + hdt * (an + aa);  // 1562
-    f = F + meta * vv;          // 1563
-    aa = f * P.inv_m;           // 1565
+    double vv = vn + P.dt * an;         // 1552
+    double f = F + meta * vv;           // 1553: updated_v() -> f = f_frame+f_pot+f_int+f_damp
+    double aa = UNIT ? f : f * P.inv_m; // 1555
+    vv = vn + hdt * (an + aa);          // 1557
+    f = F + meta * vv;                  // 1558
+    aa = UNIT ? f : f * P.inv_m;        // 1560
+    vv = vn + hdt * (an + aa);          // 1562
+    f = F + meta * vv;                  // 1563
+    aa = UNIT ? f : f * P.inv_m;        // 1565
     v = vv;
     a = aa;
     return f;
@@ -410,6 +417,37 @@ __device__ __forceinline__ double warp_min(double x)
         x = fmin(x, __shfl_xor_sync(0xffffffffu, x, o));
     }
     return x;
+}
+
+// Sums two values over a warp with one butterfly: after the call every lane holds
+// (sum of a, sum of b). Stage 1 splits the pair over even/odd lanes, stages 2..5 reduce one
+// value per lane, the final shuffles broadcast. Fixed order -> deterministic.
+__device__ __forceinline__ void warp_sum2(double& a, double& b)
+{
+    const int lane = threadIdx.x & 31;
+    const bool odd = lane & 1;
+    // even lanes collect a, odd lanes collect b
+    double send = odd ? a : b;
+    double keep = odd ? b : a;
+    keep += __shfl_xor_sync(0xffffffffu, send, 1);
+#pragma unroll
+    for (int o = 16; o > 1; o >>= 1) {
+        keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    }
+    a = __shfl_sync(0xffffffffu, keep, 0);
+    b = __shfl_sync(0xffffffffu, keep, 1);
+}
+
+// second level: lane l holds the value x_l of an interleaved array (a_0, b_0, a_1, b_1, ...)
+// of 32 entries; returns (sum a, sum b) in every lane.
+__device__ __forceinline__ void warp_sum_interleaved(double x, double& a, double& b)
+{
+#pragma unroll
+    for (int o = 16; o > 1; o >>= 1) {
+        x += __shfl_xor_sync(0xffffffffu, x, o);
+    }
+    a = __shfl_sync(0xffffffffu, x, 0);
+    b = __shfl_sync(0xffffffffu, x, 1);
 }
 
 // residual() of detail.h:1512-1520 from the two sums of squares

@@ -6,37 +6,65 @@
 
 namespace fqsb {
 
-// blocks-per-thread x threads configurations of the resident kernels
+// blocks-per-thread x threads (x wells-in-shared-memory) configurations of the resident kernels
 struct ResidentCfg {
     int B, T;
+    bool ysmem;
 };
 
-// picks the smallest configuration that holds N blocks; B == 0 if N does not fit on chip
-inline ResidentCfg resident_cfg(i64 N)
+static const ResidentCfg kResidentCfgs[] = {
+    {1, 256, false},  // 0
+    {1, 1024, false}, // 1
+    {2, 1024, false}, // 2
+    {8, 512, false},  // 3
+};
+static const int kNumResidentCfgs = 4;
+
+// largest line the resident kernels hold on chip
+static const i64 kResidentMaxN = 4096;
+
+// default configuration for N blocks; `variant` > 0 forces kResidentCfgs[variant - 1]
+// (B == 0 if the line does not fit on chip)
+inline ResidentCfg resident_cfg(i64 N, int variant = 0)
 {
+    if (variant > 0 && variant <= kNumResidentCfgs) {
+        ResidentCfg c = kResidentCfgs[variant - 1];
+        if ((i64)c.B * c.T >= N) {
+            return c;
+        }
+    }
     if (N <= 256) {
-        return {1, 256};
+        return kResidentCfgs[0];
     }
     if (N <= 1024) {
-        return {1, 1024};
+        return kResidentCfgs[1];
     }
     if (N <= 2048) {
-        return {2, 1024};
+        return kResidentCfgs[2];
     }
-    if (N <= 4096) {
-        return {8, 512};
+    if (N <= kResidentMaxN) {
+        return kResidentCfgs[3];
     }
-    if (N <= 8192) {
-        return {8, 1024};
-    }
-    return {0, 0};
+    return {0, 0, false};
 }
 
+// mu, m and k1 exactly 1: the kernels skip those multiplications (bit-identical results)
+inline bool unit_parameters(const Par& P) { return P.mu == 1.0 && P.m == 1.0 && P.k1 == 1.0; }
+
+// dynamic shared memory of k_resident (must mirror the carve-up in the kernel)
 inline size_t resident_smem(const Par& P, const ResidentCfg& c)
 {
-    size_t n = (size_t)P.N;
-    size_t words = 3 * n + (P.inter == INT_LONGRANGE1D ? n : 0) + 2 * (size_t)(c.T / 32);
-    return words * 8 + (size_t)(c.T / 32) * 4 * sizeof(int);
+    const size_t n = (size_t)P.N;
+    const size_t ghosts = P.inter < INT_LAPLACE2D ? 2 : 0;
+    size_t words = 2 * (n + ghosts) + n + (c.ysmem ? 2 * n : 0) +
+                   (P.inter == INT_LONGRANGE1D ? n : 0) + 4 * (size_t)(c.T / 32);
+    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int);
+}
+
+// dynamic shared memory of k_resident_nopassing: us[2][N], sst[N], red[NW][2]
+inline size_t resident_np_smem(const Par& P, const ResidentCfg& c)
+{
+    return (3 * (size_t)P.N + 2 * (size_t)(c.T / 32)) * 8;
 }
 
 // defined in fqsb_resident.cu (one object per potential x interaction combination)
@@ -45,8 +73,12 @@ cudaError_t launch_resident(const ResidentCfg& cfg, const Par& P, const State& S
 cudaError_t launch_resident_nopassing(const ResidentCfg& cfg, const Par& P, const State& S,
                                       const RunArgs& A, cudaStream_t stream);
 // defined in fqsb_stream.cu
+// `flip`: parity of the launch within the call (which buffer set is the input);
+// `finalise`: run the per-step stop decision (stop modes and flowSteps)
 cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
-                               cudaStream_t stream);
+                               cudaStream_t stream, int flip, int finalise);
+int stream_step_tiles(const Par& P, int generic_tiles);
+const char* stream_step_name(const Par& P);
 cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
                                 cudaStream_t stream);
 bool combination_supported(int pot, int inter);

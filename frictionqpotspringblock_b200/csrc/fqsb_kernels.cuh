@@ -105,186 +105,298 @@ __device__ __forceinline__ void track_hop(const RunArgs& A, i64 gp, i64 i_before
 // K2: resident velocity-Verlet. grid = R CTAs (the hardware block scheduler is the work queue
 // over realisations), T threads, thread t owns blocks p = t + j*T (j < B): global loads/stores
 // are coalesced and shared-memory neighbour reads are conflict-free for every stencil.
-// Shared memory: us[2][N] slips (double-buffered), sst[N] pcg32 states, pref[N] (LongRange),
-// reduction scratch.
+//
+// On-chip layout for the whole call: slips u in shared memory only (two buffers, 1-D lines
+// ghost-padded so the periodic neighbours are plain offsets), v and a in registers, the wells
+// (y_l, y_r) in registers or -- YSMEM -- in shared memory, pcg32 states in shared memory.
+// DRAM is touched at entry/exit and on the rare well change (idx, i_n).
 // =============================================================================================
-template <int POT, int INT, int B, int T>
-__global__ void __launch_bounds__(T) k_resident(const Par P, const State S, const RunArgs A)
+
+// rare path: a block left its well (out of line: keeps the hot loop's register budget small)
+static __device__ __noinline__ int hop_shared(const Par& P, double un, double* yl, double* yr, u64* st,
+                                       i64* gidx, int* underflow, i64* i_before)
+{
+    double l = *yl, r = *yr;
+    u64 s = *st;
+    const i64 i0 = *gidx;
+    int moved = well_align(P, un, l, r, s, i0, underflow);
+    *yl = l;
+    *yr = r;
+    *st = s;
+    *gidx = i0 + moved;
+    *i_before = i0;
+    return moved;
+}
+
+template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT>
+__global__ void __launch_bounds__(T)
+    k_resident(const __grid_constant__ Par P, const __grid_constant__ State S,
+               const __grid_constant__ RunArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool ONE_D = INT < INT_LAPLACE2D;
+    constexpr int G = ONE_D ? 1 : 0; // ghost cells on each side of a 1-D line
+    constexpr int NW = T / 32;
     const int N = (int)P.N;
+    const int NS = N + 2 * G;
     const int r = blockIdx.x;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
-    constexpr int NW = T / 32;
 
     Ctl& ctl = S.ctl[r];
     if (ctl.status != ST_RUNNING) {
         return;
     }
 
-    double* us = reinterpret_cast<double*>(smem_raw);              // [2][N]
-    u64* sst = reinterpret_cast<u64*>(us + 2 * (size_t)N);         // [N]
-    double* spref = reinterpret_cast<double*>(sst + N);            // [N] if LongRange
-    double* red = spref + (INT == INT_LONGRANGE1D ? N : 0);        // [NW][2]
-    int* redi = reinterpret_cast<int*>(red + 2 * NW);              // [NW][4]
+    double* us = reinterpret_cast<double*>(smem_raw);          // [2][NS]
+    u64* sst = reinterpret_cast<u64*>(us + 2 * (size_t)NS);    // [N]
+    double* syl = reinterpret_cast<double*>(sst + N);          // [N] if YSMEM
+    double* syr = syl + (YSMEM ? N : 0);                       // [N] if YSMEM
+    double* spref = syr + (YSMEM ? N : 0);                     // [N] if LongRange
+    double* red = spref + (INT == INT_LONGRANGE1D ? N : 0);    // [2][NW][2]
+    int* redi = reinterpret_cast<int*>(red + 4 * NW);          // [2][NW][4]
 
     const i64 base = (i64)r * P.N;
-    double u[B], v[B], a[B], yl[B], yr[B];
-    int didx[B];
-    int ij[B];
+    double v[B], a[B];
+    double yl[YSMEM ? 1 : B], yr[YSMEM ? 1 : B];
+    int ij[ONE_D ? 1 : B];
 
 #pragma unroll
     for (int j = 0; j < B; ++j) {
         const int p = t + j * T;
-        didx[j] = 0;
-        ij[j] = 0;
-        if (p < N) {
-            u[j] = S.u[base + p];
-            v[j] = S.v[base + p];
-            a[j] = S.a[base + p];
-            yl[j] = S.yl[base + p];
-            yr[j] = S.yr[base + p];
+        const int pc = (FULL || p < N) ? p : N - 1;
+        v[j] = S.v[base + pc];
+        a[j] = S.a[base + pc];
+        if (!YSMEM) {
+            yl[j] = S.yl[base + pc];
+            yr[j] = S.yr[base + pc];
+        }
+        if (!ONE_D) {
+            int i = pc / P.cols;
+            ij[j] = (i << 16) | (pc - i * P.cols);
+        }
+        if (FULL || p < N) {
+            us[p + G] = S.u[base + p];
+            if (YSMEM) {
+                syl[p] = S.yl[base + p];
+                syr[p] = S.yr[base + p];
+            }
             sst[p] = S.rng[base + p];
             if (INT == INT_LONGRANGE1D) {
                 spref[p] = S.pref[p];
             }
-            if (INT == INT_LAPLACE2D || INT == INT_QUARTICGRADIENT2D) {
-                int i = p / P.cols;
-                ij[j] = (i << 16) | (p - i * P.cols);
-            }
-        }
-        else {
-            u[j] = v[j] = a[j] = 0.0;
-            yl[j] = -1.7976931348623157e308;
-            yr[j] = 1.7976931348623157e308;
         }
     }
+    __syncthreads(); // clamped threads read block N-1's slip, written by its owner
 
-    Prog g;
-    prog_load(g, ctl);
-    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
     double uf = S.u_frame[r];
-    double res_last = ctl.residual;
     const double c2 = 0.5 * P.dt * P.dt; // (0.5*dt)*dt, detail.h:1549
-    int status = ST_RUNNING;
     int underflow = 0;
-    int cur = 0;
-    const i64 nloop = A.max_steps - g.steps < A.launch_steps ? A.max_steps - g.steps
-                                                             : A.launch_steps;
+    int prev = 0; // buffer holding the current slips
 
-    for (i64 it = 0; it < nloop; ++it) {
-        g.inc++; // detail.h:1541
-        if (A.flow) {
-            uf += A.v_frame * P.dt; // detail.h:1642
-        }
-        double* ucur = us + (size_t)cur * N;
-        int hops = 0, dS = 0, dA = 0;
+    // Blocks beyond N (ragged last slice) are clamped onto block N-1: they redo its arithmetic
+    // but never store, so the hot loop has no per-block branches and the B independent
+    // floating-point chains of a thread interleave.
 
-        // ---- positions (detail.h:1549) + well search (detail.h:144)
+    // ---- positions (detail.h:1549): purely local; ghosts keep the line periodic
+    auto phase1 = [&](const double* uprev, double* ucur) {
+        double un[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = t + j * T;
-            if (p < N) {
-                double un = u[j] + P.dt * v[j] + c2 * a[j];
-                u[j] = un;
-                ucur[p] = un;
-                if (un > yr[j] || !(un > yl[j])) {
-                    u64 st = sst[p];
-                    i64 i_before = S.idx[base + p] + didx[j];
-                    int moved = well_align(P, un, yl[j], yr[j], st, i_before, &underflow);
-                    sst[p] = st;
-                    didx[j] += moved;
+            const int pc = (FULL || p < N) ? p : N - 1;
+            un[j] = uprev[pc + G] + P.dt * v[j] + c2 * a[j];
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int p = t + j * T;
+            if (FULL || p < N) {
+                ucur[p + G] = un[j];
+                if (ONE_D) {
+                    if (j == 0 && t == 0) {
+                        ucur[N + 1] = un[j];
+                    }
+                    if (FULL ? (j == B - 1 && t == T - 1) : (p == N - 1)) {
+                        ucur[0] = un[j];
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- well search (detail.h:144), forces at the new positions (detail.h:1380-1386) and
+    //      the Verlet tail (detail.h:1552-1565)
+    auto phase2 = [&](const double* ucur, auto accumulate, double& sf, double& sff, int& hops,
+                      int& dS, int& dA) {
+        auto U = [&](int q) { return ucur[q + G]; };
+        double uc[B], wl[B], wr[B];
+        unsigned need = 0u;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int p = t + j * T;
+            const int pc = (FULL || p < N) ? p : N - 1;
+            uc[j] = ucur[pc + G];
+            wl[j] = YSMEM ? syl[pc] : yl[j];
+            wr[j] = YSMEM ? syr[pc] : yr[j];
+            if ((FULL || p < N) && (uc[j] > wr[j] || !(uc[j] > wl[j]))) {
+                need |= 1u << j;
+            }
+        }
+        if (need) { // rare: some block of this thread left its well
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                if ((need >> j) & 1u) {
+                    const int p = t + j * T;
+                    double l = wl[j], rr = wr[j];
+                    i64 i_before;
+                    int moved = hop_shared(P, uc[j], &l, &rr, sst + p, S.idx + base + p,
+                                           &underflow, &i_before);
+                    wl[j] = l;
+                    wr[j] = rr;
+                    if (YSMEM) {
+                        syl[p] = l;
+                        syr[p] = rr;
+                    }
+                    else {
+                        yl[j] = l;
+                        yr[j] = rr;
+                    }
                     hops += moved != 0;
                     track_hop(A, base + p, i_before, moved, dS, dA);
                 }
             }
         }
-        __syncthreads();
-
-        // ---- forces at the new positions (detail.h:1380-1386) + Verlet tail (1552-1565)
-        double sf = 0.0, sff = 0.0;
-        auto U = [&](int q) { return ucur[q]; };
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = t + j * T;
-            if (p < N) {
-                const double uc = u[j];
-                double fi = f_interactions<INT>(P, U, spref, p, ij[j] >> 16, ij[j] & 0xffff, uc);
-                double fp = f_potential<POT>(P, uc, yl[j], yr[j]);
-                double ff = P.k_frame * (uf - uc);
-                double F = ff + fp + fi;
-                double f = verlet_tail(P, F, v[j], a[j]);
-                sf += f * f;
-                sff += ff * ff;
+            const int pc = (FULL || p < N) ? p : N - 1;
+            const int qi = ONE_D ? 0 : (ij[ONE_D ? 0 : j] >> 16);
+            const int qj = ONE_D ? 0 : (ij[ONE_D ? 0 : j] & 0xffff);
+            double fi = f_interactions<INT, !ONE_D, UNIT>(P, U, spref, pc, qi, qj, uc[j]);
+            double fp = f_potential<POT, UNIT>(P, uc[j], wl[j], wr[j]);
+            double ff = P.k_frame * (uf - uc[j]);
+            double F = ff + fp + fi;
+            double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
+            if (decltype(accumulate)::value) {
+                sf += (FULL || p < N) ? f * f : 0.0;
+                sff += (FULL || p < N) ? ff * ff : 0.0;
             }
         }
+    };
 
-        if (A.mode == MODE_FIXED) {
-            // no stop test: one barrier per step thanks to the double-buffered slips
-            cur ^= 1;
-            g.steps++;
-            continue;
-        }
+    int status = ST_RUNNING;
+    i64 steps_done = ctl.steps;
+    const i64 nloop = A.max_steps - steps_done < A.launch_steps ? A.max_steps - steps_done
+                                                                : A.launch_steps;
 
-        // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
-        sf = warp_sum(sf);
-        sff = warp_sum(sff);
-        hops = warp_sum(hops);
-        if (A.track) {
-            dS = warp_sum(dS);
-            dA = warp_sum(dA);
+    if (A.mode == MODE_FIXED) {
+        // timeSteps / flowSteps: no stop test, one barrier per step
+        double sf = 0.0, sff = 0.0;
+        int hops = 0, dS = 0, dA = 0;
+        for (i64 it = 0; it < nloop; ++it) {
+            if (A.flow) {
+                uf += A.v_frame * P.dt; // detail.h:1642
+            }
+            double* ucur = us + (size_t)(prev ^ 1) * NS;
+            phase1(us + (size_t)prev * NS, ucur);
+            __syncthreads();
+            phase2(ucur, std::false_type{}, sf, sff, hops, dS, dA);
+            prev ^= 1;
         }
-        if (lane == 0) {
-            red[2 * warp] = sf;
-            red[2 * warp + 1] = sff;
-            redi[4 * warp] = hops;
-            redi[4 * warp + 1] = dS;
-            redi[4 * warp + 2] = dA;
+        steps_done += nloop;
+        if (steps_done >= A.max_steps) {
+            status = ST_EXHAUSTED;
         }
-        __syncthreads();
-        sf = lane < NW ? red[2 * lane] : 0.0;
-        sff = lane < NW ? red[2 * lane + 1] : 0.0;
-        hops = lane < NW ? redi[4 * lane] : 0;
-        dS = lane < NW ? redi[4 * lane + 1] : 0;
-        dA = lane < NW ? redi[4 * lane + 2] : 0;
-        sf = warp_sum(sf);
-        sff = warp_sum(sff);
-        hops = warp_sum(hops);
-        if (A.track) {
-            dS = warp_sum(dS);
-            dA = warp_sum(dA);
+        if (t == 0) {
+            ctl.inc += nloop; // detail.h:1541
+            ctl.steps = steps_done;
+            ctl.status = status;
+            S.u_frame[r] = uf;
         }
-        status = step_decide(A, g, ring, lane, sf, sff, hops, dS, dA, &res_last);
-        if (status != ST_RUNNING) {
-            break;
-        }
-        // the second barrier above also orders this step's reads of `ucur` before the next
-        // step's writes, so alternating buffers is not required here (kept for uniformity)
-        cur ^= 1;
     }
+    else {
+        Prog g;
+        prog_load(g, ctl);
+        double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
+        double res_last = ctl.residual;
+        // One barrier per step: after the forces of step s, the positions of step s+1 are
+        // computed speculatively (purely local, into the other slip buffer); the barrier that
+        // publishes them also publishes the partial sums of step s, whose stop decision is
+        // taken right after it. A stop discards the speculative positions.
+        if (nloop > 0) {
+            phase1(us + (size_t)prev * NS, us + (size_t)(prev ^ 1) * NS);
+            __syncthreads();
+        }
+        for (i64 it = 0; it < nloop; ++it) {
+            g.inc++; // detail.h:1541
+            double sf = 0.0, sff = 0.0;
+            int hops = 0, dS = 0, dA = 0;
+            phase2(us + (size_t)(prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
+            prev ^= 1;
 
-    if (A.mode == MODE_FIXED && g.steps >= A.max_steps) {
-        status = ST_EXHAUSTED;
+            // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
+            double* rd = red + (it & 1) * 2 * NW;
+            int* ri = redi + (it & 1) * 4 * NW;
+            warp_sum2(sf, sff);
+            hops = __reduce_add_sync(0xffffffffu, hops);
+            if (A.track) {
+                dS = __reduce_add_sync(0xffffffffu, dS);
+                dA = __reduce_add_sync(0xffffffffu, dA);
+            }
+            if (lane == 0) {
+                rd[2 * warp] = sf;
+                rd[2 * warp + 1] = sff;
+                ri[4 * warp] = hops;
+                ri[4 * warp + 1] = dS;
+                ri[4 * warp + 2] = dA;
+            }
+            phase1(us + (size_t)prev * NS, us + (size_t)(prev ^ 1) * NS); // speculative
+            __syncthreads();
+            if (2 * NW == 32) {
+                warp_sum_interleaved(rd[lane], sf, sff);
+            }
+            else {
+                sf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
+                sff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
+            }
+            hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
+            if (A.track) {
+                dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
+                dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
+            }
+            status = step_decide(A, g, ring, lane, sf, sff, hops, dS, dA, &res_last);
+            if (status != ST_RUNNING) {
+                break;
+            }
+        }
+        if (t < 32) {
+            if (lane < A.niter_tol && lane < FQSB_RING) {
+                ctl.ring[lane] = ring;
+            }
+            if (lane == 0) {
+                prog_store(g, ctl);
+                ctl.status = status;
+                ctl.residual = res_last;
+            }
+        }
     }
 
     // ---- write back; quench() on convergence (detail.h:1527-1532,1781)
+    const double* ufin = us + (size_t)prev * NS;
     bool nan = false;
 #pragma unroll
     for (int j = 0; j < B; ++j) {
         const int p = t + j * T;
         if (p < N) {
             const bool q = status == ST_CONVERGED;
-            S.u[base + p] = u[j];
+            const double uu = ufin[p + G];
+            S.u[base + p] = uu;
             S.v[base + p] = q ? 0.0 : v[j];
             S.a[base + p] = q ? 0.0 : a[j];
-            nan |= u[j] != u[j];
-            if (didx[j] != 0) {
-                S.yl[base + p] = yl[j];
-                S.yr[base + p] = yr[j];
-                S.idx[base + p] += didx[j];
-                S.rng[base + p] = sst[p];
-            }
+            nan |= uu != uu;
+            S.yl[base + p] = YSMEM ? syl[p] : yl[j];
+            S.yr[base + p] = YSMEM ? syr[p] : yr[j];
+            S.rng[base + p] = sst[p];
         }
     }
     if (nan) {
@@ -292,17 +404,6 @@ __global__ void __launch_bounds__(T) k_resident(const Par P, const State S, cons
     }
     if (underflow) {
         S.err[0] = 1;
-    }
-    if (t < 32) {
-        if (lane < A.niter_tol && lane < FQSB_RING) {
-            ctl.ring[lane] = ring;
-        }
-        if (lane == 0) {
-            prog_store(g, ctl);
-            ctl.status = status;
-            ctl.residual = res_last;
-            S.u_frame[r] = uf;
-        }
     }
 }
 
@@ -502,16 +603,225 @@ __device__ __forceinline__ void block_sum(double (&x)[NV], double* scratch /* [3
 }
 
 // =============================================================================================
-// K1: streaming velocity-Verlet, one step per launch. grid = (tiles, R), 256 threads.
-// Reads u,v,a (+ the neighbours' through L1/L2), y_l, y_r; writes u,v,a to the other buffer
-// set (neighbouring CTAs still need the old values): 64 B of DRAM traffic per block-update.
-// The last CTA of a realisation to finish reduces the per-CTA partials in index order and
-// takes the step's stop decision, so queued launches after the stop are no-ops.
+// K1: streaming velocity-Verlet, one fused step per launch over all blocks of all realisations.
+// Reads u,v,a,y_l,y_r once and writes u,v,a once: 64 B of DRAM traffic per block-update. The
+// new state goes to the other buffer set (neighbouring CTAs still need the old one); `flip` is
+// the parity of the launch within the call. In the stop modes the last CTA of a realisation to
+// finish reduces the per-CTA partials in index order and takes the step's decision, so queued
+// launches after the stop are no-ops.
 // =============================================================================================
 #define FQSB_NPART 8
 
+// per-CTA partials -> last-CTA-done finalise of the step (one warp)
+__device__ __forceinline__ void stream_finalise(const Par& P, const State& S, const RunArgs& A,
+                                                int r, int flip, double uf, double (&acc)[2],
+                                                int hops, int dS, int dA, double* scratch,
+                                                int* iscratch, int* s_last)
+{
+    Ctl& ctl = S.ctl[r];
+    block_sum<2>(acc, scratch);
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        hops = __reduce_add_sync(0xffffffffu, hops);
+        dS = __reduce_add_sync(0xffffffffu, dS);
+        dA = __reduce_add_sync(0xffffffffu, dA);
+        if (lane == 0) {
+            iscratch[warp * 4] = hops;
+            iscratch[warp * 4 + 1] = dS;
+            iscratch[warp * 4 + 2] = dA;
+        }
+        __syncthreads();
+        hops = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4] : 0);
+        dS = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4 + 1] : 0);
+        dA = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4 + 2] : 0);
+    }
+    double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
+    if (threadIdx.x == 0) {
+        part[0] = acc[0];
+        part[1] = acc[1];
+        part[2] = (double)hops;
+        part[3] = (double)dS;
+        part[4] = (double)dA;
+        __threadfence();
+        unsigned int ticket = atomicAdd(&ctl.count, 1u);
+        *s_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!*s_last || threadIdx.x >= 32) {
+        return;
+    }
+    __threadfence();
+    const int lane = threadIdx.x;
+    double sf = 0.0, sff = 0.0, dh = 0.0, ds = 0.0, da = 0.0;
+    const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
+    for (int c = lane; c < (int)gridDim.x; c += 32) {
+        sf += all[c * FQSB_NPART];
+        sff += all[c * FQSB_NPART + 1];
+        dh += all[c * FQSB_NPART + 2];
+        ds += all[c * FQSB_NPART + 3];
+        da += all[c * FQSB_NPART + 4];
+    }
+    sf = warp_sum(sf);
+    sff = warp_sum(sff);
+    dh = warp_sum(dh);
+    ds = warp_sum(ds);
+    da = warp_sum(da);
+    Prog g;
+    prog_load(g, ctl);
+    g.inc++;
+    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
+    double res_last = ctl.residual;
+    int status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da, &res_last);
+    if (lane < A.niter_tol && lane < FQSB_RING) {
+        ctl.ring[lane] = ring;
+    }
+    if (lane == 0) {
+        prog_store(g, ctl);
+        ctl.residual = res_last;
+        ctl.flip = flip ^ 1;
+        ctl.count = 0u;
+        S.u_frame[r] = uf;
+        ctl.status = status;
+    }
+}
+
+// ---- 1-D 3-point stencils: 256 threads x 8 blocks, double2 streams, halo through smem --------
+#define FQSB_ST_THREADS 256
+#define FQSB_ST_J 4
+#define FQSB_ST_SLAB (2 * FQSB_ST_THREADS)
+#define FQSB_ST_TILE (FQSB_ST_J * FQSB_ST_SLAB)
+
+template <int POT, int INT, bool UNIT>
+__global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
+    k_stream_1d(const __grid_constant__ Par P, const __grid_constant__ State S,
+                const __grid_constant__ RunArgs A, const int flip, const int finalise)
+{
+    constexpr int J = FQSB_ST_J, SLAB = FQSB_ST_SLAB;
+    __shared__ __align__(16) double sun[J][SLAB + 4]; // [1] left halo, [2..2+SLAB) data, then right
+    __shared__ double scratch[32 * 2];
+    __shared__ int iscratch[32 * 4];
+    __shared__ int s_last;
+    const int r = blockIdx.y;
+    const int t = threadIdx.x;
+    Ctl& ctl = S.ctl[r];
+    const int status = ctl.status; // consumed after the state loads are in flight
+    const int N = (int)P.N;
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
+    const double* __restrict__ vi = (flip ? S.v2 : S.v) + base;
+    const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
+    double* __restrict__ uo = (flip ? S.u : S.u2) + base;
+    double* __restrict__ vo = (flip ? S.v : S.v2) + base;
+    double* __restrict__ ao = (flip ? S.a : S.a2) + base;
+    const int tile0 = blockIdx.x * FQSB_ST_TILE;
+    const double c2 = 0.5 * P.dt * P.dt;
+
+    double2 u2[J], v2[J], a2[J], l2[J], r2[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int p0 = tile0 + j * SLAB + 2 * t;
+        if (p0 < N) {
+            u2[j] = *reinterpret_cast<const double2*>(ui + p0);
+            v2[j] = *reinterpret_cast<const double2*>(vi + p0);
+            a2[j] = *reinterpret_cast<const double2*>(ai + p0);
+            l2[j] = *reinterpret_cast<const double2*>(S.yl + base + p0);
+            r2[j] = *reinterpret_cast<const double2*>(S.yr + base + p0);
+        }
+        else {
+            u2[j] = v2[j] = a2[j] = l2[j] = r2[j] = make_double2(0.0, 0.0);
+        }
+    }
+    double uf = S.u_frame[r];
+    if (A.flow) {
+        uf += A.v_frame * P.dt; // detail.h:1642
+    }
+
+    // ---- positions (detail.h:1549)
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        u2[j].x = u2[j].x + P.dt * v2[j].x + c2 * a2[j].x;
+        u2[j].y = u2[j].y + P.dt * v2[j].y + c2 * a2[j].y;
+        if (tile0 + j * SLAB + 2 * t < N) { // (the slot after a ragged slab holds its right halo)
+            *reinterpret_cast<double2*>(&sun[j][2 + 2 * t]) = u2[j];
+        }
+    }
+    if (t < 2 * J) { // the two periodic neighbours just outside each slab
+        const int j = t >> 1, side = t & 1;
+        const int s0 = tile0 + j * SLAB;
+        if (s0 < N) {
+            const int cnt = N - s0 < SLAB ? N - s0 : SLAB;
+            int q = side ? s0 + cnt : s0 - 1;
+            q = q < 0 ? N - 1 : (q >= N ? 0 : q);
+            sun[j][side ? 2 + cnt : 1] = ui[q] + P.dt * vi[q] + c2 * ai[q];
+        }
+    }
+    if (status != ST_RUNNING) {
+        return;
+    }
+    __syncthreads();
+
+    double acc[2] = {0.0, 0.0};
+    int hops = 0, dS = 0, dA = 0, underflow = 0;
+    bool nan = false;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int p0 = tile0 + j * SLAB + 2 * t;
+        if (p0 < N) {
+            const double* row = &sun[j][2];
+            auto U = [&](int q) { return row[q]; };
+            double uc[2] = {u2[j].x, u2[j].y};
+            double wl[2] = {l2[j].x, l2[j].y};
+            double wr[2] = {r2[j].x, r2[j].y};
+            double vv[2] = {v2[j].x, v2[j].y};
+            double aa[2] = {a2[j].x, a2[j].y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (uc[e] > wr[e] || !(uc[e] > wl[e])) { // rare: well change, detail.h:144
+                    const i64 gp = base + p0 + e;
+                    u64 st = S.rng[gp];
+                    i64 i_before = S.idx[gp];
+                    int moved = well_align(P, uc[e], wl[e], wr[e], st, i_before, &underflow);
+                    S.rng[gp] = st;
+                    S.idx[gp] = i_before + moved;
+                    S.yl[gp] = wl[e];
+                    S.yr[gp] = wr[e];
+                    hops += moved != 0;
+                    track_hop(A, gp, i_before, moved, dS, dA);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double fi = f_interactions<INT, false, UNIT>(P, U, nullptr, 2 * t + e, 0, 0, uc[e]);
+                double fp = f_potential<POT, UNIT>(P, uc[e], wl[e], wr[e]);
+                double ff = P.k_frame * (uf - uc[e]);
+                double F = ff + fp + fi;
+                double f = verlet_tail<UNIT>(P, F, vv[e], aa[e]);
+                acc[0] += f * f;
+                acc[1] += ff * ff;
+                nan |= uc[e] != uc[e];
+            }
+            *reinterpret_cast<double2*>(uo + p0) = u2[j];
+            *reinterpret_cast<double2*>(vo + p0) = make_double2(vv[0], vv[1]);
+            *reinterpret_cast<double2*>(ao + p0) = make_double2(aa[0], aa[1]);
+        }
+    }
+    if (nan) {
+        S.err[1] = 1;
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+    if (finalise) {
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+    }
+}
+
+// ---- generic fallback (2-D stencils, LongRange, odd N): one block per thread, neighbours'
+//      new positions recomputed from global memory (served by L1/L2)
 template <int POT, int INT>
-__global__ void __launch_bounds__(256) k_stream_step(const Par P, const State S, const RunArgs A)
+__global__ void __launch_bounds__(256)
+    k_stream_step(const __grid_constant__ Par P, const __grid_constant__ State S,
+                  const __grid_constant__ RunArgs A, const int flip, const int finalise)
 {
     __shared__ double scratch[32 * 2];
     __shared__ int iscratch[32 * 4];
@@ -523,7 +833,6 @@ __global__ void __launch_bounds__(256) k_stream_step(const Par P, const State S,
     }
     const int N = (int)P.N;
     const i64 base = (i64)r * P.N;
-    const int flip = ctl.flip;
     const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
     const double* __restrict__ vi = (flip ? S.v2 : S.v) + base;
     const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
@@ -578,72 +887,8 @@ __global__ void __launch_bounds__(256) k_stream_step(const Par P, const State S,
     if (underflow) {
         S.err[0] = 1;
     }
-
-    // ---- per-CTA partials
-    block_sum<2>(acc, scratch);
-    {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        hops = warp_sum(hops);
-        dS = warp_sum(dS);
-        dA = warp_sum(dA);
-        if (lane == 0) {
-            iscratch[warp * 4] = hops;
-            iscratch[warp * 4 + 1] = dS;
-            iscratch[warp * 4 + 2] = dA;
-        }
-        __syncthreads();
-        hops = warp_sum(lane < nw ? iscratch[lane * 4] : 0);
-        dS = warp_sum(lane < nw ? iscratch[lane * 4 + 1] : 0);
-        dA = warp_sum(lane < nw ? iscratch[lane * 4 + 2] : 0);
-    }
-    double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
-    if (threadIdx.x == 0) {
-        part[0] = acc[0];
-        part[1] = acc[1];
-        part[2] = (double)hops;
-        part[3] = (double)dS;
-        part[4] = (double)dA;
-        __threadfence();
-        unsigned int ticket = atomicAdd(&ctl.count, 1u);
-        s_last = ticket == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (!s_last || threadIdx.x >= 32) {
-        return;
-    }
-    // ---- finalise the step (one warp of the last CTA)
-    __threadfence();
-    const int lane = threadIdx.x;
-    double sf = 0.0, sff = 0.0, dh = 0.0, ds = 0.0, da = 0.0;
-    const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
-    for (int c = lane; c < (int)gridDim.x; c += 32) {
-        sf += all[c * FQSB_NPART];
-        sff += all[c * FQSB_NPART + 1];
-        dh += all[c * FQSB_NPART + 2];
-        ds += all[c * FQSB_NPART + 3];
-        da += all[c * FQSB_NPART + 4];
-    }
-    sf = warp_sum(sf);
-    sff = warp_sum(sff);
-    dh = warp_sum(dh);
-    ds = warp_sum(ds);
-    da = warp_sum(da);
-    Prog g;
-    prog_load(g, ctl);
-    g.inc++;
-    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
-    double res_last = ctl.residual;
-    int status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da, &res_last);
-    if (lane < A.niter_tol && lane < FQSB_RING) {
-        ctl.ring[lane] = ring;
-    }
-    if (lane == 0) {
-        prog_store(g, ctl);
-        ctl.residual = res_last;
-        ctl.flip = flip ^ 1;
-        ctl.count = 0u;
-        S.u_frame[r] = uf;
-        ctl.status = status;
+    if (finalise) {
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
     }
 }
 

@@ -62,24 +62,22 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
                                                    cudaStream_t stream)
 {
     const size_t smem = resident_smem(P, c);
-    if (c.B == 1 && c.T == 256) {
-        return launch(k_resident<C_POT, C_INT, 1, 256>, 256, smem, P, S, A, stream);
+    const bool full = (i64)c.B * c.T == P.N;
+    const bool unit = unit_parameters(P);
+#define FQSB_TRY_CFG(b, t) \
+    if (c.B == b && c.T == t) { \
+        if (full && unit) \
+            return launch(k_resident<C_POT, C_INT, b, t, false, true, true>, t, smem, P, S, A, stream); \
+        if (full) \
+            return launch(k_resident<C_POT, C_INT, b, t, false, true, false>, t, smem, P, S, A, stream); \
+        if (unit) \
+            return launch(k_resident<C_POT, C_INT, b, t, false, false, true>, t, smem, P, S, A, stream); \
+        return launch(k_resident<C_POT, C_INT, b, t, false, false, false>, t, smem, P, S, A, stream); \
     }
-    if (c.B == 1 && c.T == 1024) {
-        return launch(k_resident<C_POT, C_INT, 1, 1024>, 1024, smem, P, S, A, stream);
-    }
-    if (c.B == 2 && c.T == 1024) {
-        return launch(k_resident<C_POT, C_INT, 2, 1024>, 1024, smem, P, S, A, stream);
-    }
-    if (c.B == 4 && c.T == 1024) {
-        return launch(k_resident<C_POT, C_INT, 4, 1024>, 1024, smem, P, S, A, stream);
-    }
-    if (c.B == 8 && c.T == 512) {
-        return launch(k_resident<C_POT, C_INT, 8, 512>, 512, smem, P, S, A, stream);
-    }
-    if (c.B == 8 && c.T == 1024) {
-        return launch(k_resident<C_POT, C_INT, 8, 1024>, 1024, smem, P, S, A, stream);
-    }
+    FQSB_TRY_CFG(1, 256)
+    FQSB_TRY_CFG(1, 1024)
+    FQSB_TRY_CFG(2, 1024)
+    FQSB_TRY_CFG(8, 512)
     return cudaErrorInvalidConfiguration;
 }
 
@@ -89,7 +87,7 @@ template <int INT>
 static cudaError_t launch_np(const ResidentCfg& c, const Par& P, const State& S,
                              const RunArgs& A, cudaStream_t stream)
 {
-    const size_t smem = resident_smem(P, c);
+    const size_t smem = resident_np_smem(P, c);
     if (c.B == 1 && c.T == 256) {
         return launch(k_resident_nopassing<INT, 1, 256>, 256, smem, P, S, A, stream);
     }
@@ -99,14 +97,8 @@ static cudaError_t launch_np(const ResidentCfg& c, const Par& P, const State& S,
     if (c.B == 2 && c.T == 1024) {
         return launch(k_resident_nopassing<INT, 2, 1024>, 1024, smem, P, S, A, stream);
     }
-    if (c.B == 4 && c.T == 1024) {
-        return launch(k_resident_nopassing<INT, 4, 1024>, 1024, smem, P, S, A, stream);
-    }
     if (c.B == 8 && c.T == 512) {
         return launch(k_resident_nopassing<INT, 8, 512>, 512, smem, P, S, A, stream);
-    }
-    if (c.B == 8 && c.T == 1024) {
-        return launch(k_resident_nopassing<INT, 8, 1024>, 1024, smem, P, S, A, stream);
     }
     return cudaErrorInvalidConfiguration;
 }

@@ -52,12 +52,42 @@ cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
-                               cudaStream_t stream)
+// tiles per realisation of the step kernel that launch_stream_step() picks
+static bool use_tiled_1d(const Par& P) { return P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0; }
+
+int stream_step_tiles(const Par& P, int generic_tiles)
 {
+    return use_tiled_1d(P) ? (int)((P.N + FQSB_ST_TILE - 1) / FQSB_ST_TILE) : generic_tiles;
+}
+
+const char* stream_step_name(const Par& P) { return use_tiled_1d(P) ? "stream_1d" : "stream"; }
+
+cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
+                               cudaStream_t stream, int flip, int finalise)
+{
+    if (use_tiled_1d(P)) {
+        dim3 grid((unsigned)stream_step_tiles(P, 0), (unsigned)P.R);
+        const bool unit = unit_parameters(P);
+#define FQSB_TILED(pot, inter) \
+    if (unit) \
+        k_stream_1d<pot, inter, true><<<grid, FQSB_ST_THREADS, 0, stream>>>(P, S, A, flip, finalise); \
+    else \
+        k_stream_1d<pot, inter, false><<<grid, FQSB_ST_THREADS, 0, stream>>>(P, S, A, flip, finalise); \
+    break;
+        switch (combo_of(P.pot, P.inter)) {
+        case 0: FQSB_TILED(POT_CUSPY, INT_LAPLACE1D)
+        case 1: FQSB_TILED(POT_CUSPY, INT_QUARTIC1D)
+        case 2: FQSB_TILED(POT_CUSPY, INT_QUARTICGRADIENT1D)
+        case 6: FQSB_TILED(POT_SEMISMOOTH, INT_LAPLACE1D)
+        case 7: FQSB_TILED(POT_SMOOTH, INT_LAPLACE1D)
+        case 8: FQSB_TILED(POT_CUSPY, INT_NONE)
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
 #define FQSB_STREAM(pot, inter) \
-    k_stream_step<pot, inter><<<grid, 256, 0, stream>>>(P, S, A); \
+    k_stream_step<pot, inter><<<grid, 256, 0, stream>>>(P, S, A, flip, finalise); \
     break;
     switch (combo_of(P.pot, P.inter)) {
     case 0: FQSB_STREAM(POT_CUSPY, INT_LAPLACE1D)
