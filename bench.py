@@ -288,21 +288,36 @@ def main():
     kernel_avg = kernel_sec / max(1, kernel_launches)
     achieved = per_launch_bytes / kernel_avg / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "k_resident<Cuspy,Laplace1d,8,512>" if kernel_name == "resident"
+        "bound": "hbm",
+        "kernel": "k_resident<Cuspy,Laplace1d,B=8,T=512,full,unit>" if kernel_name == "resident"
         else kernel_name,
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_block_update": ALGO_BYTES_PER_UPDATE,
         "launch_ms": 1e3 * kernel_avg,
         "note": "resident kernel: state stays on chip for all T steps of a launch, so DRAM "
-                "traffic is ~64/T B per block-update and the algorithmic-byte fraction may exceed "
-                "1; the HBM-streaming kernel (one step per pass) is reported in roofline_stream",
+                "traffic is ~64/T B per block-update and the algorithmic-byte fraction exceeds 1; "
+                "its real bound is the FP64 pipe (fp64_pipe); the HBM-streaming kernel (one step "
+                "per pass over HBM) is reported in roofline_stream",
+    }
+    # the resident kernel's own bound: 32 FP64 pipe instructions per block-update (30 DADD/DMUL
+    # in the reference's evaluation order without FMA + 2 DSETP), 64 lanes per SM per clock
+    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_peak = 148 * 64 * sm_clock * 1e6
+    roofline["fp64_pipe"] = {
+        "ops_per_block_update": 32, "achieved_ops_per_s": 32 * R * N * T / kernel_avg,
+        "peak_ops_per_s": fp64_peak, "frac": 32 * R * N * T / kernel_avg / fp64_peak,
+        "peak_source": "148 SMs x 64 FP64 lanes x measured SM clock",
     }
     traffic_file = ROOT / "profiles" / "traffic.json"
     if traffic_file.exists():
         try:
             tr = json.loads(traffic_file.read_text())
-            roofline["traffic"] = tr.get("k_resident_bytes_per_launch")
+            per_block = tr.get("k_resident_bytes_per_block_per_launch")
+            if per_block:
+                # state is read and written once per launch, whatever the step count
+                roofline["traffic"] = per_block * R * N
+                roofline["traffic_source"] = tr.get("k_resident_source")
         except Exception:
             pass
 
@@ -326,11 +341,20 @@ def main():
         per = ALGO_BYTES_PER_UPDATE * Rs * N
         ach = per / (ksec / kl) / 1e9
         roofline_stream = {
-            "bound": "hbm", "kernel": "k_stream_step<Cuspy,Laplace1d>", "achieved": ach,
+            "bound": "hbm", "kernel": "k_stream_1d<Cuspy,Laplace1d,unit>", "achieved": ach,
             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
             "launch_ms": 1e3 * ksec / kl,
             "block_updates_per_s": world * Rs * N / (ksec / kl),
         }
+        if traffic_file.exists():
+            try:
+                tr = json.loads(traffic_file.read_text())
+                per_update = tr.get("k_stream_1d_bytes_per_block_update")
+                if per_update:
+                    roofline_stream["traffic"] = per_update * Rs * N
+                    roofline_stream["traffic_source"] = tr.get("k_stream_1d_source")
+            except Exception:
+                pass
         del ens2
 
     # ---- CPU baseline (rank 0): the oracle port on all host cores, bounded sample

@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing for ensembles: independent disorder realisations are the natural shard
+(SURVEY.md section 8e). One process per GPU; rank g owns a contiguous range of realisations
+and the matching disjoint pcg32 seeds; nothing is exchanged during the evolution, per-realisation
+results (return codes, S, A, u_frame, mean f_frame) are gathered afterwards.
+
+``torch.distributed`` is plumbing only (NCCL on the GPUs, gloo in the CPU tests).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_realisations(total: int, rank: int, world: int) -> tuple[int, int]:
+    """(first, count) of the realisations rank `rank` integrates: contiguous, balanced to one."""
+    if not (0 <= rank < world) or total < 0:
+        raise ValueError("bad shard request")
+    base, extra = divmod(total, world)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def shard_seed(seed: int, first: int, size: int) -> int:
+    """Seed of a shard whose first realisation has global index `first`: realisation r of the
+    whole ensemble uses initstates seed + r*size + p (Line1d.h:148-151 per realisation)."""
+    return int(seed) + int(first) * int(size)
+
+
+def make_sharded(cls, total_realisations: int, rank: int, world: int, *, seed: int, **kw):
+    """Construct this rank's shard of an ``Ensemble_*`` class."""
+    first, count = shard_realisations(total_realisations, rank, world)
+    size = int(np.prod(kw["shape"]))
+    return cls(nrealisations=count, seed=shard_seed(seed, first, size), **kw), first, count
+
+
+def gather_per_realisation(local: np.ndarray, total: int, group=None) -> np.ndarray:
+    """All ranks receive the [total] array assembled from every rank's [count] slice."""
+    import torch
+    import torch.distributed as dist
+
+    local = np.ascontiguousarray(local)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local.copy()
+    world = dist.get_world_size(group)
+    device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    counts = [shard_realisations(total, r, world)[1] for r in range(world)]
+    width = max(counts)
+    pad = np.zeros(width, dtype=local.dtype)
+    pad[: local.size] = local
+    mine = torch.from_numpy(pad).to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])

@@ -22,4 +22,5 @@ del ens
 ens = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=4 * R, kernel=2, **kw)
 ens.u_frame = np.full(4 * R, 1.0)
 ens.timeSteps(10)
+ens.timeSteps(10)
 print("stream", 4 * R * N * 10 / ens.last_kernel_seconds)
