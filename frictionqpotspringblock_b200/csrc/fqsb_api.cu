@@ -66,6 +66,10 @@ struct fqsb_system {
     Ctl* h_ctl;         // pinned [R]
     int* h_err;         // pinned [2]
     double* d_pref;
+    // K7 (LongRange as a DMMA Toeplitz GEMM) for lines beyond the resident kernel
+    bool lr_gemm;
+    double *d_lr_tab, *d_lr_w, *d_lr_y;
+    double lr_rowsum;
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -151,7 +155,20 @@ static int ensure_forces(fqsb_system* s)
         s->forces_frozen = false;
     }
     if (!s->forces_valid && !s->forces_frozen) {
-        k_forces<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, s->F, 15);
+        int mask = 15;
+        if (s->lr_gemm) { // f_interactions through the tensor-core GEMM instead of O(N^2) loads
+            k_lr_shift<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, s->d_lr_w);
+            cudaError_t e = launch_lr_gemm(s->P, s->d_lr_tab, s->d_lr_w, s->d_lr_y, s->stream);
+            if (e != cudaSuccess) {
+                return cuda_fail(e, "k_lr_gemm");
+            }
+            s->F.lr_w = s->d_lr_w;
+            s->F.lr_y = s->d_lr_y;
+            s->F.lr_rowsum = s->lr_rowsum;
+            s->launches += 2;
+            mask = 13 | 16;
+        }
+        k_forces<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, s->F, mask);
         CU(cudaGetLastError());
         s->launches++;
         s->forces_valid = true;
@@ -311,6 +328,9 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->steps = 0;
     s->last_kernel = "";
     s->ev0 = s->ev1 = nullptr;
+    s->lr_gemm = false;
+    s->d_lr_tab = s->d_lr_w = s->d_lr_y = nullptr;
+    s->lr_rowsum = 0.0;
     s->kernel_ms = 0.0;
     s->kernel_launches = 0;
     memset(&s->F, 0, sizeof s->F);
@@ -400,6 +420,28 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
                                cudaMemcpyHostToDevice, s->stream));
             CU(cudaStreamSynchronize(s->stream));
             S.pref = s->d_pref;
+            // circulant table tab[k] = pref[min(k, N-k)] (detail.h:859-862) and its row sum
+            ResidentCfg cfg;
+            const bool stream_path = (par->kernel & 15) == 2 || resident_cfg(P.N).B == 0;
+            (void)cfg;
+            if (stream_path && P.N % 2 == 0 && P.N >= 256 &&
+                lr_gemm_smem(P.N) <= 227 * 1024) {
+                std::vector<double> tab((size_t)P.N, 0.0);
+                double rowsum = 0.0;
+                for (i64 k = 1; k < P.N; ++k) {
+                    i64 d = k < P.N - k ? k : P.N - k;
+                    tab[(size_t)k] = pref[(size_t)d];
+                    rowsum += tab[(size_t)k];
+                }
+                TRY(dev_alloc(s, &s->d_lr_tab, (size_t)P.N));
+                TRY(dev_alloc(s, &s->d_lr_w, n));
+                TRY(dev_alloc(s, &s->d_lr_y, n));
+                CU(cudaMemcpyAsync(s->d_lr_tab, tab.data(), (size_t)P.N * sizeof(double),
+                                   cudaMemcpyHostToDevice, s->stream));
+                CU(cudaStreamSynchronize(s->stream));
+                s->lr_rowsum = rowsum;
+                s->lr_gemm = true;
+            }
         }
         k_init<<<grid_for(s->n), 256, 0, s->stream>>>(P, S);
         CU(cudaGetLastError());
@@ -689,7 +731,10 @@ int fqsb_residual(fqsb_system* s, double* out)
 {
     TRY(enter(s));
     // frozen forces are reduced as stored; otherwise they are derived on the fly
-    TRY(reduce_to_host(s, s->forces_frozen ? 0 : 1, 1, nullptr));
+    if (s->lr_gemm && !s->forces_frozen) {
+        TRY(ensure_forces(s));
+    }
+    TRY(reduce_to_host(s, (s->forces_frozen || s->lr_gemm) ? 0 : 1, 1, nullptr));
     for (i64 r = 0; r < s->R; ++r) { // detail.h:1512-1520
         double r_fres = std::sqrt(s->h_out[4 * r]);
         double r_fext = std::sqrt(s->h_out[4 * r + 1]);
@@ -756,6 +801,9 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg)
 
 static int ensure_stream_buffers(fqsb_system* s)
 {
+    if (s->lr_gemm) {
+        return FQSB_OK; // the LongRange GEMM path updates in place (no neighbour reads)
+    }
     if (!s->S.u2) {
         TRY(dev_alloc(s, &s->S.u2, (size_t)s->n));
         if (s->par.minimisation != FQSB_MIN_OVERDAMPED) {
@@ -823,7 +871,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
             return fail(FQSB_EUNSUPPORTED, "system too large for the resident kernel");
         }
         TRY(ensure_stream_buffers(s));
-        s->last_kernel = overdamped ? "stream_nopassing" : stream_step_name(s->P);
+        s->last_kernel = overdamped ? "stream_nopassing"
+                                    : (s->lr_gemm ? "stream_longrange_dmma" : stream_step_name(s->P));
         // fixed-step calls without a moving frame need no per-step decision on the device
         const int finalise = (A.mode != MODE_FIXED || A.flow) ? 1 : 0;
         i64 remaining = A.max_steps; // upper bound on launches still useful
@@ -834,21 +883,25 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
                                           : (remaining < batch ? remaining : batch);
             CU(cudaEventRecord(s->ev0, s->stream));
             for (i64 b = 0; b < nb; ++b) {
-                cudaError_t e = overdamped
-                                    ? launch_stream_sweep(s->P, s->S, A, s->stream)
-                                    : launch_stream_step(s->P, s->S, A, s->stream,
-                                                         (int)((launched + b) & 1), finalise);
+                cudaError_t e =
+                    overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream)
+                    : s->lr_gemm
+                        ? launch_lr_step(s->P, s->S, A, s->d_lr_tab, s->lr_rowsum, s->d_lr_w,
+                                         s->d_lr_y, s->stream, finalise)
+                        : launch_stream_step(s->P, s->S, A, s->stream, (int)((launched + b) & 1),
+                                             finalise);
                 if (e != cudaSuccess) {
                     return cuda_fail(e, "stream kernel launch");
                 }
             }
             CU(cudaEventRecord(s->ev1, s->stream));
             launched += nb;
-            s->launches += overdamped ? 2 * nb : nb;
-            s->kernel_launches += overdamped ? 2 * nb : nb;
+            s->launches += overdamped ? 2 * nb : (s->lr_gemm ? 3 * nb : nb);
+            s->kernel_launches += overdamped ? 2 * nb : (s->lr_gemm ? 3 * nb : nb);
             remaining -= nb;
             if (!finalise && !overdamped && remaining <= 0) {
-                k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, A.max_steps);
+                k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, A.max_steps,
+                                                               s->lr_gemm ? 1 : 0);
                 CU(cudaGetLastError());
                 s->launches++;
             }

@@ -36,15 +36,24 @@ __global__ void k_stream_settle(const Par P, const State S, int with_va)
 }
 
 // fixed-step streaming calls keep no per-step bookkeeping on the device: settle it at the end
-__global__ void k_stream_fixed_done(const Par P, const State S, i64 nsteps)
+__global__ void k_stream_fixed_done(const Par P, const State S, i64 nsteps, int inplace)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < P.R) {
         Ctl& c = S.ctl[r];
         c.inc += nsteps; // detail.h:1541
         c.steps = nsteps;
-        c.flip = (int)(nsteps & 1);
+        c.flip = inplace ? 0 : (int)(nsteps & 1);
         c.status = ST_EXHAUSTED;
+    }
+}
+
+// LongRange GEMM path: W = u - u_frame, and f_interactions = Y - rowsum * W
+__global__ void k_lr_shift(const Par P, const State S, double* W)
+{
+    const i64 n = P.N * P.R;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        W[g] = S.u[g] - S.u_frame[g / P.N];
     }
 }
 
@@ -122,6 +131,8 @@ __global__ void k_align(const Par P, const State S, const double* du)
 // (detail.h:1324) from the stored components.
 struct ForceArrays {
     double *f, *f_pot, *f_int, *f_frame, *f_damp;
+    const double *lr_w, *lr_y; // mask bit 16: f_int = lr_y - lr_rowsum * lr_w (K7 path)
+    double lr_rowsum;
 };
 
 __global__ void k_forces(const Par P, const State S, const ForceArrays F, int mask)
@@ -135,7 +146,10 @@ __global__ void k_forces(const Par P, const State S, const ForceArrays F, int ma
         if (mask & 1) {
             F.f_pot[g] = f_potential_rt(P, uc, S.yl[g], S.yr[g]);
         }
-        if (mask & 2) {
+        if (mask & 16) {
+            F.f_int[g] = F.lr_y[g] - F.lr_rowsum * F.lr_w[g];
+        }
+        else if (mask & 2) {
             int i = 0, j = 0;
             if (P.rank == 2) {
                 i = p / P.cols;

@@ -82,5 +82,11 @@ const char* stream_step_name(const Par& P);
 cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
                                 cudaStream_t stream);
 bool combination_supported(int pot, int inter);
+// defined in fqsb_longrange.cu (K7: DMMA Toeplitz GEMM)
+size_t lr_gemm_smem(i64 N);
+cudaError_t launch_lr_gemm(const Par& P, const double* tab, const double* W, double* Y,
+                           cudaStream_t stream);
+cudaError_t launch_lr_step(const Par& P, const State& S, const RunArgs& A, const double* tab,
+                           double rowsum, double* W, double* Y, cudaStream_t stream, int finalise);
 
 } // namespace fqsb

@@ -34,4 +34,7 @@ def assert_same_state(o, p, exact=True, rtol=1e-12):
     assert np.array_equal(o.chunk.left_of_align, p.chunk.left_of_align)
     assert np.array_equal(o.chunk.right_of_align, p.chunk.right_of_align)
     assert o.inc == p.inc
-    assert o.u_frame == p.u_frame
+    if exact:
+        assert o.u_frame == p.u_frame
+    else:
+        assert np.isclose(o.u_frame, p.u_frame, rtol=1e-12, atol=0)

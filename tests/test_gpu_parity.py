@@ -47,7 +47,10 @@ def kicked(o, p):
 @pytest.mark.parametrize("N", [7, 300, 1000])
 def test_fixed_steps_line1d(cls, extra, exact, N, kernel):
     o, p = pair("Line1d", cls, shape=[N], k_frame=1.0 / N, kernel=kernel, **extra, **PHYS)
-    assert_same_state(o, p, exact)
+    rtol = 1e-12
+    if cls == "System_Cuspy_LongRange" and kernel == 2 and N >= 256:
+        exact, rtol = False, 1e-10  # tensor-core GEMM re-associates the O(N^2) sum (K7)
+    assert_same_state(o, p, exact, rtol)
     if cls == "System_Smooth_Laplace":
         for s in (o, p):  # no event-driven protocol for the smooth potential (detail.h:420)
             s.u_frame = 3.0
@@ -56,7 +59,7 @@ def test_fixed_steps_line1d(cls, extra, exact, N, kernel):
     for n in (1, 2, 37, 160):
         o.timeSteps(n)
         p.timeSteps(n)
-        assert_same_state(o, p, exact)
+        assert_same_state(o, p, exact, rtol)
     assert p.last_kernel.startswith("resident" if kernel == 1 else "stream")
 
 
@@ -302,3 +305,47 @@ def test_ensemble_equals_independent_systems():
         assert ens.inc[r] == s.inc
         assert ens.u_frame[r] == s.u_frame
     assert len(set(ens.inc.tolist())) > 1  # realisations stop at their own step
+
+
+@pytest.mark.parametrize("N,alpha", [(512, 1.0), (1000, 1.5), (4400, 0.5)])
+def test_longrange_tensor_core_gemm_matches_oracle(N, alpha):
+    """K7: LongRange through the DMMA Toeplitz GEMM (streaming path) against the oracle's exact
+    O(N^2) sum: forces within 1e-12 of the force scale, well indices exact over a fixed number of
+    steps (the GEMM re-associates the sum, so positions agree to rounding, not bit for bit)."""
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, alpha=alpha, **PHYS)
+    o, p = pair("Line1d", "System_Cuspy_LongRange", kernel=2, **kw)
+    rng = np.random.default_rng(5)
+    u = 3.0 * rng.standard_normal(N) + 20000.0  # large offset: exercises the cancellation (H5)
+    for s in (o, p):
+        s.u_frame = 20001.0
+        s.u = u
+    scale = np.abs(o.f_interactions).max()
+    assert np.abs(o.f_interactions - p.f_interactions).max() <= 1e-12 * scale
+    assert np.isclose(o.residual, p.residual, rtol=1e-10)
+    for s in (o, p):
+        s.timeSteps(25)
+    assert p.last_kernel == "stream_longrange_dmma"
+    assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+    assert np.abs(o.u - p.u).max() <= 1e-10
+    assert np.abs(o.v - p.v).max() <= 1e-10
+    ro = o.minimise()
+    rp = p.minimise()
+    assert ro == rp == 0
+    assert abs(o.inc - p.inc) <= 1
+    assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+
+
+def test_longrange_gemm_ensemble_matches_resident():
+    F = product()
+    N, R = 1024, 70  # ragged realisation tile (64 + 6)
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, alpha=1.5, nrealisations=R, **PHYS)
+    a = F.Line1d.Ensemble_Cuspy_LongRange(kernel=1, **kw)  # exact O(N^2) sum, resident
+    b = F.Line1d.Ensemble_Cuspy_LongRange(kernel=2, **kw)  # tensor-core GEMM
+    for s in (a, b):
+        s.u_frame = np.full(R, 1.5)
+        s.timeSteps(40)
+    assert a.last_kernel == "resident" and b.last_kernel == "stream_longrange_dmma"
+    assert np.array_equal(a.chunk.index_at_align, b.chunk.index_at_align)
+    assert np.abs(a.u - b.u).max() <= 1e-11
+    scale = np.abs(a.f_interactions).max()
+    assert np.abs(a.f_interactions - b.f_interactions).max() <= 1e-11 * scale
