@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--ref-inner", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
+    ap.add_argument("--no-events", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -357,6 +358,32 @@ def main():
                 pass
         del ens2
 
+    # ---- quasistatic events/s (BASELINE metric, second part): one event = eventDrivenStep to
+    #      the next instability + kick + minimise, on every realisation of a fresh ensemble
+    events = None
+    if not args.no_events:
+        Re = min(R, 4096)
+        ens3 = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=Re, seed=rank * R * N,
+                                               device=local_rank, **kw)
+        ens3.set_stream(stream.cuda_stream)
+        ens3.minimise()
+        nev = 3
+        barrier()
+        t0 = time.perf_counter()
+        steps0 = ens3.step_count
+        for _ in range(nev):
+            ens3.eventDrivenStep(1e-3, False)
+            ens3.eventDrivenStep(1e-3, True)
+            ret = ens3.minimise()
+            assert np.all(ret == 0)
+        barrier()
+        ev_sec = max_over_ranks(time.perf_counter() - t0)
+        events = {"value": world * Re * nev / ev_sec, "unit": "events/s",
+                  "realisations_per_gpu": Re, "events_per_realisation": nev,
+                  "mean_minimise_steps": (ens3.step_count - steps0) / (Re * nev),
+                  "block_updates_per_s": world * (ens3.step_count - steps0) * N / ev_sec}
+        del ens3
+
     # ---- CPU baseline (rank 0): the oracle port on all host cores, bounded sample
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -382,6 +409,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_sec / K},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "quasistatic_events": events,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
