@@ -816,6 +816,197 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
     }
 }
 
+// ---- 2-D stencils (5- and 9-point): row-marching strips ---------------------------------------
+// A CTA owns a strip of FQSB_S2_TX columns and marches over FQSB_S2_TY rows. The new positions
+// of rows i-1, i, i+1 live in a 4-slot ring in shared memory (one barrier per row); every cell's
+// u,v,a,y_l,y_r is loaded exactly once (plus the 2 halo rows per strip and 2 halo columns per
+// row), as double2, one row ahead of its use.
+#define FQSB_S2_THREADS 256
+#define FQSB_S2_TX (2 * FQSB_S2_THREADS)
+#define FQSB_S2_TY 32
+
+template <int INT, bool UNIT>
+__global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
+    k_stream_2d(const __grid_constant__ Par P, const __grid_constant__ State S,
+                const __grid_constant__ RunArgs A, const int flip, const int finalise)
+{
+    constexpr int TX = FQSB_S2_TX, TY = FQSB_S2_TY;
+    __shared__ __align__(16) double sun[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
+    __shared__ double scratch[32 * 2];
+    __shared__ int iscratch[32 * 4];
+    __shared__ int s_last;
+    const int t = threadIdx.x;
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    const int status = ctl.status;
+    const int R_ = P.rows, C_ = P.cols;
+    const int strips = (C_ + TX - 1) / TX;
+    const int strip = blockIdx.x % strips, band = blockIdx.x / strips;
+    const int c0 = strip * TX, row0 = band * TY;
+    const int cnt = C_ - c0 < TX ? C_ - c0 : TX; // columns of this strip (even)
+    const int nrow = R_ - row0 < TY ? R_ - row0 : TY;
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
+    const double* __restrict__ vi = (flip ? S.v2 : S.v) + base;
+    const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
+    double* __restrict__ uo = (flip ? S.u : S.u2) + base;
+    double* __restrict__ vo = (flip ? S.v : S.v2) + base;
+    double* __restrict__ ao = (flip ? S.a : S.a2) + base;
+    const double c2 = 0.5 * P.dt * P.dt;
+    const bool act = 2 * t < cnt;
+    const int col = c0 + 2 * t;
+    // periodic halo columns of this strip
+    const int hcol = t == 0 ? (c0 == 0 ? C_ - 1 : c0 - 1) : (c0 + cnt == C_ ? 0 : c0 + cnt);
+    double uf = S.u_frame[r];
+    if (A.flow) {
+        uf += A.v_frame * P.dt;
+    }
+    if (status != ST_RUNNING) {
+        return;
+    }
+
+    // raw state of global row `gr` (wrapped): own pair + this thread's halo column
+    struct RowRegs {
+        double2 u, v, a;
+        double hu, hv, ha;
+    };
+    auto load_row = [&](int gr, RowRegs& x) {
+        const int wr = gr < 0 ? gr + R_ : (gr >= R_ ? gr - R_ : gr);
+        const i64 rowoff = (i64)wr * C_;
+        if (act) {
+            x.u = *reinterpret_cast<const double2*>(ui + rowoff + col);
+            x.v = *reinterpret_cast<const double2*>(vi + rowoff + col);
+            x.a = *reinterpret_cast<const double2*>(ai + rowoff + col);
+        }
+        if (t < 2) {
+            const i64 q = rowoff + hcol;
+            x.hu = ui[q];
+            x.hv = vi[q];
+            x.ha = ai[q];
+        }
+    };
+    // new positions (detail.h:1549) of a loaded row -> ring slot; returns the own pair
+    auto positions = [&](const RowRegs& x, int slot, double2& un) {
+        if (act) {
+            un.x = x.u.x + P.dt * x.v.x + c2 * x.a.x;
+            un.y = x.u.y + P.dt * x.v.y + c2 * x.a.y;
+            *reinterpret_cast<double2*>(&sun[slot][2 + 2 * t]) = un;
+        }
+        if (t < 2) {
+            sun[slot][t == 0 ? 1 : 2 + cnt] = x.hu + P.dt * x.hv + c2 * x.ha;
+        }
+    };
+
+    double acc[2] = {0.0, 0.0};
+    int hops = 0, dS = 0, dA = 0, underflow = 0;
+    bool nan = false;
+    RowRegs cur, nxt, nn;
+    cur.u = cur.v = cur.a = nxt.u = nxt.v = nxt.a = nn.u = nn.v = nn.a = make_double2(0.0, 0.0);
+    cur.hu = cur.hv = cur.ha = nxt.hu = nxt.hv = nxt.ha = nn.hu = nn.hv = nn.ha = 0.0;
+    double2 un_c = make_double2(0.0, 0.0), un_n = un_c, un_dummy = un_c;
+    double2 l2 = un_c, r2 = un_c, l2n = un_c, r2n = un_c;
+    {
+        RowRegs top;
+        top.u = top.v = top.a = make_double2(0.0, 0.0);
+        top.hu = top.hv = top.ha = 0.0;
+        load_row(row0 - 1, top);
+        load_row(row0, cur);
+        load_row(row0 + 1, nxt);
+        if (act) {
+            l2 = *reinterpret_cast<const double2*>(S.yl + base + (i64)row0 * C_ + col);
+            r2 = *reinterpret_cast<const double2*>(S.yr + base + (i64)row0 * C_ + col);
+        }
+        positions(top, (row0 + 3) & 3, un_dummy);
+        positions(cur, row0 & 3, un_c);
+    }
+
+    for (int i = row0; i < row0 + nrow; ++i) {
+        // prefetch: raw state two rows ahead and the wells one row ahead land during this row
+        if (i + 2 <= row0 + nrow) {
+            load_row(i + 2, nn);
+        }
+        if (act && i + 1 < row0 + nrow) {
+            l2n = *reinterpret_cast<const double2*>(S.yl + base + (i64)(i + 1) * C_ + col);
+            r2n = *reinterpret_cast<const double2*>(S.yr + base + (i64)(i + 1) * C_ + col);
+        }
+        positions(nxt, (i + 1) & 3, un_n);
+        const i64 rowoff = (i64)i * C_;
+        const double2 v_c = cur.v, a_c = cur.a;
+        __syncthreads();
+        if (act) {
+            const double* up = &sun[(i + 3) & 3][2]; // row i-1
+            const double* mid = &sun[i & 3][2];
+            const double* dn = &sun[(i + 1) & 3][2];
+            double uc[2] = {un_c.x, un_c.y};
+            double wl[2] = {l2.x, l2.y};
+            double wr[2] = {r2.x, r2.y};
+            double vv[2] = {v_c.x, v_c.y};
+            double aa[2] = {a_c.x, a_c.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (uc[e] > wr[e] || !(uc[e] > wl[e])) { // rare: well change, detail.h:144
+                    const i64 gp = base + rowoff + col + e;
+                    u64 st = S.rng[gp];
+                    i64 i_before = S.idx[gp];
+                    int moved = well_align(P, uc[e], wl[e], wr[e], st, i_before, &underflow);
+                    S.rng[gp] = st;
+                    S.idx[gp] = i_before + moved;
+                    S.yl[gp] = wl[e];
+                    S.yr[gp] = wr[e];
+                    hops += moved != 0;
+                    track_hop(A, gp, i_before, moved, dS, dA);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lc = 2 * t + e;
+                double fi;
+                if (INT == INT_LAPLACE2D) { // detail.h:557-582 (same operand order)
+                    double lap = up[lc] + dn[lc] + mid[lc - 1] + mid[lc + 1] - 4 * uc[e];
+                    fi = UNIT ? lap : lap * P.k1;
+                }
+                else { // QuarticGradient2d, detail.h:700-711
+                    const double mk4_3 = P.k2 / 3.0;
+                    const double mk4_23 = 2.0 * mk4_3;
+                    const double u_pj = dn[lc], u_mj = up[lc], u_cp = mid[lc + 1], u_cm = mid[lc - 1];
+                    double l = u_pj + u_mj + u_cp + u_cm - 4 * uc[e];
+                    double dudx = 0.5 * (u_pj - u_mj);
+                    double dudy = 0.5 * (u_cp - u_cm);
+                    double d2udxdy = 0.25 * (dn[lc + 1] - dn[lc - 1] - up[lc + 1] + up[lc - 1]);
+                    double d2udx2 = u_pj - 2 * uc[e] + u_mj;
+                    double d2udy2 = u_cp - 2 * uc[e] + u_cm;
+                    fi = l * (P.k1 + mk4_3) + mk4_23 * (dudx * dudx * d2udx2 + dudy * dudy * d2udy2 +
+                                                        2.0 * dudx * dudy * d2udxdy);
+                }
+                double fp = f_potential<POT_CUSPY, UNIT>(P, uc[e], wl[e], wr[e]);
+                double ff = P.k_frame * (uf - uc[e]);
+                double F = ff + fp + fi;
+                double f = verlet_tail<UNIT>(P, F, vv[e], aa[e]);
+                acc[0] += f * f;
+                acc[1] += ff * ff;
+                nan |= uc[e] != uc[e];
+            }
+            *reinterpret_cast<double2*>(uo + rowoff + col) = un_c;
+            *reinterpret_cast<double2*>(vo + rowoff + col) = make_double2(vv[0], vv[1]);
+            *reinterpret_cast<double2*>(ao + rowoff + col) = make_double2(aa[0], aa[1]);
+        }
+        un_c = un_n;
+        cur = nxt;
+        nxt = nn;
+        l2 = l2n;
+        r2 = r2n;
+    }
+    if (nan) {
+        S.err[1] = 1;
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+    if (finalise) {
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+    }
+}
+
 // ---- generic fallback (2-D stencils, LongRange, odd N): one block per thread, neighbours'
 //      new positions recomputed from global memory (served by L1/L2)
 template <int POT, int INT>

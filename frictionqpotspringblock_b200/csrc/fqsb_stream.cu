@@ -55,12 +55,23 @@ cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
 // tiles per realisation of the step kernel that launch_stream_step() picks
 static bool use_tiled_1d(const Par& P) { return P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0; }
 
+static bool use_tiled_2d(const Par& P) { return P.rank == 2 && P.cols % 2 == 0; }
+
 int stream_step_tiles(const Par& P, int generic_tiles)
 {
-    return use_tiled_1d(P) ? (int)((P.N + FQSB_ST_TILE - 1) / FQSB_ST_TILE) : generic_tiles;
+    if (use_tiled_1d(P)) {
+        return (int)((P.N + FQSB_ST_TILE - 1) / FQSB_ST_TILE);
+    }
+    if (use_tiled_2d(P)) {
+        return ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + FQSB_S2_TY - 1) / FQSB_S2_TY);
+    }
+    return generic_tiles;
 }
 
-const char* stream_step_name(const Par& P) { return use_tiled_1d(P) ? "stream_1d" : "stream"; }
+const char* stream_step_name(const Par& P)
+{
+    return use_tiled_1d(P) ? "stream_1d" : (use_tiled_2d(P) ? "stream_2d" : "stream");
+}
 
 cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
                                cudaStream_t stream, int flip, int finalise)
@@ -82,6 +93,23 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
         case 7: FQSB_TILED(POT_SMOOTH, INT_LAPLACE1D)
         case 8: FQSB_TILED(POT_CUSPY, INT_NONE)
         default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
+    if (use_tiled_2d(P)) {
+        dim3 grid((unsigned)stream_step_tiles(P, 0), (unsigned)P.R);
+        const bool unit = unit_parameters(P);
+        if (P.inter == INT_LAPLACE2D) {
+            if (unit)
+                k_stream_2d<INT_LAPLACE2D, true><<<grid, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, finalise);
+            else
+                k_stream_2d<INT_LAPLACE2D, false><<<grid, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, finalise);
+        }
+        else {
+            if (unit)
+                k_stream_2d<INT_QUARTICGRADIENT2D, true><<<grid, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, finalise);
+            else
+                k_stream_2d<INT_QUARTICGRADIENT2D, false><<<grid, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, finalise);
         }
         return cudaGetLastError();
     }
