@@ -875,7 +875,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
                                     : (s->lr_gemm ? "stream_longrange_dmma" : stream_step_name(s->P));
         // fixed-step calls without a moving frame need no per-step decision on the device
         const int finalise = (A.mode != MODE_FIXED || A.flow) ? 1 : 0;
-        i64 remaining = A.max_steps; // upper bound on launches still useful
+        // upper bound on launches still useful (no-passing: launch l decides sweep l-1)
+        i64 remaining = overdamped ? A.max_steps + 1 : A.max_steps;
         i64 launched = 0;
         i64 batch = 16;
         for (;;) {
@@ -884,7 +885,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
             CU(cudaEventRecord(s->ev0, s->stream));
             for (i64 b = 0; b < nb; ++b) {
                 cudaError_t e =
-                    overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream)
+                    overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream,
+                                                     (int)((launched + b) & 1), launched + b == 0)
                     : s->lr_gemm
                         ? launch_lr_step(s->P, s->S, A, s->d_lr_tab, s->lr_rowsum, s->d_lr_w,
                                          s->d_lr_y, s->stream, finalise)
@@ -896,8 +898,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
             }
             CU(cudaEventRecord(s->ev1, s->stream));
             launched += nb;
-            s->launches += overdamped ? 2 * nb : (s->lr_gemm ? 3 * nb : nb);
-            s->kernel_launches += overdamped ? 2 * nb : (s->lr_gemm ? 3 * nb : nb);
+            s->launches += s->lr_gemm ? 3 * nb : nb;
+            s->kernel_launches += s->lr_gemm ? 3 * nb : nb;
             remaining -= nb;
             if (!finalise && !overdamped && remaining <= 0) {
                 k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, A.max_steps,
@@ -927,6 +929,10 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
         CU(cudaGetLastError());
         s->launches += 2;
+        if (overdamped) {
+            // wells moved by the discarded look-ahead sweep follow the kept configuration again
+            TRY(align(s, nullptr));
+        }
     }
     for (i64 r = 0; r < s->R; ++r) {
         s->steps += s->h_ctl[r].steps;

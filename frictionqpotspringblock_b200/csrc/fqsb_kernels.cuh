@@ -6,7 +6,7 @@
 //  k_resident_nopassing<..>     K6: overdamped no-passing Jacobi sweeps, same residency.
 //  k_stream_step<POT,INT>       K1: one fused Verlet step per launch over all blocks, streaming
 //                               u,v,a,y_l,y_r once (64 B per block-update), last-CTA finalise.
-//  k_stream_sweep / _residual   K6 streaming.
+//  k_stream_np                 K6 streaming (sweep fused with the previous residual).
 //  k_init / k_align / k_forces / k_reduce_* / k_chunk_data / ...   K4, K5, K8 helpers.
 #pragma once
 
@@ -1084,11 +1084,20 @@ __global__ void __launch_bounds__(256)
 }
 
 // =============================================================================================
-// K6 streaming: sweep (u -> u2) then residual of the new configuration + stop decision.
+// K6 streaming: overdamped no-passing sweeps (detail.h:1694-1753), one fused launch per sweep.
+// Launch l evaluates the residual of its INPUT configuration (= the result of sweep l-1, so the
+// stop decision of sweep l-1 is taken by this launch's last CTA) and, in the same pass over the
+// data, performs sweep l into the other buffer: u is read once and written once, the wells are
+// read once -- 32 B per block-update. When the decision says stop, the configuration to keep is
+// the input buffer; the wells the discarded sweep moved are re-aligned by the host (k_align).
 // =============================================================================================
 template <int INT>
-__global__ void __launch_bounds__(256) k_stream_sweep(const Par P, const State S, const RunArgs A)
+__global__ void __launch_bounds__(256)
+    k_stream_np(const __grid_constant__ Par P, const __grid_constant__ State S,
+                const __grid_constant__ RunArgs A, const int flip, const int first)
 {
+    __shared__ double scratch[32 * 2];
+    __shared__ int s_last;
     const int r = blockIdx.y;
     Ctl& ctl = S.ctl[r];
     if (ctl.status != ST_RUNNING) {
@@ -1097,31 +1106,50 @@ __global__ void __launch_bounds__(256) k_stream_sweep(const Par P, const State S
     constexpr bool TWO_D = INT == INT_LAPLACE2D;
     const int N = (int)P.N;
     const i64 base = (i64)r * P.N;
-    const int flip = ctl.flip;
     const double* __restrict__ uold = (flip ? S.u2 : S.u) + base;
     double* __restrict__ unew = (flip ? S.u : S.u2) + base;
     const double uf = S.u_frame[r];
     const double k = P.k1, kf = P.k_frame, mu = P.mu;
     const double denom = (TWO_D ? 4 : 2) * k + kf + mu;
     int underflow = 0;
+    bool nan = false;
+    double acc[2] = {0.0, 0.0};
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
-        double uneigh;
-        if (!TWO_D) {
+        const double uc = uold[p];
+        double uneigh, lap;
+        if (!TWO_D) { // detail.h:1715-1723 and 480-486
             int l = p == 0 ? N - 1 : p - 1, rr = p == N - 1 ? 0 : p + 1;
-            uneigh = uold[l] + uold[rr];
+            const double ul = uold[l], ur = uold[rr];
+            uneigh = ul + ur;
+            lap = ul - 2 * uc + ur;
         }
-        else {
+        else { // detail.h:557-582
             const int R = P.rows, C = P.cols, i = p / C, jj = p - i * C;
             int im = (i == 0 ? R - 1 : i - 1) * C, ip = (i == R - 1 ? 0 : i + 1) * C;
             int jm = jj == 0 ? C - 1 : jj - 1, jp = jj == C - 1 ? 0 : jj + 1;
-            uneigh = uold[im + jj] + uold[ip + jj] + uold[i * C + jm] + uold[i * C + jp];
+            const double a = uold[im + jj], b = uold[ip + jj], c = uold[i * C + jm],
+                         d = uold[i * C + jp];
+            uneigh = a + b + c + d;
+            lap = a + b + c + d - 4 * uc;
         }
         double yl = S.yl[base + p], yr = S.yr[base + p];
+        // residual of the input configuration: f = f_pot + f_int + f_frame (detail.h:1740-1745)
+        {
+            double umin = 0.5 * (yl + yr);
+            double ff = kf * (uf - uc);
+            double fp = mu * (umin - uc);
+            double fi = lap * k;
+            double f = fp + fi + ff;
+            acc[0] += f * f;
+            acc[1] += ff * ff;
+            nan |= uc != uc;
+        }
+        // the sweep (detail.h:1728-1741)
         double un;
         int total = 0;
         u64 st = 0;
+        i64 i0 = 0;
         bool loaded = false;
-        const i64 i0 = S.idx[base + p];
         for (;;) {
             double umin = 0.5 * (yl + yr);
             un = (k * uneigh + kf * uf + mu * umin) / denom;
@@ -1130,6 +1158,7 @@ __global__ void __launch_bounds__(256) k_stream_sweep(const Par P, const State S
             }
             if (!loaded) {
                 st = S.rng[base + p];
+                i0 = S.idx[base + p];
                 loaded = true;
             }
             int moved = well_align(P, un, yl, yr, st, i0 + total, &underflow);
@@ -1149,43 +1178,6 @@ __global__ void __launch_bounds__(256) k_stream_sweep(const Par P, const State S
     if (underflow) {
         S.err[0] = 1;
     }
-}
-
-template <int INT>
-__global__ void __launch_bounds__(256) k_stream_sweep_residual(const Par P, const State S,
-                                                               const RunArgs A)
-{
-    __shared__ double scratch[32 * 2];
-    __shared__ int s_last;
-    const int r = blockIdx.y;
-    Ctl& ctl = S.ctl[r];
-    if (ctl.status != ST_RUNNING) {
-        return;
-    }
-    const int N = (int)P.N;
-    const i64 base = (i64)r * P.N;
-    const int flip = ctl.flip;
-    const double* __restrict__ un = (flip ? S.u : S.u2) + base; // the sweep's output
-    const double uf = S.u_frame[r];
-    auto U = [&](int q) { return un[q]; };
-    double acc[2] = {0.0, 0.0};
-    bool nan = false;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
-        int i = 0, j = 0;
-        if (INT == INT_LAPLACE2D) {
-            i = p / P.cols;
-            j = p - i * P.cols;
-        }
-        const double uc = un[p];
-        double umin = 0.5 * (S.yl[base + p] + S.yr[base + p]);
-        double ff = P.k_frame * (uf - uc);
-        double fp = P.mu * (umin - uc);
-        double fi = f_interactions<INT>(P, U, nullptr, p, i, j, uc);
-        double f = fp + fi + ff;
-        acc[0] += f * f;
-        acc[1] += ff * ff;
-        nan |= uc != uc;
-    }
     if (nan) {
         S.err[1] = 1;
     }
@@ -1204,26 +1196,32 @@ __global__ void __launch_bounds__(256) k_stream_sweep_residual(const Par P, cons
     }
     __threadfence();
     const int lane = threadIdx.x;
-    double sf = 0.0, sff = 0.0;
-    const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
-    for (int c = lane; c < (int)gridDim.x; c += 32) {
-        sf += all[c * FQSB_NPART];
-        sff += all[c * FQSB_NPART + 1];
-    }
-    sf = warp_sum(sf);
-    sff = warp_sum(sff);
-    Prog g;
-    prog_load(g, ctl);
-    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
-    double res_last = ctl.residual;
-    int status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
-    if (lane < A.niter_tol && lane < FQSB_RING) {
-        ctl.ring[lane] = ring;
+    int status = ST_RUNNING;
+    if (!first) {
+        double sf = 0.0, sff = 0.0;
+        const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
+        for (int c = lane; c < (int)gridDim.x; c += 32) {
+            sf += all[c * FQSB_NPART];
+            sff += all[c * FQSB_NPART + 1];
+        }
+        sf = warp_sum(sf);
+        sff = warp_sum(sff);
+        Prog g;
+        prog_load(g, ctl);
+        double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
+        double res_last = ctl.residual;
+        status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
+        if (lane < A.niter_tol && lane < FQSB_RING) {
+            ctl.ring[lane] = ring;
+        }
+        if (lane == 0) {
+            prog_store(g, ctl);
+            ctl.residual = res_last;
+        }
     }
     if (lane == 0) {
-        prog_store(g, ctl);
-        ctl.residual = res_last;
-        ctl.flip = flip ^ 1;
+        // a stop keeps the input buffer (the sweep of this launch is discarded)
+        ctl.flip = status == ST_RUNNING ? flip ^ 1 : flip;
         ctl.count = 0u;
         ctl.status = status;
     }

@@ -34,5 +34,5 @@ t0 = time.perf_counter()
 ret = s.minimise(max_iter=400, max_iter_is_error=False)
 dt = time.perf_counter() - t0
 print(f"{s.last_kernel}: no-passing sweeps: ret={ret} launches={s.last_kernel_launches} "
-      f"{s.last_kernel_seconds / max(1, s.last_kernel_launches // 2) * 1e6:.1f} us/sweep "
-      f"({n * (s.last_kernel_launches // 2) / s.last_kernel_seconds:.3e} block-updates/s)")
+      f"{s.last_kernel_seconds / max(1, s.last_kernel_launches) * 1e6:.1f} us/sweep "
+      f"({n * s.last_kernel_launches / s.last_kernel_seconds:.3e} block-updates/s)")
