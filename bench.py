@@ -393,7 +393,7 @@ def main():
         cens.time_steps(50)
         sec_probe, _ = cens.time_steps(100)
         rate = nsys * N * 100 / sec_probe
-        Tc = int(min(20000, max(200, 12.0 * rate / (nsys * N))))
+        Tc = int(min(400000, max(200, 12.0 * rate / (nsys * N))))
         csec, _ = cens.time_steps(Tc)
         cpu = {"value": nsys * N * Tc / csec, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nsys} realisations x N={N} x timeSteps({Tc}) on {cores} threads "

@@ -63,6 +63,8 @@ class Params(C.Structure):
         ("seed_stride", C.c_int64),
         ("device", C.c_int32),
         ("kernel", C.c_int32),
+        ("seed_first", C.c_int64),
+        ("seed_period", C.c_int64),
     ]
 
 
@@ -114,6 +116,14 @@ SIGNATURES = {
     "fqsb_chunk_state_at": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fqsb_chunk_restore": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "fqsb_avalanche": (C.c_int, [_P, _P, _P, _P]),
+    "fqsb_set_owned_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
+    "fqsb_logged_steps": (C.c_int, [_P, C.c_int64, _P]),
+    "fqsb_snapshot": (C.c_int, [_P]),
+    "fqsb_rollback": (C.c_int, [_P]),
+    "fqsb_export_cells": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int]),
+    "fqsb_import_cells": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int]),
+    "fqsb_advance_uniformly": (C.c_int, [_P, _P, _P]),
+    "fqsb_reduce_sums": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "fqsb_host_alloc": (_P, [C.c_size_t]),
     "fqsb_host_free": (None, [_P]),
     "fqsb_launch_count": (C.c_int64, [_P]),

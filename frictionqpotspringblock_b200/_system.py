@@ -18,7 +18,7 @@ from ._capi import lib, check
 
 def _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1, k2, k_frame, dt,
             seed, distribution, parameters, offset, nchunk, nrealisations, seed_stride, device,
-            kernel):
+            kernel, seed_first=0, seed_period=0):
     if distribution not in _capi.DIST:
         raise RuntimeError("Unknown distribution: " + str(distribution))  # detail.h:65
     p = _capi.Params()
@@ -43,6 +43,8 @@ def _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
     p.seed_stride = int(seed_stride)
     p.device = int(device)
     p.kernel = int(kernel)
+    p.seed_first = int(seed_first)
+    p.seed_period = int(seed_period)
     return p
 
 
@@ -140,11 +142,11 @@ class Ensemble:
     def __init__(self, potential, interactions, shape, *, m=1.0, eta=0.0, mu=1.0, kappa=0.0,
                  k1=0.0, k2=0.0, k_frame=1.0, dt=0.0, seed=0, distribution="random",
                  parameters=(), offset=-100.0, nchunk=5000, minimisation=0, nrealisations=1,
-                 seed_stride=0, device=-1, kernel=0):
+                 seed_stride=0, device=-1, kernel=0, seed_first=0, seed_period=0):
         self._h = C.c_void_p()
         self._par = _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
                             k2, k_frame, dt, seed, distribution, parameters, offset, nchunk,
-                            nrealisations, seed_stride, device, kernel)
+                            nrealisations, seed_stride, device, kernel, seed_first, seed_period)
         self._shape = tuple(int(i) for i in shape)
         self._R = int(nrealisations)
         self._nchunk = int(nchunk)

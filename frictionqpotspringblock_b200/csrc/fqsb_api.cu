@@ -70,6 +70,16 @@ struct fqsb_system {
     bool lr_gemm;
     double *d_lr_tab, *d_lr_w, *d_lr_y;
     double lr_rowsum;
+    // slab decomposition support: owned range, state snapshot, log buffer
+    i64 own_lo, own_hi;
+    double *snap_d[5];
+    i64* snap_idx;
+    u64* snap_rng;
+    double* snap_uf;
+    Ctl* snap_ctl;
+    bool snap_valid;
+    double* d_log;
+    size_t log_cap;
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -188,7 +198,8 @@ static int frozen_update(fqsb_system* s, int mask)
 static int reduce(fqsb_system* s, int what, int direction, const i64* i_n_dev)
 {
     dim3 grid((unsigned)s->S.tiles, (unsigned)s->R);
-    k_reduce<<<grid, 256, 0, s->stream>>>(s->P, s->S, s->F, what, direction, i_n_dev, s->d_red);
+    k_reduce<<<grid, 256, 0, s->stream>>>(s->P, s->S, s->F, what, direction, i_n_dev, s->d_red,
+                                          (int)s->own_lo, (int)s->own_hi);
     k_reduce_final<<<(unsigned)s->R, 32, 0, s->stream>>>(s->d_red, s->S.tiles, s->d_out);
     CU(cudaGetLastError());
     s->launches += 2;
@@ -329,6 +340,18 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->last_kernel = "";
     s->ev0 = s->ev1 = nullptr;
     s->lr_gemm = false;
+    s->own_lo = 0;
+    s->own_hi = 0;
+    for (int k = 0; k < 5; ++k) {
+        s->snap_d[k] = nullptr;
+    }
+    s->snap_idx = nullptr;
+    s->snap_rng = nullptr;
+    s->snap_uf = nullptr;
+    s->snap_ctl = nullptr;
+    s->snap_valid = false;
+    s->d_log = nullptr;
+    s->log_cap = 0;
     s->d_lr_tab = s->d_lr_w = s->d_lr_y = nullptr;
     s->lr_rowsum = 0.0;
     s->kernel_ms = 0.0;
@@ -369,7 +392,10 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     P.offset = par->offset;
     P.seed = par->seed;
     P.seed_stride = par->seed_stride > 0 ? (u64)par->seed_stride : (u64)P.N;
+    P.seed_first = par->seed_period > 0 ? (u64)par->seed_first : 0ULL;
+    P.seed_period = par->seed_period > 0 ? (u64)par->seed_period : 0ULL;
     s->N = P.N;
+    s->own_hi = P.N;
     s->R = P.R;
     s->n = P.N * P.R;
     s->par.nrealisations = P.R;
@@ -790,9 +816,12 @@ __global__ void k_ctl_begin(const Par P, const State S, int track_user, int over
     }
 }
 
-static bool use_resident(const fqsb_system* s, ResidentCfg* cfg)
+static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
 {
     *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
+    if (mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N) {
+        return false; // slab batches run on the streaming kernels
+    }
     if ((s->par.kernel & 15) == 2 || cfg->B == 0) {
         return false;
     }
@@ -817,9 +846,12 @@ static int ensure_stream_buffers(fqsb_system* s)
 // Runs one dynamics call to completion. On return h_ctl holds the final control blocks.
 static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
 {
-    if (A.mode != MODE_FIXED && (A.niter_tol < 1 || A.niter_tol > FQSB_RING)) {
+    if (A.mode != MODE_FIXED && A.mode != MODE_LOG &&
+        (A.niter_tol < 1 || A.niter_tol > FQSB_RING)) {
         return fail(FQSB_EUNSUPPORTED, "niter_tol must be in [1, 32]");
     }
+    A.own_lo = (int)s->own_lo;
+    A.own_hi = (int)s->own_hi;
     const unsigned rg = (unsigned)((s->R + 127) / 128);
     k_ctl_begin<<<rg, 128, 0, s->stream>>>(s->P, s->S, track_user ? 1 : 0, overdamped ? 1 : 0,
                                            s->d_out);
@@ -837,7 +869,7 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
     }
 
     ResidentCfg cfg;
-    if (use_resident(s, &cfg)) {
+    if (use_resident(s, &cfg, A.mode)) {
         s->last_kernel = overdamped ? "resident_nopassing" : "resident";
         const i64 chunk = (i64)1 << 20;
         for (;;) {
@@ -886,7 +918,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
             for (i64 b = 0; b < nb; ++b) {
                 cudaError_t e =
                     overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream,
-                                                     (int)((launched + b) & 1), launched + b == 0)
+                                                     (int)((launched + b) & 1), launched + b == 0,
+                                                     launched + b < A.max_steps)
                     : s->lr_gemm
                         ? launch_lr_step(s->P, s->S, A, s->d_lr_tab, s->lr_rowsum, s->d_lr_w,
                                          s->d_lr_y, s->stream, finalise)
@@ -1377,6 +1410,183 @@ int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* 
             out_A[r] = (int64_t)s->h_out[4 * r + 1];
         }
     }
+    return FQSB_OK;
+}
+
+// ---- slab decomposition primitives (used by frictionqpotspringblock_b200/slab.py) ---------------
+int fqsb_set_owned_range(fqsb_system* s, int64_t lo, int64_t hi)
+{
+    TRY(enter(s));
+    if (lo < 0 || hi > s->N || lo >= hi) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("0 <= lo < hi <= size"));
+    }
+    s->own_lo = lo;
+    s->own_hi = hi;
+    return FQSB_OK;
+}
+
+int fqsb_logged_steps(fqsb_system* s, int64_t k, double* log)
+{
+    TRY(enter(s));
+    if (k < 1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("k >= 1"));
+    }
+    const size_t need = (size_t)s->R * (size_t)k * FQSB_NLOG;
+    if (need > s->log_cap) {
+        TRY(dev_alloc(s, &s->d_log, need));
+        s->log_cap = need;
+    }
+    CU(cudaMemsetAsync(s->d_log, 0, need * sizeof(double), s->stream));
+    RunArgs A = make_args(MODE_LOG, k);
+    A.log = s->d_log;
+    TRY(run(s, A, s->par.minimisation == FQSB_MIN_OVERDAMPED, false));
+    CU(cudaMemcpyAsync(log, s->d_log, need * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_snapshot(fqsb_system* s)
+{
+    TRY(enter(s));
+    const size_t n = (size_t)s->n;
+    if (!s->snap_idx) {
+        for (int k = 0; k < 5; ++k) {
+            TRY(dev_alloc(s, &s->snap_d[k], n));
+        }
+        TRY(dev_alloc(s, &s->snap_idx, n));
+        TRY(dev_alloc(s, &s->snap_rng, n));
+        TRY(dev_alloc(s, &s->snap_uf, (size_t)s->R));
+        TRY(dev_alloc(s, &s->snap_ctl, (size_t)s->R));
+    }
+    const double* src[5] = {s->S.u, s->S.v, s->S.a, s->S.yl, s->S.yr};
+    for (int k = 0; k < 5; ++k) {
+        CU(cudaMemcpyAsync(s->snap_d[k], src[k], n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU(cudaMemcpyAsync(s->snap_idx, s->S.idx, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->snap_rng, s->S.rng, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->snap_uf, s->S.u_frame, (size_t)s->R * 8, cudaMemcpyDeviceToDevice,
+                       s->stream));
+    CU(cudaMemcpyAsync(s->snap_ctl, s->S.ctl, (size_t)s->R * sizeof(Ctl),
+                       cudaMemcpyDeviceToDevice, s->stream));
+    s->snap_valid = true;
+    return FQSB_OK;
+}
+
+int fqsb_rollback(fqsb_system* s)
+{
+    TRY(enter(s));
+    if (!s->snap_valid) {
+        return fail(FQSB_EASSERT, "no snapshot to roll back to");
+    }
+    const size_t n = (size_t)s->n;
+    double* dst[5] = {s->S.u, s->S.v, s->S.a, s->S.yl, s->S.yr};
+    for (int k = 0; k < 5; ++k) {
+        CU(cudaMemcpyAsync(dst[k], s->snap_d[k], n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU(cudaMemcpyAsync(s->S.idx, s->snap_idx, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->S.rng, s->snap_rng, n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    CU(cudaMemcpyAsync(s->S.u_frame, s->snap_uf, (size_t)s->R * 8, cudaMemcpyDeviceToDevice,
+                       s->stream));
+    CU(cudaMemcpyAsync(s->S.ctl, s->snap_ctl, (size_t)s->R * sizeof(Ctl),
+                       cudaMemcpyDeviceToDevice, s->stream));
+    invalidate_forces(s);
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+static int cells_args(fqsb_system* s, int64_t first, int64_t count)
+{
+    if (first < 0 || count < 1 || first + count > s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("0 <= first, first + count <= size"));
+    }
+    return FQSB_OK;
+}
+
+int fqsb_export_cells(fqsb_system* s, int64_t first, int64_t count, void* buf, int on_device)
+{
+    TRY(enter(s));
+    TRY(cells_args(s, first, count));
+    const size_t bytes = (size_t)count * 7 * 8;
+    u64* dbuf = (u64*)buf;
+    if (!on_device) {
+        TRY(scratch(s, bytes));
+        dbuf = (u64*)s->d_scratch;
+    }
+    k_export_cells<<<grid_for(count), 256, 0, s->stream>>>(s->S, first, count, dbuf);
+    CU(cudaGetLastError());
+    s->launches++;
+    if (!on_device) {
+        CU(cudaMemcpyAsync(buf, dbuf, bytes, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_import_cells(fqsb_system* s, int64_t first, int64_t count, const void* buf, int on_device)
+{
+    TRY(enter(s));
+    TRY(cells_args(s, first, count));
+    const size_t bytes = (size_t)count * 7 * 8;
+    const u64* dbuf = (const u64*)buf;
+    if (!on_device) {
+        TRY(scratch(s, bytes));
+        CU(cudaMemcpyAsync(s->d_scratch, buf, bytes, cudaMemcpyHostToDevice, s->stream));
+        dbuf = (const u64*)s->d_scratch;
+    }
+    k_import_cells<<<grid_for(count), 256, 0, s->stream>>>(s->S, first, count, dbuf);
+    CU(cudaGetLastError());
+    s->launches++;
+    invalidate_forces(s);
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+// advanceUniformly(du, false) with externally agreed displacements (detail.h:2027-2050)
+int fqsb_advance_uniformly(fqsb_system* s, const double* du, const double* du_frame)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s)); // (keeps the stream ordered; cheap)
+    std::vector<double> uf((size_t)s->R);
+    CU(cudaMemcpyAsync(uf.data(), s->S.u_frame, (size_t)s->R * 8, cudaMemcpyDeviceToHost,
+                       s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    for (i64 r = 0; r < s->R; ++r) {
+        uf[(size_t)r] += du_frame[r];
+    }
+    CU(cudaMemcpyAsync(s->S.u_frame, uf.data(), (size_t)s->R * 8, cudaMemcpyHostToDevice,
+                       s->stream));
+    CU(cudaMemcpyAsync(s->d_du, du, (size_t)s->R * 8, cudaMemcpyHostToDevice, s->stream));
+    TRY(advance(s));
+    return check_flags(s);
+}
+
+// raw per-realisation sums over the owned range: out [R][4]
+//   what 1: {sum f^2, sum f_frame^2}   2: {sum v^2, sum f_frame}
+//   what 3: {-, off-branch count, -, min displacement}   4: {sum (i-i_n), #(i != i_n), sum |i-i_n|}
+int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, double* out)
+{
+    TRY(enter(s));
+    if (what < 1 || what > 4) {
+        return fail(FQSB_EASSERT, "unknown reduction");
+    }
+    const i64* d_in = nullptr;
+    if (what == 4) {
+        if (!s->d_in) {
+            TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
+        }
+        CU(cudaMemcpyAsync(s->d_in, i_n, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
+                           s->stream));
+        d_in = s->d_in;
+    }
+    if (what == 3) {
+        TRY(align(s, nullptr));
+    }
+    if (what == 1 && s->lr_gemm) {
+        TRY(ensure_forces(s));
+        what = 0;
+    }
+    TRY(reduce_to_host(s, what, direction, d_in));
+    memcpy(out, s->h_out, (size_t)s->R * 4 * sizeof(double));
     return FQSB_OK;
 }
 

@@ -76,7 +76,11 @@ __global__ void k_init(const Par P, const State S)
     const i64 n = P.N * P.R;
     for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
         const i64 r = g / P.N, p = g - r * P.N;
-        u64 st = pcg_seed(P.seed + (u64)r * P.seed_stride + (u64)p);
+        u64 gp = (u64)p;
+        if (P.seed_period) { // slab: local block p is global block (seed_first + p) mod period
+            gp = (P.seed_first + (u64)p) % P.seed_period;
+        }
+        u64 st = pcg_seed(P.seed + (u64)r * P.seed_stride + gp);
         double d0 = spacing_peek(P, st);
         if (P.consumes) {
             st = pcg_next(st);
@@ -176,7 +180,8 @@ __global__ void k_forces(const Par P, const State S, const ForceArrays F, int ma
 //       4 {sum (i - i_n), #(i != i_n)} and part[2] = sum |i - i_n|
 __global__ void __launch_bounds__(256) k_reduce(const Par P, const State S, const ForceArrays F,
                                                 int what, int direction, const i64* i_n,
-                                                double* part /* [R][tiles][4] */)
+                                                double* part /* [R][tiles][4] */, int own_lo,
+                                                int own_hi)
 {
     __shared__ double scratch[32 * 3];
     const int r = blockIdx.y;
@@ -186,7 +191,8 @@ __global__ void __launch_bounds__(256) k_reduce(const Par P, const State S, cons
     double mn = 1.7976931348623157e308;
     const double uf = S.u_frame[r];
     const double* ur = S.u + base;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += gridDim.x * blockDim.x) {
+    for (int p = own_lo + blockIdx.x * blockDim.x + threadIdx.x; p < own_hi;
+         p += gridDim.x * blockDim.x) {
         const i64 g = base + p;
         if (what == 0) {
             acc[0] += F.f[g] * F.f[g];
@@ -274,6 +280,36 @@ __global__ void k_reduce_final(const double* part, int tiles, double* out /* [R]
         out[4 * r + 1] = a1;
         out[4 * r + 2] = a2;
         out[4 * r + 3] = mn;
+    }
+}
+
+// slab halo exchange: the full state of `count` consecutive blocks as 7 planes of 8-byte words
+// (u, v, a, y_l, y_r, idx, rng)
+__global__ void k_export_cells(const State S, i64 first, i64 count, u64* buf)
+{
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < count; k += (i64)gridDim.x * blockDim.x) {
+        const i64 g = first + k;
+        buf[k] = (u64)__double_as_longlong(S.u[g]);
+        buf[count + k] = (u64)__double_as_longlong(S.v[g]);
+        buf[2 * count + k] = (u64)__double_as_longlong(S.a[g]);
+        buf[3 * count + k] = (u64)__double_as_longlong(S.yl[g]);
+        buf[4 * count + k] = (u64)__double_as_longlong(S.yr[g]);
+        buf[5 * count + k] = (u64)S.idx[g];
+        buf[6 * count + k] = S.rng[g];
+    }
+}
+
+__global__ void k_import_cells(const State S, i64 first, i64 count, const u64* buf)
+{
+    for (i64 k = blockIdx.x * (i64)blockDim.x + threadIdx.x; k < count; k += (i64)gridDim.x * blockDim.x) {
+        const i64 g = first + k;
+        S.u[g] = __longlong_as_double((i64)buf[k]);
+        S.v[g] = __longlong_as_double((i64)buf[count + k]);
+        S.a[g] = __longlong_as_double((i64)buf[2 * count + k]);
+        S.yl[g] = __longlong_as_double((i64)buf[3 * count + k]);
+        S.yr[g] = __longlong_as_double((i64)buf[4 * count + k]);
+        S.idx[g] = (i64)buf[5 * count + k];
+        S.rng[g] = buf[6 * count + k];
     }
 }
 

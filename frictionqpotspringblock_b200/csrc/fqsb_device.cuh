@@ -30,6 +30,8 @@ struct Par {
     double dpar[4];
     double offset;
     u64 seed, seed_stride;
+    // slab decomposition: local block p is global block (seed_first + p) mod seed_period
+    u64 seed_first, seed_period;
 };
 
 // ---- per-realisation control block (device global memory) ---------------------------------
@@ -43,7 +45,15 @@ enum Status : int {
     ST_IDLE = 6
 };
 
-enum Mode : int { MODE_FIXED = 0, MODE_MINIMISE = 1, MODE_UNTIL_EVENT = 2, MODE_TRUNCATE = 3 };
+enum Mode : int {
+    MODE_FIXED = 0,
+    MODE_MINIMISE = 1,
+    MODE_UNTIL_EVENT = 2,
+    MODE_TRUNCATE = 3,
+    MODE_LOG = 4 // slab decomposition: record the per-step sums, decide on the host per batch
+};
+
+#define FQSB_NLOG 5 // logged per step: sum f^2, sum f_frame^2, hops, dS, dA
 
 #define FQSB_RING 32
 
@@ -71,6 +81,10 @@ struct RunArgs {
     i64 A_truncate, S_truncate;
     double tol, tol2, v_frame;
     const i64* i_n; // device [R*N] or nullptr
+    // slab decomposition: only blocks [own_lo, own_hi) of the local array enter the sums (the
+    // rest are halo copies of a neighbour's blocks); MODE_LOG appends the sums of every step
+    int own_lo, own_hi;
+    double* log; // device [R][max_steps][FQSB_NLOG]
 };
 
 struct State {

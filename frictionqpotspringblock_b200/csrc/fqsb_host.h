@@ -81,7 +81,7 @@ int stream_step_tiles(const Par& P, int generic_tiles);
 const char* stream_step_name(const Par& P);
 // no-passing: launch l decides sweep l-1 and performs sweep l (`first`: nothing to decide yet)
 cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
-                                cudaStream_t stream, int flip, int first);
+                                cudaStream_t stream, int flip, int first, int do_sweep);
 bool combination_supported(int pot, int inter);
 // defined in fqsb_longrange.cu (K7: DMMA Toeplitz GEMM)
 size_t lr_gemm_smem(i64 N);

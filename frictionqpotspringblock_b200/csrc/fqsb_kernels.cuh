@@ -89,6 +89,20 @@ __device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, double& ri
     return g.steps >= A.max_steps ? ST_EXHAUSTED : ST_RUNNING;
 }
 
+// MODE_LOG: append the sums of the step that just finished; no decision on the device
+__device__ __forceinline__ int step_log(const RunArgs& A, int r, Prog& g, double sf, double sff,
+                                        double hops, double dS, double dA)
+{
+    double* e = A.log + ((size_t)r * A.max_steps + g.steps) * FQSB_NLOG;
+    e[0] = sf;
+    e[1] = sff;
+    e[2] = hops;
+    e[3] = dS;
+    e[4] = dA;
+    g.steps++;
+    return g.steps >= A.max_steps ? ST_EXHAUSTED : ST_RUNNING;
+}
+
 // change of |i - i_n| and (i != i_n) when a block moves by `moved` wells
 __device__ __forceinline__ void track_hop(const RunArgs& A, i64 gp, i64 i_before, int moved,
                                           int& dS, int& dA)
@@ -671,9 +685,15 @@ __device__ __forceinline__ void stream_finalise(const Par& P, const State& S, co
     g.inc++;
     double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
     double res_last = ctl.residual;
-    int status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da, &res_last);
-    if (lane < A.niter_tol && lane < FQSB_RING) {
-        ctl.ring[lane] = ring;
+    int status;
+    if (A.mode == MODE_LOG) {
+        status = lane == 0 ? step_log(A, r, g, sf, sff, dh, ds, da) : ST_RUNNING;
+    }
+    else {
+        status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da, &res_last);
+        if (lane < A.niter_tol && lane < FQSB_RING) {
+            ctl.ring[lane] = ring;
+        }
     }
     if (lane == 0) {
         prog_store(g, ctl);
@@ -785,8 +805,10 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
                     S.idx[gp] = i_before + moved;
                     S.yl[gp] = wl[e];
                     S.yr[gp] = wr[e];
-                    hops += moved != 0;
-                    track_hop(A, gp, i_before, moved, dS, dA);
+                    if (p0 + e >= A.own_lo && p0 + e < A.own_hi) {
+                        hops += moved != 0;
+                        track_hop(A, gp, i_before, moved, dS, dA);
+                    }
                 }
             }
 #pragma unroll
@@ -796,8 +818,9 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
                 double ff = P.k_frame * (uf - uc[e]);
                 double F = ff + fp + fi;
                 double f = verlet_tail<UNIT>(P, F, vv[e], aa[e]);
-                acc[0] += f * f;
-                acc[1] += ff * ff;
+                const bool own = p0 + e >= A.own_lo && p0 + e < A.own_hi;
+                acc[0] += own ? f * f : 0.0;
+                acc[1] += own ? ff * ff : 0.0;
                 nan |= uc[e] != uc[e];
             }
             *reinterpret_cast<double2*>(uo + p0) = u2[j];
@@ -953,10 +976,13 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
                     S.idx[gp] = i_before + moved;
                     S.yl[gp] = wl[e];
                     S.yr[gp] = wr[e];
-                    hops += moved != 0;
-                    track_hop(A, gp, i_before, moved, dS, dA);
+                    if (rowoff + col + e >= A.own_lo && rowoff + col + e < A.own_hi) {
+                        hops += moved != 0;
+                        track_hop(A, gp, i_before, moved, dS, dA);
+                    }
                 }
             }
+            const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi; // whole rows
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int lc = 2 * t + e;
@@ -982,8 +1008,8 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
                 double ff = P.k_frame * (uf - uc[e]);
                 double F = ff + fp + fi;
                 double f = verlet_tail<UNIT>(P, F, vv[e], aa[e]);
-                acc[0] += f * f;
-                acc[1] += ff * ff;
+                acc[0] += own ? f * f : 0.0;
+                acc[1] += own ? ff * ff : 0.0;
                 nan |= uc[e] != uc[e];
             }
             *reinterpret_cast<double2*>(uo + rowoff + col) = un_c;
@@ -1051,8 +1077,10 @@ __global__ void __launch_bounds__(256)
             S.idx[base + p] = i_before + moved;
             S.yl[base + p] = yl;
             S.yr[base + p] = yr;
-            hops += moved != 0;
-            track_hop(A, base + p, i_before, moved, dS, dA);
+            if (p >= A.own_lo && p < A.own_hi) {
+                hops += moved != 0;
+                track_hop(A, base + p, i_before, moved, dS, dA);
+            }
         }
         int i = 0, j = 0;
         if (INT == INT_LAPLACE2D || INT == INT_QUARTICGRADIENT2D) {
@@ -1068,8 +1096,9 @@ __global__ void __launch_bounds__(256)
         uo[p] = un;
         vo[p] = v;
         ao[p] = a;
-        acc[0] += f * f;
-        acc[1] += ff * ff;
+        const bool own = p >= A.own_lo && p < A.own_hi;
+        acc[0] += own ? f * f : 0.0;
+        acc[1] += own ? ff * ff : 0.0;
         nan |= un != un;
     }
     if (nan) {
@@ -1094,7 +1123,8 @@ __global__ void __launch_bounds__(256)
 template <int INT>
 __global__ void __launch_bounds__(256)
     k_stream_np(const __grid_constant__ Par P, const __grid_constant__ State S,
-                const __grid_constant__ RunArgs A, const int flip, const int first)
+                const __grid_constant__ RunArgs A, const int flip, const int first,
+                const int do_sweep)
 {
     __shared__ double scratch[32 * 2];
     __shared__ int s_last;
@@ -1140,9 +1170,13 @@ __global__ void __launch_bounds__(256)
             double fp = mu * (umin - uc);
             double fi = lap * k;
             double f = fp + fi + ff;
-            acc[0] += f * f;
-            acc[1] += ff * ff;
+            const bool own = p >= A.own_lo && p < A.own_hi;
+            acc[0] += own ? f * f : 0.0;
+            acc[1] += own ? ff * ff : 0.0;
             nan |= uc != uc;
+        }
+        if (!do_sweep) { // last launch of a logged batch: residual only
+            continue;
         }
         // the sweep (detail.h:1728-1741)
         double un;
@@ -1210,9 +1244,15 @@ __global__ void __launch_bounds__(256)
         prog_load(g, ctl);
         double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
         double res_last = ctl.residual;
-        status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
-        if (lane < A.niter_tol && lane < FQSB_RING) {
-            ctl.ring[lane] = ring;
+        if (A.mode == MODE_LOG) {
+            status = lane == 0 ? step_log(A, r, g, sf, sff, 0.0, 0.0, 0.0) : ST_RUNNING;
+            status = __shfl_sync(0xffffffffu, status, 0);
+        }
+        else {
+            status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
+            if (lane < A.niter_tol && lane < FQSB_RING) {
+                ctl.ring[lane] = ring;
+            }
         }
         if (lane == 0) {
             prog_store(g, ctl);
@@ -1221,7 +1261,7 @@ __global__ void __launch_bounds__(256)
     }
     if (lane == 0) {
         // a stop keeps the input buffer (the sweep of this launch is discarded)
-        ctl.flip = status == ST_RUNNING ? flip ^ 1 : flip;
+        ctl.flip = (status == ST_RUNNING && do_sweep) ? flip ^ 1 : flip;
         ctl.count = 0u;
         ctl.status = status;
     }

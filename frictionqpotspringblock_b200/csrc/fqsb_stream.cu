@@ -133,14 +133,14 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
 }
 
 cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
-                                cudaStream_t stream, int flip, int first)
+                                cudaStream_t stream, int flip, int first, int do_sweep)
 {
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
     if (P.inter == INT_LAPLACE2D) {
-        k_stream_np<INT_LAPLACE2D><<<grid, 256, 0, stream>>>(P, S, A, flip, first);
+        k_stream_np<INT_LAPLACE2D><<<grid, 256, 0, stream>>>(P, S, A, flip, first, do_sweep);
     }
     else {
-        k_stream_np<INT_LAPLACE1D><<<grid, 256, 0, stream>>>(P, S, A, flip, first);
+        k_stream_np<INT_LAPLACE1D><<<grid, 256, 0, stream>>>(P, S, A, flip, first, do_sweep);
     }
     return cudaGetLastError();
 }

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQSB_ABI_VERSION 1
+#define FQSB_ABI_VERSION 2
 
 typedef enum {
     FQSB_OK = 0,
@@ -96,6 +96,10 @@ typedef struct {
     int64_t seed_stride;   /* 0 is read as prod(shape) */
     int32_t device;        /* CUDA ordinal; -1 = current device */
     int32_t kernel;        /* 0 auto, 1 force resident (one CTA per realisation), 2 force streaming */
+    /* slab decomposition: local block p is global block (seed_first + p) mod seed_period and draws
+     * the global block's pcg32 stream; seed_period == 0 disables the mapping */
+    int64_t seed_first;
+    int64_t seed_period;
 } fqsb_params;
 
 typedef struct fqsb_system fqsb_system;
@@ -189,6 +193,24 @@ int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* valu
 /* signed well-index change since `i_n` summed per realisation (the examples' S) and the number
  * of blocks that changed (A): out_S [R], out_A [R] (either may be NULL) */
 int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A);
+
+/* slab decomposition primitives (new surface; one very large line / interface over several GPUs,
+ * driven by frictionqpotspringblock_b200/slab.py) ----------------------- */
+/* only blocks [lo, hi) of the local array enter reductions (the rest are halo copies) */
+int fqsb_set_owned_range(fqsb_system* s, int64_t lo, int64_t hi);
+/* k steps (Verlet, or no-passing sweeps) without a stop decision; log [R][k][5] receives per step
+ * {sum f^2, sum f_frame^2, #well changes, dS, dA} over the owned range */
+int fqsb_logged_steps(fqsb_system* s, int64_t k, double* log);
+int fqsb_snapshot(fqsb_system* s);
+int fqsb_rollback(fqsb_system* s);
+/* full state (u, v, a, y_l, y_r, idx, rng: 7 planes of 8-byte words) of `count` consecutive
+ * blocks; `buf` is a device pointer when on_device != 0 */
+int fqsb_export_cells(fqsb_system* s, int64_t first, int64_t count, void* buf, int on_device);
+int fqsb_import_cells(fqsb_system* s, int64_t first, int64_t count, const void* buf, int on_device);
+/* u += du[r], u_frame += du_frame[r], re-align (advanceUniformly, ref: detail.h:2027-2050) */
+int fqsb_advance_uniformly(fqsb_system* s, const double* du, const double* du_frame);
+/* raw sums over the owned range, out [R][4] (see fqsb_api.cu) */
+int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, double* out);
 
 /* host staging helpers (pinned memory for the e2e path) ---------------------------------- */
 void* fqsb_host_alloc(size_t bytes);

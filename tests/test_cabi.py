@@ -34,15 +34,15 @@ def test_library_exports_every_declared_symbol():
     assert missing == []
     # and the Python binding declares a signature for each of them
     assert sorted(_capi.SIGNATURES) == declared_symbols()
-    assert lib.fqsb_abi_version() == 1
+    assert lib.fqsb_abi_version() == 2
 
 
 def test_params_struct_layout_matches_header():
     from frictionqpotspringblock_b200 import _capi
 
     # 4 int32 + 2 int64 + 8 double + uint64 + 2 int32 + 4 double + double + int64 (=160)
-    # + 2 int64 + 2 int32 (=184)
-    assert C.sizeof(_capi.Params) == 184
+    # + 2 int64 + 2 int32 (=184) + 2 int64 (=200)
+    assert C.sizeof(_capi.Params) == 200
 
 
 def test_no_cpu_fallback():
