@@ -110,6 +110,10 @@ def exchange_halos(export_cells, import_cells, layout, rank, world, group=None, 
         ops.append(dist.P2POp(dist.irecv, t, peer, group))
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+    if str(device).startswith("cuda"):
+        # req.wait() only orders torch's current stream after the NCCL transfer; the import
+        # kernels run on the handle's own stream, so the host has to wait for the data
+        torch.cuda.synchronize()
     for which, t in inbox:
         import_cells(*layout[which], t)
 
@@ -165,8 +169,9 @@ class SlabSystem:
             raise ValueError("halo too small")
         import torch
 
-        self._tdev = (torch.device("cuda", torch.cuda.current_device())
-                      if self.backend == "nccl" else torch.device("cpu"))
+        # halo / reduction buffers live on the device unless the group can only move host memory
+        self._tdev = (torch.device("cpu") if self.backend == "gloo"
+                      else torch.device("cuda", torch.cuda.current_device()))
 
     # ---- plumbing
     def _export(self, first, count, tensor):
