@@ -809,6 +809,7 @@ __global__ void k_ctl_begin(const Par P, const State S, int track_user, int over
     c.residual = 0.0;
     for (int k = 0; k < FQSB_RING; ++k) {
         c.ring[k] = __longlong_as_double(0x7ff0000000000000LL); // +inf (App. A.4)
+        c.ring_den[k] = 1.0;
     }
     if (overdamped) { // detail.h:1704-1705
         c.qs_first = c.inc;

@@ -66,7 +66,10 @@ struct Ctl {
     i64 inc;   // increment number m_inc (detail.h:1067)
     i64 qs_first, qs_last; // detail.h:1068-1069
     double residual;       // last residual inserted
-    double ring[FQSB_RING]; // GooseFEM::Iterate::StopList
+    // GooseFEM::Iterate::StopList. Entry k is kept as the pair (num, den) with residual^2 =
+    // num / den: num = sum f^2, den = sum f_frame^2 (or 1 when that is 0, detail.h:1516-1519)
+    double ring[FQSB_RING];
+    double ring_den[FQSB_RING];
     unsigned int count;     // streaming path: CTAs of this realisation that finished the step
     int flip;               // streaming path: which of the two u/v/a buffer sets is current
 };
@@ -386,23 +389,47 @@ __device__ __forceinline__ double verlet_tail(const Par& P, double F, double& v,
 }
 
 // ---- GooseFEM::Iterate::StopList held in the lanes of a warp -----------
-// lane l < n holds entry l; entries start at +inf.
-__device__ __forceinline__ double ring_roll_insert(double ring, double x, int n, int lane)
+// lane l < n holds entry l as the pair (num, den), residual_l^2 = num / den; entries start at
+// +inf. The criterion only COMPARES residuals (detail.h:1615,1748,1780,1874):
+//     r_l < tol      <=>  num_l < tol^2 * den_l
+//     r_{l+1} <= r_l <=>  num_{l+1} * den_l <= num_l * den_{l+1}
+// so no square root or division is needed per step (they cost ~150 FP64-pipe instructions per
+// warp, redundantly in every warp of a resident CTA). Equivalent in exact arithmetic; in floating
+// point it can differ from sqrt()/sqrt() only where two residuals agree to the last bits, i.e.
+// where the summation order of the norms already decides.
+struct RingEntry {
+    double num, den;
+};
+
+__device__ __forceinline__ RingEntry ring_entry(double sf, double sff)
 {
-    double nxt = __shfl_down_sync(0xffffffffu, ring, 1);
+    RingEntry e;
+    e.num = sf;
+    e.den = sff != 0.0 ? sff : 1.0; // residual() falls back to |f| when |f_frame| == 0
+    return e;
+}
+
+__device__ __forceinline__ RingEntry ring_roll_insert(RingEntry ring, RingEntry x, int n, int lane)
+{
+    RingEntry nxt;
+    nxt.num = __shfl_down_sync(0xffffffffu, ring.num, 1);
+    nxt.den = __shfl_down_sync(0xffffffffu, ring.den, 1);
     return lane == n - 1 ? x : nxt;
 }
 
-__device__ __forceinline__ bool ring_stop(double ring, int n, int lane, double tol, double tol2)
+__device__ __forceinline__ bool ring_stop(RingEntry ring, int n, int lane, double tol2, double tol4)
 {
-    double nxt = __shfl_down_sync(0xffffffffu, ring, 1);
-    bool desc = (lane >= n - 1) || !(nxt > ring);       // std::is_sorted(..., greater)
-    bool less1 = (lane >= n) || (ring < tol);           // all_less(tol): strict
-    bool less2 = (lane >= n) || (ring < tol2);
+    RingEntry nxt;
+    nxt.num = __shfl_down_sync(0xffffffffu, ring.num, 1);
+    nxt.den = __shfl_down_sync(0xffffffffu, ring.den, 1);
+    // std::is_sorted(..., greater): never r_{l+1} > r_l
+    bool desc = (lane >= n - 1) || !(nxt.num * ring.den > ring.num * nxt.den);
+    bool less1 = (lane >= n) || (ring.num < tol2 * ring.den); // all_less(tol): strict
+    bool less2 = (lane >= n) || (ring.num < tol4 * ring.den); // all_less(tol * tol)
     bool descending = __all_sync(0xffffffffu, desc);
     bool all1 = __all_sync(0xffffffffu, less1);
     bool all2 = __all_sync(0xffffffffu, less2);
-    return (descending && all1) || all2; // detail.h:1615,1748,1780,1874
+    return (descending && all1) || all2;
 }
 
 // ---- warp reductions (fixed butterfly order -> deterministic) --------------------------------

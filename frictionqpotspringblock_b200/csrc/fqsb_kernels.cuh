@@ -46,9 +46,8 @@ __device__ __forceinline__ void prog_store(const Prog& g, Ctl& c)
 
 // The per-step decisions of timeStepsUntilEvent (detail.h:1605-1619), minimise (1764-1784)
 // and minimise_truncate (1858-1886), evaluated by a full warp (ring entry l lives in lane l).
-__device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, double& ring, int lane,
-                                           double sf, double sff, int hops, int dS, int dA,
-                                           double* res_out)
+__device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, RingEntry& ring, int lane,
+                                           double sf, double sff, int hops, int dS, int dA)
 {
     g.steps++;
     if (A.mode == MODE_FIXED) {
@@ -60,9 +59,7 @@ __device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, double& ri
     if (A.mode == MODE_UNTIL_EVENT && hops > 0) {
         return ST_EVENT;
     }
-    double res = residual_from_sums(sf, sff);
-    *res_out = res;
-    ring = ring_roll_insert(ring, res, A.niter_tol, lane);
+    ring = ring_roll_insert(ring, ring_entry(sf, sff), A.niter_tol, lane);
     if (A.track) {
         g.S += dS;
         g.A += dA;
@@ -75,7 +72,7 @@ __device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, double& ri
         }
         g.s_n = g.S;
     }
-    if (ring_stop(ring, A.niter_tol, lane, A.tol, A.tol2)) {
+    if (ring_stop(ring, A.niter_tol, lane, A.tol2, A.tol2 * A.tol2)) {
         return ST_CONVERGED;
     }
     if (A.mode == MODE_TRUNCATE) {
@@ -87,6 +84,23 @@ __device__ __forceinline__ int step_decide(const RunArgs& A, Prog& g, double& ri
         }
     }
     return g.steps >= A.max_steps ? ST_EXHAUSTED : ST_RUNNING;
+}
+
+__device__ __forceinline__ RingEntry ring_load(const Ctl& c, const RunArgs& A, int lane)
+{
+    RingEntry e;
+    const bool in = lane < A.niter_tol && lane < FQSB_RING;
+    e.num = in ? c.ring[lane] : 0.0;
+    e.den = in ? c.ring_den[lane] : 1.0;
+    return e;
+}
+
+__device__ __forceinline__ void ring_store(Ctl& c, const RunArgs& A, int lane, RingEntry e)
+{
+    if (lane < A.niter_tol && lane < FQSB_RING) {
+        c.ring[lane] = e.num;
+        c.ring_den[lane] = e.den;
+    }
 }
 
 // MODE_LOG: append the sums of the step that just finished; no decision on the device
@@ -142,7 +156,9 @@ static __device__ __noinline__ int hop_shared(const Par& P, double un, double* y
     return moved;
 }
 
-template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT>
+// STOP = false: timeSteps / flowSteps only (MODE_FIXED); STOP = true: the stop modes. Two
+// instantiations so that the bookkeeping of the stop modes costs the fixed-step loop no registers.
+template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT, bool STOP>
 __global__ void __launch_bounds__(T)
     k_resident(const __grid_constant__ Par P, const __grid_constant__ State S,
                const __grid_constant__ RunArgs A)
@@ -213,7 +229,9 @@ __global__ void __launch_bounds__(T)
     // floating-point chains of a thread interleave.
 
     // ---- positions (detail.h:1549): purely local; ghosts keep the line periodic
-    auto phase1 = [&](const double* uprev, double* ucur) {
+    auto phase1 = [&](const int oprev, const int ocur) {
+        const double* uprev = us + oprev;
+        double* ucur = us + ocur;
         double un[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
@@ -240,8 +258,9 @@ __global__ void __launch_bounds__(T)
 
     // ---- well search (detail.h:144), forces at the new positions (detail.h:1380-1386) and
     //      the Verlet tail (detail.h:1552-1565)
-    auto phase2 = [&](const double* ucur, auto accumulate, double& sf, double& sff, int& hops,
+    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
                       int& dS, int& dA) {
+        const double* ucur = us + ocur;
         auto U = [&](int q) { return ucur[q + G]; };
         double uc[B], wl[B], wr[B];
         unsigned need = 0u;
@@ -303,7 +322,7 @@ __global__ void __launch_bounds__(T)
     const i64 nloop = A.max_steps - steps_done < A.launch_steps ? A.max_steps - steps_done
                                                                 : A.launch_steps;
 
-    if (A.mode == MODE_FIXED) {
+    if (!STOP) {
         // timeSteps / flowSteps: no stop test, one barrier per step
         double sf = 0.0, sff = 0.0;
         int hops = 0, dS = 0, dA = 0;
@@ -311,10 +330,9 @@ __global__ void __launch_bounds__(T)
             if (A.flow) {
                 uf += A.v_frame * P.dt; // detail.h:1642
             }
-            double* ucur = us + (size_t)(prev ^ 1) * NS;
-            phase1(us + (size_t)prev * NS, ucur);
+            phase1(prev * NS, (prev ^ 1) * NS);
             __syncthreads();
-            phase2(ucur, std::false_type{}, sf, sff, hops, dS, dA);
+            phase2((prev ^ 1) * NS, std::false_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
         }
         steps_done += nloop;
@@ -329,28 +347,32 @@ __global__ void __launch_bounds__(T)
         }
     }
     else {
-        Prog g;
-        prog_load(g, ctl);
-        double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
-        double res_last = ctl.residual;
+        // Per-thread bookkeeping is kept minimal (the decision is taken redundantly by every
+        // warp): the StopList ring, and the running S, A of minimise_truncate. The activity
+        // timestamps (detail.h:1770-1776) are written by thread 0 on the rare steps that change
+        // S; step and increment numbers follow from the loop counter.
+        RingEntry ring = ring_load(ctl, A, lane);
+        double last_sf = 0.0, last_sff = 0.0;
+        i64 S_run = ctl.S, A_run = ctl.A;
+        const i64 inc0 = ctl.inc;
+        i64 its = 0;
         // One barrier per step: after the forces of step s, the positions of step s+1 are
         // computed speculatively (purely local, into the other slip buffer); the barrier that
         // publishes them also publishes the partial sums of step s, whose stop decision is
         // taken right after it. A stop discards the speculative positions.
         if (nloop > 0) {
-            phase1(us + (size_t)prev * NS, us + (size_t)(prev ^ 1) * NS);
+            phase1(prev * NS, (prev ^ 1) * NS);
             __syncthreads();
         }
         for (i64 it = 0; it < nloop; ++it) {
-            g.inc++; // detail.h:1541
             double sf = 0.0, sff = 0.0;
             int hops = 0, dS = 0, dA = 0;
-            phase2(us + (size_t)(prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
+            phase2((prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
 
             // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
-            double* rd = red + (it & 1) * 2 * NW;
-            int* ri = redi + (it & 1) * 4 * NW;
+            double* rd = red + (int)(it & 1) * 2 * NW;
+            int* ri = redi + (int)(it & 1) * 4 * NW;
             warp_sum2(sf, sff);
             hops = __reduce_add_sync(0xffffffffu, hops);
             if (A.track) {
@@ -364,7 +386,7 @@ __global__ void __launch_bounds__(T)
                 ri[4 * warp + 1] = dS;
                 ri[4 * warp + 2] = dA;
             }
-            phase1(us + (size_t)prev * NS, us + (size_t)(prev ^ 1) * NS); // speculative
+            phase1(prev * NS, (prev ^ 1) * NS); // speculative
             __syncthreads();
             if (2 * NW == 32) {
                 warp_sum_interleaved(rd[lane], sf, sff);
@@ -374,23 +396,59 @@ __global__ void __launch_bounds__(T)
                 sff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
             }
             hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
-            if (A.track) {
+            last_sf = sf;
+            last_sff = sff;
+            its = it + 1;
+            const i64 step_global = steps_done + its; // steps of this call so far
+            if (sf != sf) { // NaN forces <=> NaN positions (detail.h:1567)
+                status = ST_NAN;
+                break;
+            }
+            if (A.mode == MODE_UNTIL_EVENT && hops > 0) { // detail.h:1609
+                status = ST_EVENT;
+                break;
+            }
+            ring = ring_roll_insert(ring, ring_entry(sf, sff), A.niter_tol, lane);
+            if (A.track) { // detail.h:1768-1778, 1863-1872
                 dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
                 dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
+                S_run += dS;
+                A_run += dA;
+                // s != s_n  <=>  S changed in this step (s_n starts at 0 before the first step)
+                if ((dS != 0 || (step_global == 1 && S_run != 0)) && t == 0) {
+                    if (ctl.init) {
+                        ctl.init = 0;
+                        ctl.qs_first = inc0 + its;
+                    }
+                    ctl.qs_last = inc0 + its;
+                }
             }
-            status = step_decide(A, g, ring, lane, sf, sff, hops, dS, dA, &res_last);
-            if (status != ST_RUNNING) {
+            if (ring_stop(ring, A.niter_tol, lane, A.tol2, A.tol2 * A.tol2)) {
+                status = ST_CONVERGED;
+                break;
+            }
+            if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
+                if ((A.A_truncate > 0 && A_run >= A.A_truncate) ||
+                    (A.S_truncate > 0 && S_run >= A.S_truncate)) {
+                    status = ST_TRUNCATED;
+                    break;
+                }
+            }
+            if (step_global >= A.max_steps) {
+                status = ST_EXHAUSTED;
                 break;
             }
         }
         if (t < 32) {
-            if (lane < A.niter_tol && lane < FQSB_RING) {
-                ctl.ring[lane] = ring;
-            }
+            ring_store(ctl, A, lane, ring);
             if (lane == 0) {
-                prog_store(g, ctl);
+                ctl.steps = steps_done + its;
+                ctl.inc = inc0 + its; // detail.h:1541
+                ctl.S = S_run;
+                ctl.A = A_run;
+                ctl.s_n = S_run;
                 ctl.status = status;
-                ctl.residual = res_last;
+                ctl.residual = residual_from_sums(last_sf, last_sff);
             }
         }
     }
@@ -472,9 +530,9 @@ __global__ void __launch_bounds__(T) k_resident_nopassing(const Par P, const Sta
     }
     Prog g;
     prog_load(g, ctl);
-    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
+    RingEntry ring = ring_load(ctl, A, lane);
     const double uf = S.u_frame[r];
-    double res_last = ctl.residual;
+    double last_sf = 0.0, last_sff = 0.0;
     const double k = P.k1, kf = P.k_frame, mu = P.mu;
     const double denom = (TWO_D ? 4 : 2) * k + kf + mu;
     int status = ST_RUNNING, underflow = 0, cur = 0;
@@ -548,7 +606,9 @@ __global__ void __launch_bounds__(T) k_resident_nopassing(const Par P, const Sta
         sf = warp_sum(lane < NW ? red[2 * lane] : 0.0);
         sff = warp_sum(lane < NW ? red[2 * lane + 1] : 0.0);
         cur ^= 1;
-        status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
+        last_sf = sf;
+        last_sff = sff;
+        status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0);
         if (status != ST_RUNNING) {
             break;
         }
@@ -580,13 +640,11 @@ __global__ void __launch_bounds__(T) k_resident_nopassing(const Par P, const Sta
         S.err[0] = 1;
     }
     if (t < 32) {
-        if (lane < A.niter_tol && lane < FQSB_RING) {
-            ctl.ring[lane] = ring;
-        }
+        ring_store(ctl, A, lane, ring);
         if (lane == 0) {
             prog_store(g, ctl);
             ctl.status = status;
-            ctl.residual = res_last;
+            ctl.residual = residual_from_sums(last_sf, last_sff);
         }
     }
 }
@@ -683,21 +741,18 @@ __device__ __forceinline__ void stream_finalise(const Par& P, const State& S, co
     Prog g;
     prog_load(g, ctl);
     g.inc++;
-    double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
-    double res_last = ctl.residual;
+    RingEntry ring = ring_load(ctl, A, lane);
     int status;
     if (A.mode == MODE_LOG) {
         status = lane == 0 ? step_log(A, r, g, sf, sff, dh, ds, da) : ST_RUNNING;
     }
     else {
-        status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da, &res_last);
-        if (lane < A.niter_tol && lane < FQSB_RING) {
-            ctl.ring[lane] = ring;
-        }
+        status = step_decide(A, g, ring, lane, sf, sff, (int)dh, (int)ds, (int)da);
+        ring_store(ctl, A, lane, ring);
     }
     if (lane == 0) {
         prog_store(g, ctl);
-        ctl.residual = res_last;
+        ctl.residual = residual_from_sums(sf, sff);
         ctl.flip = flip ^ 1;
         ctl.count = 0u;
         S.u_frame[r] = uf;
@@ -1242,21 +1297,18 @@ __global__ void __launch_bounds__(256)
         sff = warp_sum(sff);
         Prog g;
         prog_load(g, ctl);
-        double ring = (lane < A.niter_tol && lane < FQSB_RING) ? ctl.ring[lane] : 0.0;
-        double res_last = ctl.residual;
+        RingEntry ring = ring_load(ctl, A, lane);
         if (A.mode == MODE_LOG) {
             status = lane == 0 ? step_log(A, r, g, sf, sff, 0.0, 0.0, 0.0) : ST_RUNNING;
             status = __shfl_sync(0xffffffffu, status, 0);
         }
         else {
-            status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0, &res_last);
-            if (lane < A.niter_tol && lane < FQSB_RING) {
-                ctl.ring[lane] = ring;
-            }
+            status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0);
+            ring_store(ctl, A, lane, ring);
         }
         if (lane == 0) {
             prog_store(g, ctl);
-            ctl.residual = res_last;
+            ctl.residual = residual_from_sums(sf, sff);
         }
     }
     if (lane == 0) {

@@ -64,15 +64,22 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
     const size_t smem = resident_smem(P, c);
     const bool full = (i64)c.B * c.T == P.N;
     const bool unit = unit_parameters(P);
+    const bool stop = A.mode != MODE_FIXED;
+#define FQSB_TRY_MODE(b, t, full_, unit_) \
+    return stop ? launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, true>, t, smem, P, S, A, stream) \
+                : launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false>, t, smem, P, S, A, stream);
 #define FQSB_TRY_CFG(b, t) \
     if (c.B == b && c.T == t) { \
-        if (full && unit) \
-            return launch(k_resident<C_POT, C_INT, b, t, false, true, true>, t, smem, P, S, A, stream); \
-        if (full) \
-            return launch(k_resident<C_POT, C_INT, b, t, false, true, false>, t, smem, P, S, A, stream); \
-        if (unit) \
-            return launch(k_resident<C_POT, C_INT, b, t, false, false, true>, t, smem, P, S, A, stream); \
-        return launch(k_resident<C_POT, C_INT, b, t, false, false, false>, t, smem, P, S, A, stream); \
+        if (full && unit) { \
+            FQSB_TRY_MODE(b, t, true, true) \
+        } \
+        if (full) { \
+            FQSB_TRY_MODE(b, t, true, false) \
+        } \
+        if (unit) { \
+            FQSB_TRY_MODE(b, t, false, true) \
+        } \
+        FQSB_TRY_MODE(b, t, false, false) \
     }
     FQSB_TRY_CFG(1, 256)
     FQSB_TRY_CFG(1, 1024)

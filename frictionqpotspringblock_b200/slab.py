@@ -35,18 +35,34 @@ NLOG = 5  # fqsb_device.cuh: FQSB_NLOG
 
 # ---- pure host logic (unit-tested on CPU) ---------------------------------------------------------
 class StopList:
-    """GooseFEM::Iterate::StopList (SURVEY.md App. A.4) + the criterion of detail.h:1615,1780."""
+    """GooseFEM::Iterate::StopList (SURVEY.md App. A.4) + the criterion of detail.h:1615,1780, in
+    the form the device uses (fqsb_device.cuh: ring_stop): entry k is the pair (num, den) with
+    residual_k^2 = num / den and residuals are only ever compared, by cross-multiplication."""
 
     def __init__(self, n: int):
-        self.r = np.full(int(n), np.inf)
+        self.num = np.full(int(n), np.inf)
+        self.den = np.ones(int(n))
 
-    def roll_insert(self, x: float):
-        self.r[:-1] = self.r[1:]
-        self.r[-1] = x
+    def roll_insert(self, sf: float, sff: float):
+        self.num[:-1] = self.num[1:]
+        self.den[:-1] = self.den[1:]
+        self.num[-1] = sf
+        self.den[-1] = sff if sff != 0.0 else 1.0  # detail.h:1516-1519
 
     def stop(self, tol: float) -> bool:
-        descending = bool(np.all(self.r[1:] <= self.r[:-1]))
-        return (descending and bool(np.all(self.r < tol))) or bool(np.all(self.r < tol * tol))
+        tol2 = tol * tol
+        tol4 = tol2 * tol2
+        with np.errstate(invalid="ignore"):
+            descending = not bool(np.any(self.num[1:] * self.den[:-1] > self.num[:-1] * self.den[1:]))
+            less1 = bool(np.all(self.num < tol2 * self.den))
+            less2 = bool(np.all(self.num < tol4 * self.den))
+        return (descending and less1) or less2
+
+    def state(self):
+        return self.num.copy(), self.den.copy()
+
+    def restore(self, state):
+        self.num, self.den = state[0].copy(), state[1].copy()
 
 
 def residual_from_sums(sf: float, sff: float) -> float:
@@ -61,7 +77,7 @@ def first_stop(log: np.ndarray, ring: StopList, tol: float) -> int:
     for j in range(log.shape[0]):
         if np.isnan(log[j, 0]):
             raise RuntimeError("NaN entries found")  # detail.h:1568
-        ring.roll_insert(residual_from_sums(log[j, 0], log[j, 1]))
+        ring.roll_insert(log[j, 0], log[j, 1])
         if ring.stop(tol):
             return j + 1
     return 0
@@ -284,13 +300,13 @@ class SlabSystem:
         while done < max_iter:
             k = int(min(self.batch, max_iter - done))
             check(lib.fqsb_snapshot(self._h))
-            saved = ring.r.copy()
+            saved = ring.state()
             log = self._allreduce(self._logged(k))
             stop = first_stop(log, ring, tol)
             if stop:
                 if stop < k:  # the criterion fired inside the batch: redo exactly `stop` steps
                     check(lib.fqsb_rollback(self._h))
-                    ring.r = saved
+                    ring.restore(saved)
                     log = self._allreduce(self._logged(stop))
                     assert first_stop(log, ring, tol) == stop
                 self.exchange()
