@@ -9,7 +9,7 @@ All numerical work runs in hand-written sm_100a CUDA kernels behind the C ABI of
 
 from . import _capi  # noqa: F401  (raises ImportError when libfqsb.so is missing)
 from ._system import Ensemble, System  # noqa: F401
-from . import Line1d, Line2d  # noqa: F401
+from . import Line1d, Line2d, Particles  # noqa: F401
 
 
 def version() -> str:

@@ -368,6 +368,7 @@ def _common(kw):
 
 Line1d = _Namespace()
 Line2d = _Namespace()
+Particles = _Namespace()
 
 
 def _mk(potential, interactions, k1name=None, k2name=None, kappa=False, minimisation=0):
@@ -392,6 +393,8 @@ Line1d.System_Smooth_Laplace = _mk("Smooth", "Laplace1d", "k_interactions")
 Line1d.System_Cuspy_Quartic = _mk("Cuspy", "Quartic1d", "a1", "a2")
 Line1d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient1d", "k2", "k4")
 Line1d.System_Cuspy_LongRange = _mk("Cuspy", "LongRange1d", "k_interactions", "alpha")
+# Particles.h:93-135 (no interactions)
+Particles.System_Cuspy = _mk("Cuspy", "None")
 # Line2d.h:77-162 (+ the new 2-D no-passing system)
 Line2d.System_Cuspy_Laplace = _mk("Cuspy", "Laplace2d", "k_interactions")
 Line2d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient2d", "k2", "k4")

@@ -21,6 +21,7 @@ LAYOUT = {
     "Line1d_SemiSmooth_Laplace": 1000,
     "Line2d_Cuspy_Laplace": 1000,
     "Line1d_Cuspy_Laplace_LongRange": 200,
+    "Particles_Cuspy": 2000,  # first dataset is named u_frame in this file (same layout)
 }
 
 

@@ -18,9 +18,11 @@ BASE = dict(
 )
 
 
-def make(ns1d, ns2d, name):
+def make(ns1d, ns2d, name, nsp=None):
     """Construct the system of example `name` from namespaces exposing the reference classes."""
     b = dict(BASE)
+    if name == "Particles_Cuspy":
+        return nsp.System_Cuspy(**b)
     if name == "Line1d_Cuspy_Laplace":
         return ns1d.System_Cuspy_Laplace(k_interactions=1.0, **b)
     if name == "Line1d_Cuspy_Laplace_Nopassing":

@@ -250,12 +250,13 @@ def test_no_convergence_and_nan_errors():
     ("Line1d_SemiSmooth_Laplace", 400),
     ("Line1d_Cuspy_Laplace_LongRange", 20),
     ("Line2d_Cuspy_Laplace", 60),
+    ("Particles_Cuspy", 400),
 ])
 def test_golden_protocol_on_gpu(name, nstep, golden_dir):
     """The reference's own regression: examples/<name>.py against its committed .h5."""
     F = product()
     golden = np.load(golden_dir / f"{name}.npz")
-    system = protocol.make(F.Line1d, F.Line2d, name)
+    system = protocol.make(F.Line1d, F.Line2d, name, F.Particles)
     protocol.check(golden, *protocol.run(system, nstep))
 
 

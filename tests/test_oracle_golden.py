@@ -24,6 +24,7 @@ CASES = {
     "Line1d_SemiSmooth_Laplace": (300, 1000),
     "Line1d_Cuspy_Laplace_LongRange": (12, 200),
     "Line2d_Cuspy_Laplace": (40, 1000),
+    "Particles_Cuspy": (300, 2000),
 }
 
 
@@ -31,7 +32,7 @@ CASES = {
 def test_oracle_reproduces_golden(name, golden_dir):
     nstep = CASES[name][1] if FULL else CASES[name][0]
     golden = np.load(golden_dir / f"{name}.npz")
-    system = protocol.make(orc.Line1d, orc.Line2d, name)
+    system = protocol.make(orc.Line1d, orc.Line2d, name, orc.Particles)
     protocol.check(golden, *protocol.run(system, nstep))
 
 
