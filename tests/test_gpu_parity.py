@@ -352,3 +352,76 @@ def test_longrange_gemm_ensemble_matches_resident():
     assert np.abs(a.u - b.u).max() <= 1e-11
     scale = np.abs(a.f_interactions).max()
     assert np.abs(a.f_interactions - b.f_interactions).max() <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("N", [2, 3, 4, 32, 33])
+def test_tiny_lines(N, kernel):
+    """smallest periodic lines (N = 2: both neighbours are the same block) and warp-edge sizes."""
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=0.1, k_interactions=1.0,
+                kernel=kernel, **PHYS)
+    for s in (o, p):
+        s.u_frame = 3.0
+        s.timeSteps(50)
+    assert_same_state(o, p)
+    for s in (o, p):
+        assert s.minimise() == 0
+    assert o.inc == p.inc
+    assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+
+
+@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+def test_backward_driving_and_negative_direction(kernel):
+    """direction = -1 (detail.h:1949-1959): wells are regenerated backwards (inverse LCG)."""
+    N = 128
+    o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
+                kernel=kernel, **PHYS)
+    for s in (o, p):
+        s.u_frame = 0.5
+        assert s.minimise() == 0
+    for step in range(12):
+        i_n = o.chunk.index_at_align
+        for s in (o, p):
+            s.eventDrivenStep(1e-3, False, direction=-1)
+            s.eventDrivenStep(1e-3, True, direction=-1)
+            assert s.minimise() == 0
+        assert o.inc == p.inc
+        assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+        assert np.array_equal(o.u, p.u)
+        assert o.u_frame == p.u_frame
+    assert np.sum(o.chunk.index_at_align - i_n) <= 0
+
+
+def test_landscape_underflow_is_reported():
+    """u below the first yield position: the reference's chunk cannot go there either."""
+    F = product()
+    kw = dict(shape=[16], k_frame=0.1, k_interactions=1.0, **{**PHYS, "offset": 5.0})
+    with pytest.raises(RuntimeError, match="lower the offset"):
+        F.Line1d.System_Cuspy_Laplace(**kw)
+    p = F.Line1d.System_Cuspy_Laplace(shape=[16], k_frame=0.1, k_interactions=1.0, **PHYS)
+    with pytest.raises(RuntimeError, match="yield landscape exhausted"):
+        p.u = np.full(16, -1000.0)
+
+
+def test_shape_and_argument_validation():
+    F = product()
+    kw = dict(k_frame=0.1, k_interactions=1.0, **PHYS)
+    p = F.Line1d.System_Cuspy_Laplace(shape=[8], **kw)
+    with pytest.raises(RuntimeError, match="has_shape"):
+        p.v = np.zeros(7)
+    with pytest.raises(RuntimeError, match="has_shape"):
+        p.minimise_truncate(i_n=np.zeros(9, dtype=int))
+    with pytest.raises(RuntimeError, match="direction == 1"):
+        p.eventDrivenStep(1e-3, True, direction=2)
+    with pytest.raises(RuntimeError, match="niter_tol"):
+        p.minimise(niter_tol=33)
+    with pytest.raises(TypeError):
+        F.Line1d.System_Cuspy_Laplace(shape=[8], seed=0)
+    with pytest.raises(AttributeError):
+        F.Line1d.System_Cuspy_Laplace_Nopassing(
+            mu=1.0, k_interactions=1.0, k_frame=0.1, shape=[8], seed=0, distribution="random",
+            parameters=[2.0], offset=-50).timeStep()
+    p.t = 12.3
+    assert p.inc == 123 and np.isclose(p.t, 12.3)
+    p.inc = 7
+    assert p.quasistaticActivityFirst == 7 and p.quasistaticActivityLast == 7
