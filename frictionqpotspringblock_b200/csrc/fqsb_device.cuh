@@ -228,6 +228,21 @@ __host__ __device__ __forceinline__ int well_align(const Par& P, double u, doubl
     return moved;
 }
 
+// ---- correctly rounded a / b for a loop-invariant divisor ------------------------------------
+// rcp = RN(1 / b) (IEEE division, computed once). q0 = RN(a * rcp) is within 2 ulp of a / b; one
+// residual step (r = a - q*b exact through FMA, q += r*rcp) makes it faithful, a second one
+// yields RN(a / b) (Markstein's theorem) -- the same bits as the IEEE division the reference
+// performs, at 5 FP64 instructions instead of ~50. (Explicit fma(): this file is compiled with
+// -fmad=false, which only forbids *implicit* contraction.)
+__device__ __forceinline__ double div_by_invariant(double a, double b, double rcp)
+{
+    double q = a * rcp;
+    double r = fma(-q, b, a);
+    q = fma(r, rcp, q);
+    r = fma(-q, b, a);
+    return fma(r, rcp, q);
+}
+
 // ---- potentials -----------------------------------------------------------------------------
 enum { POT_CUSPY = 0, POT_SEMISMOOTH = 1, POT_SMOOTH = 2 };
 
@@ -241,8 +256,9 @@ __device__ __forceinline__ double f_potential(const Par& P, double u, double yl,
     }
     else if (POT == POT_SEMISMOOTH) { // detail.h:261-276
         double xi = 0.5 * (yl + yr);
-        double u_r = (P.mu * xi + P.kappa * yr) / (P.mu + P.kappa);
-        double u_l = (P.mu * xi + P.kappa * yl) / (P.mu + P.kappa);
+        const double mk = P.mu + P.kappa, rmk = 1.0 / mk;
+        double u_r = div_by_invariant(P.mu * xi + P.kappa * yr, mk, rmk);
+        double u_l = div_by_invariant(P.mu * xi + P.kappa * yl, mk, rmk);
         if (u < u_l) {
             return P.kappa * (u - yl);
         }

@@ -535,6 +535,7 @@ __global__ void __launch_bounds__(T) k_resident_nopassing(const Par P, const Sta
     double last_sf = 0.0, last_sff = 0.0;
     const double k = P.k1, kf = P.k_frame, mu = P.mu;
     const double denom = (TWO_D ? 4 : 2) * k + kf + mu;
+    const double rdenom = 1.0 / denom;
     int status = ST_RUNNING, underflow = 0, cur = 0;
     const i64 nloop = A.max_steps - g.steps < A.launch_steps ? A.max_steps - g.steps
                                                              : A.launch_steps;
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(T) k_resident_nopassing(const Par P, const Sta
                 double un;
                 for (;;) { // detail.h:1728-1738
                     double umin = 0.5 * (yl[j] + yr[j]);
-                    un = (k * uneigh + kf * uf + mu * umin) / denom;
+                    un = div_by_invariant(k * uneigh + kf * uf + mu * umin, denom, rdenom);
                     if (!(un > yr[j] || !(un > yl[j])) || un != un) {
                         break;
                     }
@@ -1175,6 +1176,47 @@ __global__ void __launch_bounds__(256)
 // read once -- 32 B per block-update. When the decision says stop, the configuration to keep is
 // the input buffer; the wells the discarded sweep moved are re-aligned by the host (k_align).
 // =============================================================================================
+// last-CTA decision of a no-passing launch: decides sweep l-1 from the residual of the input
+__device__ __forceinline__ void np_finalise(const Par& P, const State& S, const RunArgs& A,
+                                            const int r, const int flip, const int first,
+                                            const int do_sweep)
+{
+    Ctl& ctl = S.ctl[r];
+    const int lane = threadIdx.x;
+    int status = ST_RUNNING;
+    if (!first) {
+        double sf = 0.0, sff = 0.0;
+        const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
+        for (int c = lane; c < (int)gridDim.x; c += 32) {
+            sf += all[c * FQSB_NPART];
+            sff += all[c * FQSB_NPART + 1];
+        }
+        sf = warp_sum(sf);
+        sff = warp_sum(sff);
+        Prog g;
+        prog_load(g, ctl);
+        RingEntry ring = ring_load(ctl, A, lane);
+        if (A.mode == MODE_LOG) {
+            status = lane == 0 ? step_log(A, r, g, sf, sff, 0.0, 0.0, 0.0) : ST_RUNNING;
+            status = __shfl_sync(0xffffffffu, status, 0);
+        }
+        else {
+            status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0);
+            ring_store(ctl, A, lane, ring);
+        }
+        if (lane == 0) {
+            prog_store(g, ctl);
+            ctl.residual = residual_from_sums(sf, sff);
+        }
+    }
+    if (lane == 0) {
+        // a stop keeps the input buffer (the sweep of this launch is discarded)
+        ctl.flip = (status == ST_RUNNING && do_sweep) ? flip ^ 1 : flip;
+        ctl.count = 0u;
+        ctl.status = status;
+    }
+}
+
 template <int INT>
 __global__ void __launch_bounds__(256)
     k_stream_np(const __grid_constant__ Par P, const __grid_constant__ State S,
@@ -1196,6 +1238,7 @@ __global__ void __launch_bounds__(256)
     const double uf = S.u_frame[r];
     const double k = P.k1, kf = P.k_frame, mu = P.mu;
     const double denom = (TWO_D ? 4 : 2) * k + kf + mu;
+    const double rdenom = 1.0 / denom;
     int underflow = 0;
     bool nan = false;
     double acc[2] = {0.0, 0.0};
@@ -1241,7 +1284,7 @@ __global__ void __launch_bounds__(256)
         bool loaded = false;
         for (;;) {
             double umin = 0.5 * (yl + yr);
-            un = (k * uneigh + kf * uf + mu * umin) / denom;
+            un = div_by_invariant(k * uneigh + kf * uf + mu * umin, denom, rdenom);
             if (!(un > yr || !(un > yl)) || un != un) {
                 break;
             }
@@ -1284,39 +1327,191 @@ __global__ void __launch_bounds__(256)
         return;
     }
     __threadfence();
-    const int lane = threadIdx.x;
-    int status = ST_RUNNING;
-    if (!first) {
-        double sf = 0.0, sff = 0.0;
-        const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
-        for (int c = lane; c < (int)gridDim.x; c += 32) {
-            sf += all[c * FQSB_NPART];
-            sff += all[c * FQSB_NPART + 1];
-        }
-        sf = warp_sum(sf);
-        sff = warp_sum(sff);
-        Prog g;
-        prog_load(g, ctl);
-        RingEntry ring = ring_load(ctl, A, lane);
-        if (A.mode == MODE_LOG) {
-            status = lane == 0 ? step_log(A, r, g, sf, sff, 0.0, 0.0, 0.0) : ST_RUNNING;
-            status = __shfl_sync(0xffffffffu, status, 0);
-        }
-        else {
-            status = step_decide(A, g, ring, lane, sf, sff, 0, 0, 0);
-            ring_store(ctl, A, lane, ring);
-        }
-        if (lane == 0) {
-            prog_store(g, ctl);
-            ctl.residual = residual_from_sums(sf, sff);
-        }
+    np_finalise(P, S, A, r, flip, first, do_sweep);
+}
+
+// ---- no-passing sweep on a 2-D lattice: row-marching strips like k_stream_2d (u only) -----------
+// Same fused launch semantics as k_stream_np (residual of the input configuration + next sweep).
+template <int UNUSED> // (a template only to get weak linkage from a header)
+__global__ void __launch_bounds__(FQSB_S2_THREADS, 4)
+    k_stream_np_2d(const __grid_constant__ Par P, const __grid_constant__ State S,
+                   const __grid_constant__ RunArgs A, const int flip, const int first,
+                   const int do_sweep)
+{
+    constexpr int TX = FQSB_S2_TX, TY = FQSB_S2_TY;
+    __shared__ __align__(16) double su[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
+    __shared__ double scratch[32 * 2];
+    __shared__ int s_last;
+    const int t = threadIdx.x;
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    if (ctl.status != ST_RUNNING) {
+        return;
     }
-    if (lane == 0) {
-        // a stop keeps the input buffer (the sweep of this launch is discarded)
-        ctl.flip = (status == ST_RUNNING && do_sweep) ? flip ^ 1 : flip;
-        ctl.count = 0u;
-        ctl.status = status;
+    const int R_ = P.rows, C_ = P.cols;
+    const int strips = (C_ + TX - 1) / TX;
+    const int strip = blockIdx.x % strips, band = blockIdx.x / strips;
+    const int c0 = strip * TX, row0 = band * TY;
+    const int cnt = C_ - c0 < TX ? C_ - c0 : TX;
+    const int nrow = R_ - row0 < TY ? R_ - row0 : TY;
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ uold = (flip ? S.u2 : S.u) + base;
+    double* __restrict__ unew = (flip ? S.u : S.u2) + base;
+    const bool act = 2 * t < cnt;
+    const int col = c0 + 2 * t;
+    const int hcol = t == 0 ? (c0 == 0 ? C_ - 1 : c0 - 1) : (c0 + cnt == C_ ? 0 : c0 + cnt);
+    const double uf = S.u_frame[r];
+    const double k = P.k1, kf = P.k_frame, mu = P.mu;
+    const double denom = 4 * k + kf + mu;
+    const double rdenom = 1.0 / denom;
+
+    struct Row {
+        double2 u;
+        double h;
+    };
+    auto load_row = [&](int gr, Row& x) {
+        const int wr = gr < 0 ? gr + R_ : (gr >= R_ ? gr - R_ : gr);
+        const i64 rowoff = (i64)wr * C_;
+        if (act) {
+            x.u = *reinterpret_cast<const double2*>(uold + rowoff + col);
+        }
+        if (t < 2) {
+            x.h = uold[rowoff + hcol];
+        }
+    };
+    auto publish = [&](const Row& x, int slot) {
+        if (act) {
+            *reinterpret_cast<double2*>(&su[slot][2 + 2 * t]) = x.u;
+        }
+        if (t < 2) {
+            su[slot][t == 0 ? 1 : 2 + cnt] = x.h;
+        }
+    };
+
+    // software pipeline: slips are loaded three rows ahead, wells two rows ahead of their use
+    // (a sweep moves only 32 B per block, so one row of look-ahead leaves too little in flight)
+    Row top, cur, nxt, nn, n3;
+    top.u = cur.u = nxt.u = nn.u = n3.u = make_double2(0.0, 0.0);
+    top.h = cur.h = nxt.h = nn.h = n3.h = 0.0;
+    double2 l2 = make_double2(0.0, 0.0), r2 = l2, l2n = l2, r2n = l2, l2nn = l2, r2nn = l2;
+    auto load_wells = [&](int gr, double2& l, double2& rr) {
+        if (act && gr < row0 + nrow) {
+            l = *reinterpret_cast<const double2*>(S.yl + base + (i64)gr * C_ + col);
+            rr = *reinterpret_cast<const double2*>(S.yr + base + (i64)gr * C_ + col);
+        }
+    };
+    load_row(row0 - 1, top);
+    load_row(row0, cur);
+    load_row(row0 + 1, nxt);
+    load_row(row0 + 2, nn);
+    load_wells(row0, l2, r2);
+    load_wells(row0 + 1, l2n, r2n);
+    publish(top, (row0 + 3) & 3);
+    publish(cur, row0 & 3);
+
+    double acc[2] = {0.0, 0.0};
+    int underflow = 0;
+    bool nan = false;
+    for (int i = row0; i < row0 + nrow; ++i) {
+        if (i + 3 <= row0 + nrow) {
+            load_row(i + 3, n3);
+        }
+        load_wells(i + 2, l2nn, r2nn);
+        publish(nxt, (i + 1) & 3);
+        const i64 rowoff = (i64)i * C_;
+        __syncthreads();
+        if (act) {
+            const double* up = &su[(i + 3) & 3][2];
+            const double* mid = &su[i & 3][2];
+            const double* dn = &su[(i + 1) & 3][2];
+            double ucv[2] = {cur.u.x, cur.u.y};
+            double wl[2] = {l2.x, l2.y};
+            double wr[2] = {r2.x, r2.y};
+            double out[2];
+            const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lc = 2 * t + e;
+                const double uc = ucv[e];
+                const double a = up[lc], b = dn[lc], c = mid[lc - 1], d = mid[lc + 1];
+                const double uneigh = a + b + c + d;           // detail.h:1715-1723 (2-D)
+                const double lap = a + b + c + d - 4 * uc;     // detail.h:557-582
+                {
+                    double umin = 0.5 * (wl[e] + wr[e]);
+                    double ff = kf * (uf - uc);
+                    double fp = mu * (umin - uc);
+                    double fi = lap * k;
+                    double f = fp + fi + ff;
+                    acc[0] += own ? f * f : 0.0;
+                    acc[1] += own ? ff * ff : 0.0;
+                    nan |= uc != uc;
+                }
+                double un = uc;
+                if (do_sweep) {
+                    int total = 0;
+                    u64 st = 0;
+                    i64 i0 = 0;
+                    bool loaded = false;
+                    const i64 gp = base + rowoff + col + e;
+                    for (;;) { // detail.h:1728-1738
+                        double umin = 0.5 * (wl[e] + wr[e]);
+                        un = div_by_invariant(k * uneigh + kf * uf + mu * umin, denom, rdenom);
+                        if (!(un > wr[e] || !(un > wl[e])) || un != un) {
+                            break;
+                        }
+                        if (!loaded) {
+                            st = S.rng[gp];
+                            i0 = S.idx[gp];
+                            loaded = true;
+                        }
+                        int moved = well_align(P, un, wl[e], wr[e], st, i0 + total, &underflow);
+                        total += moved;
+                        if (moved == 0) {
+                            break;
+                        }
+                    }
+                    if (loaded) {
+                        S.rng[gp] = st;
+                        S.idx[gp] = i0 + total;
+                        S.yl[gp] = wl[e];
+                        S.yr[gp] = wr[e];
+                    }
+                }
+                out[e] = un;
+            }
+            if (do_sweep) {
+                *reinterpret_cast<double2*>(unew + rowoff + col) = make_double2(out[0], out[1]);
+            }
+        }
+        cur = nxt;
+        nxt = nn;
+        nn = n3;
+        l2 = l2n;
+        r2 = r2n;
+        l2n = l2nn;
+        r2n = r2nn;
     }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+    if (nan) {
+        S.err[1] = 1;
+    }
+    block_sum<2>(acc, scratch);
+    double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
+    if (threadIdx.x == 0) {
+        part[0] = acc[0];
+        part[1] = acc[1];
+        __threadfence();
+        unsigned int ticket = atomicAdd(&ctl.count, 1u);
+        s_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) {
+        return;
+    }
+    __threadfence();
+    np_finalise(P, S, A, r, flip, first, do_sweep);
 }
 
 } // namespace fqsb

@@ -135,6 +135,11 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
 cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
                                 cudaStream_t stream, int flip, int first, int do_sweep)
 {
+    if (use_tiled_2d(P)) {
+        dim3 grid2((unsigned)stream_step_tiles(P, 0), (unsigned)P.R);
+        k_stream_np_2d<0><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
     if (P.inter == INT_LAPLACE2D) {
         k_stream_np<INT_LAPLACE2D><<<grid, 256, 0, stream>>>(P, S, A, flip, first, do_sweep);

@@ -253,9 +253,14 @@ def test_no_convergence_and_nan_errors():
     ("Particles_Cuspy", 400),
 ])
 def test_golden_protocol_on_gpu(name, nstep, golden_dir):
-    """The reference's own regression: examples/<name>.py against its committed .h5."""
+    """The reference's own regression: examples/<name>.py against its committed .h5.
+    FQSB_FULL_GOLDEN=1 runs every example to the end of its golden."""
+    import os
+
     F = product()
     golden = np.load(golden_dir / f"{name}.npz")
+    if os.environ.get("FQSB_FULL_GOLDEN", "0") == "1":
+        nstep = len(golden["S"])
     system = protocol.make(F.Line1d, F.Line2d, name, F.Particles)
     protocol.check(golden, *protocol.run(system, nstep))
 
