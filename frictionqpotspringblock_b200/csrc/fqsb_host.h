@@ -13,10 +13,10 @@ struct ResidentCfg {
 };
 
 static const ResidentCfg kResidentCfgs[] = {
-    {1, 256, false},  // 0
-    {1, 1024, false}, // 1
-    {2, 1024, false}, // 2
-    {8, 512, false},  // 3
+    {1, 256, false},  // 0: N <= 256
+    {2, 512, false},  // 1: N <= 1024 (1.43 us/step at N = 1000, vs 2.07 with 1 x 1024)
+    {4, 512, false},  // 2: N <= 2048
+    {8, 512, false},  // 3: N <= 4096
 };
 static const int kNumResidentCfgs = 4;
 

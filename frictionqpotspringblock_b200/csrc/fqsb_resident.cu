@@ -82,8 +82,8 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
         FQSB_TRY_MODE(b, t, false, false) \
     }
     FQSB_TRY_CFG(1, 256)
-    FQSB_TRY_CFG(1, 1024)
-    FQSB_TRY_CFG(2, 1024)
+    FQSB_TRY_CFG(2, 512)
+    FQSB_TRY_CFG(4, 512)
     FQSB_TRY_CFG(8, 512)
     return cudaErrorInvalidConfiguration;
 }
@@ -98,11 +98,11 @@ static cudaError_t launch_np(const ResidentCfg& c, const Par& P, const State& S,
     if (c.B == 1 && c.T == 256) {
         return launch(k_resident_nopassing<INT, 1, 256>, 256, smem, P, S, A, stream);
     }
-    if (c.B == 1 && c.T == 1024) {
-        return launch(k_resident_nopassing<INT, 1, 1024>, 1024, smem, P, S, A, stream);
+    if (c.B == 2 && c.T == 512) {
+        return launch(k_resident_nopassing<INT, 2, 512>, 512, smem, P, S, A, stream);
     }
-    if (c.B == 2 && c.T == 1024) {
-        return launch(k_resident_nopassing<INT, 2, 1024>, 1024, smem, P, S, A, stream);
+    if (c.B == 4 && c.T == 512) {
+        return launch(k_resident_nopassing<INT, 4, 512>, 512, smem, P, S, A, stream);
     }
     if (c.B == 8 && c.T == 512) {
         return launch(k_resident_nopassing<INT, 8, 512>, 512, smem, P, S, A, stream);
