@@ -37,3 +37,63 @@ def test_cpp_host_reproduces_golden(golden_dir):
     assert np.allclose([float(r[1]) for r in rows], golden["x_frame"][:n])
     assert np.allclose([float(r[2]) for r in rows], golden["f_frame"][:n])
     assert "error fqsb: assertion failed (tol < 1.0)" in out
+
+
+def _pybind():
+    import importlib
+    import sys
+
+    sys.path.insert(0, str(PKG))
+    try:
+        return importlib.import_module("_FrictionQPotSpringBlock")
+    finally:
+        sys.path.remove(str(PKG))
+
+
+def test_pybind_module_builds_and_refuses_without_gpu():
+    """The reference's binder templates (python/main.cpp) re-bound on include/fqsb.hpp."""
+    P = _pybind()
+    assert P.version() == "0.1.0"
+    for name in ("System_Cuspy_Laplace", "System_Cuspy_Laplace_Nopassing",
+                 "System_SemiSmooth_Laplace", "System_Smooth_Laplace", "System_Cuspy_Quartic",
+                 "System_Cuspy_QuarticGradient", "System_Cuspy_LongRange"):
+        assert hasattr(P.Line1d, name)
+    assert hasattr(P.Line2d, "System_Cuspy_Laplace")
+    import frictionqpotspringblock_b200 as F
+
+    if F.device_count() == 0:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            P.Line1d.System_Cuspy_Laplace(m=1, eta=1, mu=1, k_interactions=1, k_frame=0.1,
+                                          dt=0.1, shape=[8], seed=0, distribution="random",
+                                          parameters=[2.0])
+
+
+@pytest.mark.gpu
+def test_pybind_module_reproduces_golden(golden_dir):
+    from tests import protocol
+
+    P = _pybind()
+
+    class Chunk:  # the examples read system.chunk.index_at_align
+        def __init__(self, s):
+            self._s = s
+
+        @property
+        def index_at_align(self):
+            return self._s.index_at_align
+
+    system = P.Line1d.System_Cuspy_Laplace(k_interactions=1.0, **protocol.BASE)
+    system_proxy = type("Proxy", (), {})()
+    golden = np.load(golden_dir / "Line1d_Cuspy_Laplace.npz")
+
+    class Wrapped:
+        chunk = Chunk(system)
+
+        def __getattr__(self, k):
+            return getattr(system, k)
+
+        def __setattr__(self, k, v):
+            setattr(system, k, v)
+
+    protocol.check(golden, *protocol.run(Wrapped(), 60))
+    del system_proxy
