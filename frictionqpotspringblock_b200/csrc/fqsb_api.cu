@@ -447,9 +447,11 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
             CU(cudaStreamSynchronize(s->stream));
             S.pref = s->d_pref;
             // circulant table tab[k] = pref[min(k, N-k)] (detail.h:859-862) and its row sum
-            ResidentCfg cfg;
-            const bool stream_path = (par->kernel & 15) == 2 || resident_cfg(P.N).B == 0;
-            (void)cfg;
+            // chosen for lines beyond the resident kernel, when streaming is forced, and -- in
+            // auto mode -- for ensembles, where the exact-order O(N^2) sum inside the resident
+            // kernel (bit-identical to the reference's loop) would leave the tensor cores idle
+            const bool stream_path = (par->kernel & 15) == 2 || resident_cfg(P.N).B == 0 ||
+                                     ((par->kernel & 15) == 0 && P.R >= 32);
             if (stream_path && P.N % 2 == 0 && P.N >= 256 &&
                 lr_gemm_smem(P.N) <= 227 * 1024) {
                 std::vector<double> tab((size_t)P.N, 0.0);
@@ -822,6 +824,9 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
     *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
     if (mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N) {
         return false; // slab batches run on the streaming kernels
+    }
+    if (s->lr_gemm) {
+        return false; // LongRange through the tensor-core GEMM (K7)
     }
     if ((s->par.kernel & 15) == 2 || cfg->B == 0) {
         return false;

@@ -95,18 +95,23 @@ def halo_plan(rank: int, world: int):
     return sends, recvs
 
 
-def exchange_halos(export_cells, import_cells, layout, rank, world, group=None, device="cpu"):
+def exchange_halos(export_cells, import_cells, layout, rank, world, group=None, device="cpu",
+                   buffers=None):
     """Refresh the halo rows from the neighbours' owned rows.
 
     ``export_cells(first, count, tensor)`` / ``import_cells(first, count, tensor)`` move the packed
     state of ``count`` cells starting at local cell ``first`` to / from a torch int64 tensor of
     7*count words on ``device``. ``layout`` = dict(top=(first,count), bottom=..., top_halo=...,
-    bottom_halo=...)."""
+    bottom_halo=...). ``buffers``: optional dict reused across calls (one tensor per entry)."""
     import torch
     import torch.distributed as dist
 
     def buf(which):
-        return torch.empty(7 * layout[which][1], dtype=torch.int64, device=device)
+        if buffers is None:
+            return torch.empty(7 * layout[which][1], dtype=torch.int64, device=device)
+        if which not in buffers:
+            buffers[which] = torch.empty(7 * layout[which][1], dtype=torch.int64, device=device)
+        return buffers[which]
 
     if world == 1:  # periodic wrap onto oneself
         for src, dst in (("top", "bottom_halo"), ("bottom", "top_halo")):
@@ -129,7 +134,7 @@ def exchange_halos(export_cells, import_cells, layout, rank, world, group=None, 
     if str(device).startswith("cuda"):
         # req.wait() only orders torch's current stream after the NCCL transfer; the import
         # kernels run on the handle's own stream, so the host has to wait for the data
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
     for which, t in inbox:
         import_cells(*layout[which], t)
 
@@ -176,6 +181,7 @@ class SlabSystem:
         }
         self._mu, self._k_frame = float(kw["mu"]), float(kw["k_frame"])
         self._overdamped = "Nopassing" in cls
+        self._buffers = {}
         # Steps per batch. Verlet: after k steps the garbage entering through the outermost halo
         # row has corrupted v,a of halo row k-1 but not yet its position, so the owned rows and
         # their forces are exact for k = halo. Jacobi sweeps: the residual of state k reads the
@@ -200,7 +206,7 @@ class SlabSystem:
 
     def exchange(self):
         exchange_halos(self._export, self._import, self.layout, self.rank, self.world,
-                       self.group, self._tdev)
+                       self.group, self._tdev, self._buffers)
 
     def _allreduce(self, arr: np.ndarray, op: str = "sum") -> np.ndarray:
         if self.world == 1:

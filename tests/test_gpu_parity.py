@@ -348,7 +348,7 @@ def test_longrange_gemm_ensemble_matches_resident():
     N, R = 1024, 70  # ragged realisation tile (64 + 6)
     kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, alpha=1.5, nrealisations=R, **PHYS)
     a = F.Line1d.Ensemble_Cuspy_LongRange(kernel=1, **kw)  # exact O(N^2) sum, resident
-    b = F.Line1d.Ensemble_Cuspy_LongRange(kernel=2, **kw)  # tensor-core GEMM
+    b = F.Line1d.Ensemble_Cuspy_LongRange(**kw)  # auto: tensor-core GEMM for an ensemble
     for s in (a, b):
         s.u_frame = np.full(R, 1.5)
         s.timeSteps(40)
