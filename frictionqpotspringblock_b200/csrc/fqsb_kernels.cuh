@@ -720,25 +720,26 @@ __device__ __forceinline__ void stream_finalise(const Par& P, const State& S, co
         *s_last = ticket == gridDim.x - 1;
     }
     __syncthreads();
-    if (!*s_last || threadIdx.x >= 32) {
+    if (!*s_last) {
         return;
     }
+    // the last CTA of the realisation: all its threads gather the per-CTA partials (thread t
+    // takes CTAs t, t + blockDim, ... in order), then one fixed-order block reduction
     __threadfence();
-    const int lane = threadIdx.x;
-    double sf = 0.0, sff = 0.0, dh = 0.0, ds = 0.0, da = 0.0;
+    double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const volatile double* all = S.part + (size_t)r * gridDim.x * FQSB_NPART;
-    for (int c = lane; c < (int)gridDim.x; c += 32) {
-        sf += all[c * FQSB_NPART];
-        sff += all[c * FQSB_NPART + 1];
-        dh += all[c * FQSB_NPART + 2];
-        ds += all[c * FQSB_NPART + 3];
-        da += all[c * FQSB_NPART + 4];
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            tot[k] += all[c * FQSB_NPART + k];
+        }
     }
-    sf = warp_sum(sf);
-    sff = warp_sum(sff);
-    dh = warp_sum(dh);
-    ds = warp_sum(ds);
-    da = warp_sum(da);
+    block_sum<5>(tot, scratch);
+    if (threadIdx.x >= 32) {
+        return;
+    }
+    const int lane = threadIdx.x;
+    const double sf = tot[0], sff = tot[1], dh = tot[2], ds = tot[3], da = tot[4];
     Prog g;
     prog_load(g, ctl);
     g.inc++;
@@ -774,7 +775,7 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
 {
     constexpr int J = FQSB_ST_J, SLAB = FQSB_ST_SLAB;
     __shared__ __align__(16) double sun[J][SLAB + 4]; // [1] left halo, [2..2+SLAB) data, then right
-    __shared__ double scratch[32 * 2];
+    __shared__ double scratch[32 * 5];
     __shared__ int iscratch[32 * 4];
     __shared__ int s_last;
     const int r = blockIdx.y;
@@ -911,7 +912,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
 {
     constexpr int TX = FQSB_S2_TX, TY = FQSB_S2_TY;
     __shared__ __align__(16) double sun[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
-    __shared__ double scratch[32 * 2];
+    __shared__ double scratch[32 * 5];
     __shared__ int iscratch[32 * 4];
     __shared__ int s_last;
     const int t = threadIdx.x;
@@ -1096,7 +1097,7 @@ __global__ void __launch_bounds__(256)
     k_stream_step(const __grid_constant__ Par P, const __grid_constant__ State S,
                   const __grid_constant__ RunArgs A, const int flip, const int finalise)
 {
-    __shared__ double scratch[32 * 2];
+    __shared__ double scratch[32 * 5];
     __shared__ int iscratch[32 * 4];
     __shared__ int s_last;
     const int r = blockIdx.y;

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256)
                 const __grid_constant__ RunArgs A, const double* __restrict__ W,
                 const double* __restrict__ Y, const double rowsum, const int finalise)
 {
-    __shared__ double scratch[32 * 2];
+    __shared__ double scratch[32 * 5];
     __shared__ int iscratch[32 * 4];
     __shared__ int s_last;
     const int r = blockIdx.y;
