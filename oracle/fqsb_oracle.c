@@ -1340,7 +1340,7 @@ typedef struct {
     orc_ensemble* e;
     int tid;
     int64_t nsteps;
-    int prepare;
+    int prepare; /* 1: create + minimise + kick, 2: kick only, 0: timeSteps */
     double checksum;
 } ens_arg;
 
@@ -1350,7 +1350,14 @@ static void* ens_worker(void* vp)
     orc_ensemble* e = a->e;
     double cs = 0.0;
     for (int64_t r = a->tid; r < e->nsys; r += e->nthreads) {
-        if (a->prepare) {
+        if (a->prepare == 2) {
+            if (e->sys[r]) {
+                double du;
+                orc_event_driven_step(e->sys[r], 1e-3, 0, 1, &du);
+                orc_event_driven_step(e->sys[r], 1e-3, 1, 1, &du);
+            }
+        }
+        else if (a->prepare) {
             orc_params par = e->par;
             int64_t n = par.shape[0] * (par.rank == 2 ? par.shape[1] : 1);
             par.seed = e->par.seed + (uint64_t)(r * n);
@@ -1416,6 +1423,9 @@ double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum
 {
     return ens_run(e, 0, nsteps, checksum);
 }
+
+/* eventDrivenStep(eps, false) + eventDrivenStep(eps, true) on every system (untimed by callers) */
+void orc_ensemble_kick(orc_ensemble* e) { ens_run(e, 2, 0, NULL); }
 
 void orc_ensemble_destroy(orc_ensemble* e)
 {

@@ -147,6 +147,7 @@ double orc_draw_to_spacing(double r, int32_t distribution, const double* par);
 typedef struct orc_ensemble orc_ensemble;
 orc_ensemble* orc_ensemble_create(const orc_params* par, int64_t nsys, int nthreads);
 double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum);
+void orc_ensemble_kick(orc_ensemble* e);
 void orc_ensemble_destroy(orc_ensemble* e);
 
 #ifdef __cplusplus

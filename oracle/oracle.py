@@ -94,6 +94,7 @@ def lib():
         L.orc_ensemble_time_steps.restype = C.c_double
         L.orc_ensemble_time_steps.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.orc_ensemble_destroy.argtypes = [C.c_void_p]
+        L.orc_ensemble_kick.argtypes = [C.c_void_p]
         L.orc_set_u_frame.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_t.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_inc.argtypes = [C.c_void_p, C.c_int64]
@@ -412,6 +413,10 @@ class CpuEnsemble:
         cs = C.c_double()
         sec = lib().orc_ensemble_time_steps(self._e, int(nsteps), C.byref(cs))
         return sec, cs.value
+
+    def kick(self):
+        """eventDrivenStep(1e-3, False) + eventDrivenStep(1e-3, True) on every line."""
+        lib().orc_ensemble_kick(self._e)
 
     def __del__(self):
         if getattr(self, "_e", None):
