@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-events", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=8, help="handles of the pipelined e2e arm")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,7 +247,8 @@ def main():
         check(lib.fqsb_get(ens._h, 0, hout.data_ptr(), n))
         check(lib.fqsb_mean_f_frame(ens._h, hmean.ctypes.data))
 
-    # ---- end-to-end arm (host buffers, copies inside the timed region)
+    # ---- end-to-end arm (host buffers, copies inside the timed region), one handle: the three
+    #      uploads, the kernel and the download of a step serialise
     for _ in range(max(1, W // 2)):
         e2e_step()
     barrier()
@@ -254,10 +256,66 @@ def main():
     for _ in range(K):
         e2e_step()
     barrier()
-    e2e_sec = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * R * N * T * K / e2e_sec
+    e2e1_sec = max_over_ranks(time.perf_counter() - t0)
+    e2e1_value = world * R * N * T * K / e2e1_sec
     h2d = 3 * n * 8
     d2h = n * 8 + R * 8
+
+    # ---- end-to-end arm, pipelined: the same ensemble split over `npipe` handles driven by
+    #      host threads through the same public calls (ctypes releases the GIL, every handle owns
+    #      a stream), so one handle's PCIe copies overlap another handle's kernel. Same bytes,
+    #      same steps, all copies inside the timed region.
+    npipe = args.pipeline if R % max(1, args.pipeline) == 0 else 1
+    e2e_sec, e2e_value = e2e1_sec, e2e1_value
+    if npipe > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        Rp = R // npipe
+        npart = Rp * N
+        parts = []
+        for k in range(npipe):
+            ek = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=Rp, device=local_rank,
+                                                 seed=rank * R * N + k * Rp * N, **kw)
+            assert np.all(ek.minimise() == 0)
+            ek.eventDrivenStep(1e-3, False)
+            ek.eventDrivenStep(1e-3, True)
+            sl = slice(k * npart, (k + 1) * npart)
+            for which, buf in ((0, hu), (1, hv), (2, ha)):
+                check(lib.fqsb_get(ek._h, which, buf[sl].data_ptr(), npart))
+            parts.append((ek, sl, np.empty(Rp, dtype=np.float64)))
+
+        def part_step(part):
+            ek, sl, mean = part
+            torch.cuda.set_device(local_rank)
+            check(lib.fqsb_set_u(ek._h, hu[sl].data_ptr(), npart))
+            check(lib.fqsb_set_v(ek._h, hv[sl].data_ptr(), npart))
+            check(lib.fqsb_set_a(ek._h, ha[sl].data_ptr(), npart))
+            check(lib.fqsb_time_steps(ek._h, T))
+            check(lib.fqsb_get(ek._h, 0, hout[sl].data_ptr(), npart))
+            check(lib.fqsb_mean_f_frame(ek._h, mean.ctypes.data))
+
+        def part_loop(arg):
+            part, nsteps, delay = arg
+            time.sleep(delay)  # stagger the handles so that copies and kernels interleave
+            for _ in range(nsteps):
+                part_step(part)
+
+        with ThreadPoolExecutor(max_workers=npipe) as pool:
+            list(pool.map(part_loop, [(p, max(1, W // 2), 0.0) for p in parts]))
+            barrier()
+            # offset of about one part's upload time (copies are ~1/4 of a single-handle step)
+            stagger = 0.25 * e2e1_sec / K / npipe
+            t0 = time.perf_counter()
+            list(pool.map(part_loop, [(p, K, k * stagger) for k, p in enumerate(parts)]))
+            barrier()
+            e2e_sec = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = world * R * N * T * K / e2e_sec
+        for ek, _sl, _m in parts:
+            del ek
+        del parts
+        # restore the single-handle snapshot for the device-resident arm
+        for which, buf in ((0, hu), (1, hv), (2, ha)):
+            check(lib.fqsb_get(ens._h, which, buf.data_ptr(), n))
 
     # ---- device-resident arm: the state is already in HBM when the timed region starts
     check(lib.fqsb_set_u(ens._h, hu.data_ptr(), n))
@@ -417,7 +475,13 @@ def main():
             "config": workload_config(args, R, T, "gpu"),
             "roofline": roofline, "roofline_stream": roofline_stream, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_sec / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_sec / K,
+                    "handles": npipe,
+                    "how": "set_u/set_v/set_a from pinned host memory, timeSteps(T), get u + "
+                           "mean f_frame per realisation, through the C ABI; the ensemble is "
+                           "split over `handles` handles driven by host threads so copies "
+                           "overlap kernels",
+                    "single_handle": {"value": e2e1_value, "ms_per_step": 1e3 * e2e1_sec / K}},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
             "quasistatic_events": events,
         }
