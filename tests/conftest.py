@@ -16,3 +16,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+def pytest_sessionstart(session):
+    """A clean checkout has no built artefacts (they are git-ignored): build them once."""
+    lib = ROOT / "frictionqpotspringblock_b200" / "libfqsb.so"
+    ora = ROOT / "oracle" / "libfqsb_oracle.so"
+    if not lib.exists() or not ora.exists():
+        import __graft_entry__
+
+        __graft_entry__.build()
