@@ -80,6 +80,10 @@ struct fqsb_system {
     bool snap_valid;
     double* d_log;
     size_t log_cap;
+    // K2b (temporally blocked tiles of a long 1-D line): second set of the well arrays, log
+    BlockedArgs bk;
+    bool bk_ready;
+    int bk_log_tiles;
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -352,6 +356,9 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->snap_valid = false;
     s->d_log = nullptr;
     s->log_cap = 0;
+    memset(&s->bk, 0, sizeof s->bk);
+    s->bk_ready = false;
+    s->bk_log_tiles = 0;
     s->d_lr_tab = s->d_lr_w = s->d_lr_y = nullptr;
     s->lr_rowsum = 0.0;
     s->kernel_ms = 0.0;
@@ -834,6 +841,134 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
     return resident_smem(s->P, *cfg) <= 227 * 1024;
 }
 
+// K2b: 1-D nearest-neighbour lines beyond one CTA take the temporally blocked kernel
+// (par.kernel: low 4 bits 0 = auto, 3 = force; bits 8..15 steps per launch, bits 16..31 owned
+// blocks per tile -- both 0 = planner's choice)
+static bool use_blocked(const fqsb_system* s, int mode, bool overdamped)
+{
+    const int sel = s->par.kernel & 15;
+    if (overdamped || mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N || s->lr_gemm) {
+        return false;
+    }
+    if (!blocked_supported(s->P)) {
+        return false;
+    }
+    return sel == 3 || (sel == 0 && s->N > kResidentMaxN);
+}
+
+static int ensure_stream_buffers(fqsb_system* s);
+
+static int ensure_blocked_buffers(fqsb_system* s, const BlockedPlan& plan)
+{
+    TRY(ensure_stream_buffers(s));
+    if (!s->bk_ready) {
+        TRY(dev_alloc(s, &s->bk.yl2, (size_t)s->n));
+        TRY(dev_alloc(s, &s->bk.yr2, (size_t)s->n));
+        TRY(dev_alloc(s, &s->bk.idx2, (size_t)s->n));
+        TRY(dev_alloc(s, &s->bk.rng2, (size_t)s->n));
+        TRY(dev_alloc(s, &s->bk.uf2, (size_t)s->R));
+        s->bk_ready = true;
+    }
+    if (plan.ntiles > s->bk_log_tiles) { // (the geometry depends on the batch length)
+        TRY(dev_alloc(s, &s->bk.log,
+                      (size_t)s->R * FQSB_BK_MAXSTEPS * (size_t)plan.ntiles * FQSB_NLOG));
+        s->bk_log_tiles = plan.ntiles;
+    }
+    s->bk.own = plan.own;
+    s->bk.H = plan.H;
+    s->bk.ksteps = plan.ksteps;
+    s->bk.ntiles = plan.ntiles;
+    return FQSB_OK;
+}
+
+// one dynamics call on the blocked kernel: batches of up to plan.ksteps steps per launch
+static int run_blocked(fqsb_system* s, RunArgs A)
+{
+    // steps per launch: long batches amortise the pass over memory (measured on one line of
+    // 2^20 blocks: 4.76 / 4.44 / 3.66 us per step at 16 / 32 / 64 steps per launch); a stop
+    // inside a batch costs a replay of the batch up to that step, so timeStepsUntilEvent --
+    // which stops within a few steps while an avalanche runs -- takes short ones
+    int ksteps = (s->par.kernel >> 8) & 255;
+    if (ksteps == 0) {
+        ksteps = A.mode == MODE_UNTIL_EVENT ? 8 : FQSB_BK_MAXSTEPS;
+    }
+    const BlockedPlan plan = blocked_plan(s->P, ksteps, (s->par.kernel >> 16) & 0xffff);
+    if (plan.B < 2 || plan.B > 8 || blocked_smem(plan.B) > 227 * 1024) {
+        return fail(FQSB_EUNSUPPORTED, "no tile geometry for the blocked kernel");
+    }
+    TRY(ensure_blocked_buffers(s, plan));
+    s->last_kernel = "blocked_1d";
+    BlockedArgs K = s->bk;
+    if (A.mode == MODE_FIXED) {
+        CU(cudaEventRecord(s->ev0, s->stream));
+        i64 done = 0;
+        int flip = 0;
+        while (done < A.max_steps) {
+            const i64 left = A.max_steps - done;
+            K.nsteps = (int)(left < plan.ksteps ? left : plan.ksteps);
+            K.flip = flip;
+            cudaError_t e = launch_blocked(plan, s->P, s->S, A, K, s->stream);
+            if (e != cudaSuccess) {
+                return cuda_fail(e, "blocked kernel launch");
+            }
+            done += K.nsteps;
+            flip ^= 1;
+            s->launches++;
+            s->kernel_launches++;
+        }
+        CU(cudaEventRecord(s->ev1, s->stream));
+        CU(launch_blocked_fixed_done(s->P, s->S, A.max_steps, flip, s->stream));
+        s->launches++;
+    }
+    else {
+        CU(launch_blocked_begin(s->P, s->S, plan.ksteps, A.max_steps, s->stream));
+        s->launches++;
+        i64 nb = 4;
+        for (;;) {
+            CU(cudaEventRecord(s->ev0, s->stream));
+            for (i64 b = 0; b < nb; ++b) {
+                cudaError_t e = launch_blocked(plan, s->P, s->S, A, K, s->stream);
+                if (e != cudaSuccess) {
+                    return cuda_fail(e, "blocked kernel launch");
+                }
+            }
+            CU(cudaEventRecord(s->ev1, s->stream));
+            s->launches += nb;
+            s->kernel_launches += nb;
+            TRY(pull_ctl(s));
+            {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+                s->kernel_ms += ms;
+            }
+            bool running = false;
+            for (i64 r = 0; r < s->R; ++r) {
+                running |= s->h_ctl[r].status == ST_RUNNING;
+            }
+            if (!running) {
+                break;
+            }
+            if (nb < 64) {
+                nb *= 2;
+            }
+        }
+    }
+    CU(launch_blocked_settle(s->P, s->S, s->bk, s->stream));
+    {
+        const unsigned rg = (unsigned)((s->R + 127) / 128);
+        k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
+        CU(cudaGetLastError());
+    }
+    s->launches += 2;
+    if (A.mode == MODE_FIXED) {
+        TRY(pull_ctl(s));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->kernel_ms += ms;
+    }
+    return FQSB_OK;
+}
+
 static int ensure_stream_buffers(fqsb_system* s)
 {
     if (s->lr_gemm) {
@@ -875,7 +1010,11 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
     }
 
     ResidentCfg cfg;
-    if (use_resident(s, &cfg, A.mode)) {
+    const int sel = s->par.kernel & 15;
+    if (sel != 1 && sel != 2 && use_blocked(s, A.mode, overdamped)) {
+        TRY(run_blocked(s, A));
+    }
+    else if (use_resident(s, &cfg, A.mode)) {
         s->last_kernel = overdamped ? "resident_nopassing" : "resident";
         const i64 chunk = (i64)1 << 20;
         for (;;) {

@@ -1,0 +1,437 @@
+// fqsb_blocked.cuh -- K2b: temporally blocked velocity-Verlet for 1-D lines that do not fit one CTA.
+//
+// A line of N > 4096 blocks (BASELINE config #3: N = 2^20) cannot live in the shared memory of
+// one SM, and streaming it once per step (k_stream_1d) is bound by memory traffic: 64 B per
+// block-update. The 3-point stencils (detail.h:474-487, 639-652, 778-804) only couple nearest
+// neighbours, so information travels one block per step: a tile of `own` blocks extended by H
+// halo blocks on each side can be integrated for k <= H steps WITHOUT any exchange -- after s
+// steps only the outermost s blocks of each side have been contaminated by the missing
+// neighbours, and those are halo copies whose owner tile computes them exactly. One launch
+// therefore advances the whole line by k steps with ONE pass over HBM / L2 (all seven per-block
+// arrays in, all seven out: 112 B per block per launch = 3.5 B per block-update at k = 32), and
+// the inner loop is the on-chip loop of k_resident (slips in shared memory, v, a, wells in
+// registers, pcg32 states in shared memory), bound by the FP64 pipe instead of by memory.
+//
+// grid = (tiles, R). The new state goes to the other buffer set (neighbouring tiles still read
+// the old one as their halo), which also makes a launch revocable: in the stop modes every tile
+// logs its per-step partial sums (owned blocks only), the last tile to finish adds them up in
+// tile order, replays the per-step decisions of timeStepsUntilEvent / minimise /
+// minimise_truncate (detail.h:1605-1619, 1764-1784, 1858-1886) and either commits the batch
+// (flips the buffer set) or -- the criterion fired at step s* < k -- leaves the input set
+// current and asks for a batch of exactly s* steps. No host round trip is involved; the host
+// only polls the status every few batches.
+#pragma once
+
+#include "fqsb_kernels.cuh"
+
+namespace fqsb {
+
+// rare path: a block of the tile left its well. The global index is idx_in + sdidx (the delta
+// accumulated during this launch); the input set is never written.
+static __device__ __noinline__ int hop_blocked(const Par& P, double un, double* yl, double* yr,
+                                               u64* st, i64 i0, int* underflow)
+{
+    double l = *yl, r = *yr;
+    u64 s = *st;
+    int moved = well_align(P, un, l, r, s, i0, underflow);
+    *yl = l;
+    *yr = r;
+    *st = s;
+    return moved;
+}
+
+template <int POT, int INT, int B, bool UNIT, bool STOP>
+__global__ void __launch_bounds__(FQSB_BK_T)
+    k_blocked(const __grid_constant__ Par P, const __grid_constant__ State S,
+              const __grid_constant__ RunArgs A, const __grid_constant__ BlockedArgs K)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int T = FQSB_BK_T, NW = T / 32, LMAX = B * T;
+    __shared__ int s_last;
+    const int c = blockIdx.x, r = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    Ctl& ctl = S.ctl[r];
+    if (ctl.status != ST_RUNNING) {
+        return;
+    }
+    const int flip = STOP ? ctl.flip : K.flip;
+    const int nsteps = STOP ? ctl.batch : K.nsteps;
+    if (nsteps <= 0) {
+        return;
+    }
+    const int N = (int)P.N;
+    const int own0 = c * K.own;
+    const int cnt = N - own0 < K.own ? N - own0 : K.own;
+    const int H = K.H;
+    const int L = cnt + 2 * H; // local blocks q = 0..L-1 are global blocks own0 - H + q (mod N)
+    const int NS = LMAX + 2;   // slip buffer stride: one ghost cell on each side
+    auto GP = [&](int q) {
+        int p = own0 - H + q;
+        return p < 0 ? p + N : (p >= N ? p - N : p);
+    };
+
+    double* us = reinterpret_cast<double*>(smem_raw);          // [2][NS]
+    u64* sst = reinterpret_cast<u64*>(us + 2 * (size_t)NS);    // [LMAX]
+    double* slog = reinterpret_cast<double*>(sst + LMAX);      // [MAXSTEPS][NW][2]
+    int* ilog = reinterpret_cast<int*>(slog + FQSB_BK_MAXSTEPS * NW * 2); // [MAXSTEPS][NW][4]
+    int* sdidx = ilog + FQSB_BK_MAXSTEPS * NW * 4;             // [LMAX]
+
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
+    const double* __restrict__ vi = (flip ? S.v2 : S.v) + base;
+    const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
+    const double* __restrict__ yli = (flip ? K.yl2 : S.yl) + base;
+    const double* __restrict__ yri = (flip ? K.yr2 : S.yr) + base;
+    const i64* __restrict__ idxi = (flip ? K.idx2 : S.idx) + base;
+    const u64* __restrict__ rngi = (flip ? K.rng2 : S.rng) + base;
+    double uf = (flip ? K.uf2 : S.u_frame)[r];
+
+    double v[B], a[B], yl[B], yr[B];
+    unsigned ownmask = 0u;
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        const int q = t + j * T;
+        const int qc = q < L ? q : L - 1;
+        const int gp = GP(qc);
+        v[j] = vi[gp];
+        a[j] = ai[gp];
+        yl[j] = yli[gp];
+        yr[j] = yri[gp];
+        if (q < L) {
+            us[q + 1] = ui[gp];
+            sst[q] = rngi[gp];
+            sdidx[q] = 0;
+        }
+        if (q >= H && q < H + cnt) {
+            ownmask |= 1u << j;
+        }
+    }
+    // the cells just outside the tile stay frozen at their input value: the error this makes
+    // enters at the outermost halo block and moves inwards one block per step
+    if (t < 2) {
+        const double g = ui[GP(t == 0 ? -1 : L)];
+        const int cell = t == 0 ? 0 : L + 1;
+        us[cell] = g;
+        us[NS + cell] = g;
+    }
+    __syncthreads();
+
+    const double c2 = 0.5 * P.dt * P.dt; // (0.5*dt)*dt, detail.h:1549
+    int underflow = 0;
+    int prev = 0;
+
+    // ---- positions (detail.h:1549)
+    auto phase1 = [&](const int oprev, const int ocur) {
+        const double* uprev = us + oprev;
+        double* ucur = us + ocur;
+        double un[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int q = t + j * T;
+            const int qc = q < L ? q : L - 1;
+            un[j] = uprev[qc + 1] + P.dt * v[j] + c2 * a[j];
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int q = t + j * T;
+            if (q < L) {
+                ucur[q + 1] = un[j];
+            }
+        }
+    };
+
+    // ---- well search (detail.h:144), forces (detail.h:1380-1386), Verlet tail (1552-1565)
+    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
+                      int& dS, int& dA) {
+        const double* ucur = us + ocur;
+        auto U = [&](int q) { return ucur[q + 1]; };
+        double uc[B];
+        unsigned need = 0u;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int q = t + j * T;
+            const int qc = q < L ? q : L - 1;
+            uc[j] = ucur[qc + 1];
+            if (q < L && (uc[j] > yr[j] || !(uc[j] > yl[j]))) {
+                need |= 1u << j;
+            }
+        }
+        if (need) { // rare: some block of this thread left its well
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                if ((need >> j) & 1u) {
+                    const int q = t + j * T;
+                    const int gp = GP(q);
+                    const i64 i0 = idxi[gp] + sdidx[q];
+                    int uflag = 0;
+                    double l = yl[j], rr = yr[j];
+                    int moved = hop_blocked(P, uc[j], &l, &rr, sst + q, i0, &uflag);
+                    yl[j] = l;
+                    yr[j] = rr;
+                    sdidx[q] += moved;
+                    if ((ownmask >> j) & 1u) { // halo copies are accounted for by their owner
+                        underflow |= uflag;
+                        hops += moved != 0;
+                        track_hop(A, base + gp, i0, moved, dS, dA);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int q = t + j * T;
+            const int qc = q < L ? q : L - 1;
+            double fi = f_interactions<INT, false, UNIT>(P, U, nullptr, qc, 0, 0, uc[j]);
+            double fp = f_potential<POT, UNIT>(P, uc[j], yl[j], yr[j]);
+            double ff = P.k_frame * (uf - uc[j]);
+            double F = ff + fp + fi;
+            double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
+            if (decltype(accumulate)::value) {
+                const bool own = (ownmask >> j) & 1u;
+                sf += own ? f * f : 0.0;
+                sff += own ? ff * ff : 0.0;
+            }
+        }
+    };
+
+    if (!STOP) {
+        double sf = 0.0, sff = 0.0;
+        int hops = 0, dS = 0, dA = 0;
+        for (int it = 0; it < nsteps; ++it) {
+            if (A.flow) {
+                uf += A.v_frame * P.dt; // detail.h:1642
+            }
+            phase1(prev * NS, (prev ^ 1) * NS);
+            __syncthreads();
+            phase2((prev ^ 1) * NS, std::false_type{}, sf, sff, hops, dS, dA);
+            prev ^= 1;
+        }
+    }
+    else {
+        for (int it = 0; it < nsteps; ++it) {
+            double sf = 0.0, sff = 0.0;
+            int hops = 0, dS = 0, dA = 0;
+            phase1(prev * NS, (prev ^ 1) * NS);
+            __syncthreads();
+            phase2((prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
+            prev ^= 1;
+            // per-warp partials of this step; nobody waits for them before the launch ends
+            warp_sum2(sf, sff);
+            hops = __reduce_add_sync(0xffffffffu, hops);
+            if (A.track) {
+                dS = __reduce_add_sync(0xffffffffu, dS);
+                dA = __reduce_add_sync(0xffffffffu, dA);
+            }
+            if (lane == 0) {
+                slog[(it * NW + warp) * 2] = sf;
+                slog[(it * NW + warp) * 2 + 1] = sff;
+                ilog[(it * NW + warp) * 4] = hops;
+                ilog[(it * NW + warp) * 4 + 1] = dS;
+                ilog[(it * NW + warp) * 4 + 2] = dA;
+            }
+        }
+    }
+
+    // ---- owned blocks -> the other buffer set
+    {
+        double* __restrict__ uo = (flip ? S.u : S.u2) + base;
+        double* __restrict__ vo = (flip ? S.v : S.v2) + base;
+        double* __restrict__ ao = (flip ? S.a : S.a2) + base;
+        double* __restrict__ ylo = (flip ? S.yl : K.yl2) + base;
+        double* __restrict__ yro = (flip ? S.yr : K.yr2) + base;
+        i64* __restrict__ idxo = (flip ? S.idx : K.idx2) + base;
+        u64* __restrict__ rngo = (flip ? S.rng : K.rng2) + base;
+        const double* ufin = us + (size_t)prev * NS;
+        bool nan = false;
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            if ((ownmask >> j) & 1u) {
+                const int q = t + j * T;
+                const int gp = own0 - H + q; // owned: no wrap
+                const double uu = ufin[q + 1];
+                uo[gp] = uu;
+                vo[gp] = v[j];
+                ao[gp] = a[j];
+                ylo[gp] = yl[j];
+                yro[gp] = yr[j];
+                rngo[gp] = sst[q];
+                idxo[gp] = idxi[gp] + sdidx[q];
+                nan |= uu != uu;
+            }
+        }
+        if (nan) {
+            S.err[1] = 1;
+        }
+        if (underflow) {
+            S.err[0] = 1;
+        }
+        if (c == 0 && t == 0) {
+            (flip ? S.u_frame : K.uf2)[r] = uf;
+        }
+    }
+    if (!STOP) {
+        return;
+    }
+
+    // ---- this tile's per-step sums (warps added in order) -> global log
+    __syncthreads();
+    for (int s = t; s < nsteps; s += T) {
+        double a0 = 0.0, a1 = 0.0;
+        int h = 0, ds = 0, da = 0;
+        for (int w = 0; w < NW; ++w) {
+            a0 += slog[(s * NW + w) * 2];
+            a1 += slog[(s * NW + w) * 2 + 1];
+            h += ilog[(s * NW + w) * 4];
+            ds += ilog[(s * NW + w) * 4 + 1];
+            da += ilog[(s * NW + w) * 4 + 2];
+        }
+        double* e = K.log + (((size_t)r * FQSB_BK_MAXSTEPS + s) * K.ntiles + c) * FQSB_NLOG;
+        e[0] = a0;
+        e[1] = a1;
+        e[2] = (double)h;
+        e[3] = (double)ds;
+        e[4] = (double)da;
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        unsigned int ticket = atomicAdd(&ctl.count, 1u);
+        s_last = ticket == (unsigned)K.ntiles - 1u;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    // ---- the last tile of the realisation: totals per step (tiles added in order: lane-strided
+    //      partial sums, then a fixed butterfly), then the sequential replay of the decisions
+    __threadfence();
+    double* tot = slog; // [MAXSTEPS][FQSB_NLOG] (the warp partials have been consumed)
+    for (int s = warp; s < nsteps; s += NW) {
+        double x[FQSB_NLOG];
+#pragma unroll
+        for (int k = 0; k < FQSB_NLOG; ++k) {
+            x[k] = 0.0;
+        }
+        const volatile double* e =
+            K.log + ((size_t)r * FQSB_BK_MAXSTEPS + s) * K.ntiles * FQSB_NLOG;
+        for (int cc = lane; cc < K.ntiles; cc += 32) {
+#pragma unroll
+            for (int k = 0; k < FQSB_NLOG; ++k) {
+                x[k] += e[cc * FQSB_NLOG + k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FQSB_NLOG; ++k) {
+            x[k] = warp_sum(x[k]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < FQSB_NLOG; ++k) {
+                tot[s * FQSB_NLOG + k] = x[k];
+            }
+        }
+    }
+    __syncthreads();
+    if (warp != 0) {
+        return;
+    }
+    Prog g;
+    prog_load(g, ctl);
+    RingEntry ring = ring_load(ctl, A, lane);
+    int status = ST_RUNNING;
+    double sf = 0.0, sff = 0.0;
+    int s = 0;
+    for (; s < nsteps; ++s) {
+        sf = tot[s * FQSB_NLOG];
+        sff = tot[s * FQSB_NLOG + 1];
+        g.inc++; // detail.h:1541
+        status = step_decide(A, g, ring, lane, sf, sff, (int)tot[s * FQSB_NLOG + 2],
+                             (int)tot[s * FQSB_NLOG + 3], (int)tot[s * FQSB_NLOG + 4]);
+        if (status != ST_RUNNING) {
+            break;
+        }
+    }
+    if (status == ST_RUNNING || s == nsteps - 1) {
+        // commit: the output set becomes current
+        ring_store(ctl, A, lane, ring);
+        if (lane == 0) {
+            prog_store(g, ctl);
+            ctl.residual = residual_from_sums(sf, sff);
+            ctl.flip = flip ^ 1;
+            const i64 left = A.max_steps - g.steps;
+            ctl.batch = (int)(left < K.ksteps ? left : K.ksteps);
+            ctl.count = 0u;
+            ctl.status = status;
+        }
+    }
+    else if (lane == 0) {
+        // the criterion fired inside the batch: keep the input set, redo exactly s + 1 steps
+        // (the replay of that shorter batch stops at its last step and commits)
+        ctl.batch = s + 1;
+        ctl.count = 0u;
+    }
+}
+
+#ifdef FQSB_BLOCKED_HELPERS
+// start of a stop-mode call: size of the first batch
+__global__ void k_blocked_begin(const Par P, const State S, int ksteps, i64 max_steps)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P.R) {
+        S.ctl[r].batch = (int)(max_steps < ksteps ? max_steps : ksteps);
+    }
+}
+
+// end of a fixed-step call (no per-step bookkeeping on the device)
+__global__ void k_blocked_fixed_done(const Par P, const State S, i64 nsteps, int flip)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < P.R) {
+        Ctl& c = S.ctl[r];
+        c.inc += nsteps; // detail.h:1541
+        c.steps = nsteps;
+        c.flip = flip;
+        c.status = ST_EXHAUSTED;
+    }
+}
+
+// bring the current set back into the primary arrays; quench() on convergence
+// (detail.h:1527-1532, 1781)
+__global__ void k_blocked_settle(const Par P, const State S, const BlockedArgs K)
+{
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    const int flip = ctl.flip;
+    const bool quench = ctl.status == ST_CONVERGED;
+    if (!flip && !quench) {
+        return;
+    }
+    const i64 base = (i64)r * P.N;
+    for (i64 p = blockIdx.x * (i64)blockDim.x + threadIdx.x; p < P.N;
+         p += (i64)gridDim.x * blockDim.x) {
+        const i64 g = base + p;
+        if (flip) {
+            S.u[g] = S.u2[g];
+            S.yl[g] = K.yl2[g];
+            S.yr[g] = K.yr2[g];
+            S.idx[g] = K.idx2[g];
+            S.rng[g] = K.rng2[g];
+        }
+        if (quench) {
+            S.v[g] = 0.0;
+            S.a[g] = 0.0;
+        }
+        else if (flip) {
+            S.v[g] = S.v2[g];
+            S.a[g] = S.a2[g];
+        }
+    }
+    if (flip && blockIdx.x == 0 && threadIdx.x == 0) {
+        S.u_frame[r] = K.uf2[r];
+    }
+}
+
+#endif // FQSB_BLOCKED_HELPERS
+
+} // namespace fqsb

@@ -72,6 +72,8 @@ struct Ctl {
     double ring_den[FQSB_RING];
     unsigned int count;     // streaming path: CTAs of this realisation that finished the step
     int flip;               // streaming path: which of the two u/v/a buffer sets is current
+    int batch;              // blocked path: steps of the next launch (k, or the redo length)
+    int pad1;
 };
 
 struct RunArgs {
@@ -102,6 +104,25 @@ struct State {
     const double* pref;   // LongRange prefactor table [N] (detail.h:829-844)
     double* part;         // streaming path: per-CTA partial sums
     int tiles;            // streaming path: CTAs per realisation
+};
+
+// ---- K2b (fqsb_blocked.cuh): temporally blocked tiles of a long 1-D line ----------------------
+#define FQSB_BK_T 512       // threads per tile
+#define FQSB_BK_MAXSTEPS 64 // upper bound of steps per launch (size of the per-step log)
+
+struct BlockedArgs {
+    int own;    // owned blocks per tile (the last tile may own fewer)
+    int H;      // halo blocks on each side (>= ksteps unless the system has no interactions)
+    int ksteps; // steps per launch
+    int ntiles;
+    int nsteps; // fixed-step calls: steps of this launch (stop modes: Ctl::batch)
+    int flip;   // fixed-step calls: which set is the input (stop modes: Ctl::flip)
+    // second buffer set of the arrays that State does not already double (u2, v2, a2 do)
+    double *yl2, *yr2;
+    i64* idx2;
+    u64* rng2;
+    double* uf2; // [R]
+    double* log; // [R][FQSB_BK_MAXSTEPS][ntiles][FQSB_NLOG]
 };
 
 // ---- prrng::pcg32 ------------------------------------------------------

@@ -72,6 +72,31 @@ cudaError_t launch_resident(const ResidentCfg& cfg, const Par& P, const State& S
                             const RunArgs& A, cudaStream_t stream);
 cudaError_t launch_resident_nopassing(const ResidentCfg& cfg, const Par& P, const State& S,
                                       const RunArgs& A, cudaStream_t stream);
+// defined in fqsb_blocked.cu (one object per potential x interaction combination): K2b, the
+// temporally blocked kernel for 1-D lines beyond one CTA
+struct BlockedPlan {
+    int B;      // blocks per thread (tile capacity B * 512 local blocks)
+    int own;    // owned blocks per tile
+    int H;      // halo blocks on each side
+    int ksteps; // steps per launch
+    int ntiles;
+};
+bool blocked_supported(const Par& P);
+BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint);
+// dynamic shared memory of k_blocked (must mirror the carve-up in the kernel)
+inline size_t blocked_smem(int B)
+{
+    const size_t lmax = (size_t)B * FQSB_BK_T, nw = FQSB_BK_T / 32;
+    return 2 * (lmax + 2) * 8 + lmax * 8 + FQSB_BK_MAXSTEPS * nw * (2 * 8 + 4 * 4) + lmax * 4;
+}
+cudaError_t launch_blocked(const BlockedPlan& plan, const Par& P, const State& S,
+                           const RunArgs& A, const BlockedArgs& K, cudaStream_t stream);
+cudaError_t launch_blocked_begin(const Par& P, const State& S, int ksteps, i64 max_steps,
+                                 cudaStream_t stream);
+cudaError_t launch_blocked_fixed_done(const Par& P, const State& S, i64 nsteps, int flip,
+                                      cudaStream_t stream);
+cudaError_t launch_blocked_settle(const Par& P, const State& S, const BlockedArgs& K,
+                                  cudaStream_t stream);
 // defined in fqsb_stream.cu
 // `flip`: parity of the launch within the call (which buffer set is the input);
 // `finalise`: run the per-step stop decision (stop modes and flowSteps)

@@ -95,7 +95,10 @@ typedef struct {
     int64_t nrealisations; /* 0 is read as 1 */
     int64_t seed_stride;   /* 0 is read as prod(shape) */
     int32_t device;        /* CUDA ordinal; -1 = current device */
-    int32_t kernel;        /* 0 auto, 1 force resident (one CTA per realisation), 2 force streaming */
+    int32_t kernel;        /* low 4 bits: 0 auto, 1 force resident (one CTA per realisation), 2 force
+                              streaming (one step per launch), 3 force the temporally blocked tiles
+                              (1-D nearest-neighbour lines; bits 8..15 steps per launch, bits 16..31
+                              owned blocks per tile, 0 = planner's choice); bits 4..7 resident variant */
     /* slab decomposition: local block p is global block (seed_first + p) mod seed_period and draws
      * the global block's pcg32 stream; seed_period == 0 disables the mapping */
     int64_t seed_first;

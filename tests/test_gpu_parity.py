@@ -16,6 +16,13 @@ pytestmark = pytest.mark.gpu
 PHYS = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, dt=0.1, seed=3, distribution="random",
             parameters=[2.0], offset=-50)
 
+# kernel selector of the temporally blocked path (K2b): 3 | steps per launch << 8 | owned blocks
+# per tile << 16 -- small tiles and short batches so that tile seams, ragged last tiles, partial
+# batches and redone batches are all exercised at test sizes
+BLOCKED = 3 | (6 << 8) | (101 << 16)
+KERNELS = dict(argvalues=[1, 2, BLOCKED], ids=["resident", "stream", "blocked"])
+KERNEL_NAME = {1: "resident", 2: "stream", BLOCKED: "blocked"}
+
 SYSTEMS_1D = [
     ("System_Cuspy_Laplace", dict(k_interactions=1.0), True),
     ("System_Cuspy_Quartic", dict(a1=1.0, a2=0.7), True),
@@ -42,10 +49,12 @@ def kicked(o, p):
         s.eventDrivenStep(1e-3, True)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("kernel", **KERNELS)
 @pytest.mark.parametrize("cls,extra,exact", SYSTEMS_1D, ids=[s[0] for s in SYSTEMS_1D])
 @pytest.mark.parametrize("N", [7, 300, 1000])
 def test_fixed_steps_line1d(cls, extra, exact, N, kernel):
+    if kernel == BLOCKED and cls == "System_Cuspy_LongRange":
+        pytest.skip("all-to-all interaction: no temporal blocking")
     o, p = pair("Line1d", cls, shape=[N], k_frame=1.0 / N, kernel=kernel, **extra, **PHYS)
     rtol = 1e-12
     if cls == "System_Cuspy_LongRange" and kernel == 2 and N >= 256:
@@ -60,7 +69,7 @@ def test_fixed_steps_line1d(cls, extra, exact, N, kernel):
         o.timeSteps(n)
         p.timeSteps(n)
         assert_same_state(o, p, exact, rtol)
-    assert p.last_kernel.startswith("resident" if kernel == 1 else "stream")
+    assert p.last_kernel.startswith(KERNEL_NAME[kernel])
 
 
 @pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
@@ -90,7 +99,7 @@ def test_large_resident_configurations():
         assert_same_state(o, p)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("kernel", **KERNELS)
 def test_minimise_and_event_driven_match_oracle(kernel):
     N = 400
     o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
@@ -118,7 +127,7 @@ def test_minimise_and_event_driven_match_oracle(kernel):
         assert np.isclose(o.residual, p.residual, rtol=1e-9, atol=1e-300)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("kernel", **KERNELS)
 def test_time_steps_until_event(kernel):
     N = 300
     o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
@@ -142,7 +151,7 @@ def test_time_steps_until_event(kernel):
     assert o.timeStepsUntilEvent(max_iter=3) == p.timeStepsUntilEvent(max_iter=3)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("kernel", **KERNELS)
 def test_minimise_truncate_and_activity(kernel):
     N = 500
     o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0 / N, k_interactions=1.0,
@@ -188,6 +197,61 @@ def test_streaming_multi_tile(N):
     assert p.last_kernel == ("stream_1d" if N % 2 == 0 else "stream")
 
 
+@pytest.mark.parametrize("cls,extra", [
+    ("System_Cuspy_Laplace", dict(k_interactions=1.0)),
+    ("System_Cuspy_Quartic", dict(a1=1.0, a2=1.0)),
+    ("System_SemiSmooth_Laplace", dict(k_interactions=1.0, kappa=1.0)),
+])
+@pytest.mark.parametrize("N", [4097, 9000, 20000])
+def test_blocked_default_geometry(cls, extra, N):
+    """lines beyond one CTA take the temporally blocked kernel by default (planner's tiles, 32
+    steps per launch): fixed steps, a partial batch, the stop modes and a quasistatic cycle."""
+    o, p = pair("Line1d", cls, shape=[N], k_frame=1.0 / N, **extra, **PHYS)
+    for s in (o, p):
+        s.u_frame = 2.5
+        s.timeSteps(70)
+    assert p.last_kernel == "blocked_1d"
+    assert_same_state(o, p)
+    ro = o.timeStepsUntilEvent()
+    rp = p.timeStepsUntilEvent()
+    assert ro == rp
+    assert_same_state(o, p)
+    assert o.minimise() == p.minimise() == 0
+    assert_same_state(o, p)
+    i_n = o.chunk.index_at_align
+    for s in (o, p):
+        s.eventDrivenStep(1e-3, False)
+        s.eventDrivenStep(1e-3, True)
+    assert o.minimise(time_activity=True) == p.minimise(time_activity=True) == 0
+    assert o.quasistaticActivityFirst == p.quasistaticActivityFirst
+    assert o.quasistaticActivityLast == p.quasistaticActivityLast
+    assert_same_state(o, p)
+    S, A = p.avalanche(i_n)
+    assert S == np.sum(o.chunk.index_at_align - i_n)
+    assert A == np.sum(o.chunk.index_at_align != i_n)
+    assert p.last_kernel == "blocked_1d"
+
+
+def test_blocked_ensemble_equals_streaming():
+    """an ensemble of long lines: every realisation takes its own stop decision per batch."""
+    F = product()
+    N, R = 6000, 5
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, nrealisations=R, **PHYS)
+    a = F.Line1d.Ensemble_Cuspy_Laplace(kernel=2, **kw)
+    b = F.Line1d.Ensemble_Cuspy_Laplace(**kw)
+    for s in (a, b):
+        s.u_frame = np.full(R, 0.5)
+        assert s.minimise().tolist() == [0] * R
+        s.eventDrivenStep(1e-3, False)
+        s.eventDrivenStep(1e-3, True)
+        s.timeSteps(101)
+        assert s.minimise().tolist() == [0] * R
+    assert a.last_kernel == "stream_1d" and b.last_kernel == "blocked_1d"
+    assert np.array_equal(a.u, b.u)
+    assert np.array_equal(a.inc, b.inc)
+    assert np.array_equal(a.chunk.index_at_align, b.chunk.index_at_align)
+
+
 def test_streaming_ensemble_matches_resident():
     F = product()
     N, R = 2048, 6
@@ -206,7 +270,7 @@ def test_streaming_ensemble_matches_resident():
     assert np.array_equal(a.chunk.index_at_align, b.chunk.index_at_align)
 
 
-@pytest.mark.parametrize("kernel", [1, 2], ids=["resident", "stream"])
+@pytest.mark.parametrize("kernel", **KERNELS)
 def test_flow_steps_and_temperature(kernel):
     N = 256
     o, p = pair("Line1d", "System_Cuspy_Laplace", shape=[N], k_frame=1.0, k_interactions=1.0,
