@@ -26,14 +26,22 @@ def version_compiler():
     return ["nvcc=12.9", "std=c++17", "arch=sm_100a"]
 
 
-def _define(name, potential, interactions, lead, minimisation=0, doc=""):
-    """Create System_<name> / Ensemble_<name>; `lead` = leading constructor arguments."""
+_FORCING = ("mean", "stddev", "seed_forcing", "dinc_init", "dinc")
+
+
+def _define(name, potential, interactions, lead, minimisation=0, doc="", forcing=False):
+    """Create System_<name> / Ensemble_<name>; `lead` = leading constructor arguments.
+    `forcing`: External = RandomNormalForcing (Line1d.h:261-330: its five arguments follow
+    `lead`; minimisation = None)."""
+    if forcing:
+        lead = tuple(lead) + _FORCING
+        minimisation = 2
 
     def make(base, prefix):
         def __init__(self, *args, **kw):
             names = list(lead) + ["shape", "seed", "distribution", "parameters", "offset",
                                   "nchunk"]
-            if minimisation:
+            if minimisation == 1:
                 names += ["eta", "dt"]  # Line1d.h:199-211
             if len(args) > len(names):
                 raise TypeError(f"{prefix}{name}: too many positional arguments")
@@ -56,6 +64,8 @@ def _define(name, potential, interactions, lead, minimisation=0, doc=""):
                     k2 = kw.pop(key)
             if "kappa" in lead:
                 kappa = kw.pop("kappa")
+            if forcing:
+                kw["forcing"] = tuple(kw.pop(key) for key in _FORCING)
             base.__init__(
                 self, potential, interactions, kw.pop("shape"),
                 m=kw.pop("m", 1.0), eta=kw.pop("eta", 0.0), mu=kw.pop("mu"), kappa=kappa,
@@ -89,5 +99,10 @@ _define("Cuspy_Quartic", "Cuspy", "Quartic1d", ("m", "eta", "mu", "a1", "a2", "k
         doc="Line1d.h:428-480.")
 _define("Cuspy_QuarticGradient", "Cuspy", "QuarticGradient1d",
         ("m", "eta", "mu", "k2", "k4", "k_frame", "dt"), doc="Line1d.h:562-614.")
+_define("Cuspy_Laplace_RandomForcing", "Cuspy", "Laplace1d", _STD, forcing=True,
+        doc="Line1d.h:261-330: System_Cuspy_Laplace plus a random force per block drawn from a "
+            "normal distribution (External = RandomNormalForcing); no minimisation.")
+_define("Cuspy_Quartic_RandomForcing", "Cuspy", "Quartic1d",
+        ("m", "eta", "mu", "a1", "a2", "k_frame", "dt"), forcing=True, doc="Line1d.h:486-556.")
 _define("Cuspy_LongRange", "Cuspy", "LongRange1d",
         ("m", "eta", "mu", "k_interactions", "alpha", "k_frame", "dt"), doc="Line1d.h:620-672.")

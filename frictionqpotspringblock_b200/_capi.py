@@ -124,6 +124,14 @@ SIGNATURES = {
     "fqsb_import_cells": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int]),
     "fqsb_advance_uniformly": (C.c_int, [_P, _P, _P]),
     "fqsb_reduce_sums": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "fqsb_enable_random_forcing": (C.c_int, [_P, C.c_double, C.c_double, C.c_uint64, C.c_int64,
+                                             _P, _P, C.c_int64]),
+    "fqsb_external_get_f_thermal": (C.c_int, [_P, _P, C.c_int64]),
+    "fqsb_external_set_f_thermal": (C.c_int, [_P, _P, C.c_int64]),
+    "fqsb_external_get_next": (C.c_int, [_P, _P, C.c_int64]),
+    "fqsb_external_set_next": (C.c_int, [_P, _P, C.c_int64]),
+    "fqsb_external_get_state": (C.c_int, [_P, _P]),
+    "fqsb_external_set_state": (C.c_int, [_P, _P]),
     "fqsb_host_alloc": (_P, [C.c_size_t]),
     "fqsb_host_free": (None, [_P]),
     "fqsb_launch_count": (C.c_int64, [_P]),

@@ -129,6 +129,52 @@ class _Chunk:
         self._start = index.copy()
 
 
+class _External:
+    """``system.external``: the ``detail::RandomNormalForcing`` object of a thermal system
+    (main.cpp:250-275: ``state``, ``f_thermal``, ``next``)."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def _get(self, fn, dtype):
+        o = self._o
+        out = np.empty(o._full_shape, dtype=dtype)
+        check(fn(o._h, out.ctypes.data, out.size))
+        return o._squeeze(out)
+
+    def _set(self, fn, arg, dtype, text):
+        o = self._o
+        arg = np.ascontiguousarray(arg, dtype=dtype)
+        if arg.shape != o._user_shape:  # detail.h:978,997
+            raise RuntimeError(f"assertion failed (xt::has_shape({text}, m_{text}.shape()))")
+        check(fn(o._h, arg.ctypes.data, arg.size))
+
+    f_thermal = property(
+        lambda self: self._get(lib.fqsb_external_get_f_thermal, np.float64),
+        lambda self, x: self._set(lib.fqsb_external_set_f_thermal, x, np.float64, "f_thermal"),
+        doc="Random force")
+    next = property(
+        lambda self: self._get(lib.fqsb_external_get_next, np.int64),
+        lambda self, x: self._set(lib.fqsb_external_set_next, x, np.int64, "next"),
+        doc="Next draw increment")
+
+    @property
+    def state(self):
+        """State of RNG"""
+        out = np.empty(self._o._R, dtype=np.uint64)
+        check(lib.fqsb_external_get_state(self._o._h, out.ctypes.data))
+        return int(out[0]) if self._o._squeeze_realisation else out
+
+    @state.setter
+    def state(self, arg):
+        arg = np.ascontiguousarray(np.broadcast_to(np.asarray(arg, dtype=np.uint64),
+                                                   (self._o._R,)))
+        check(lib.fqsb_external_set_state(self._o._h, arg.ctypes.data))
+
+    def __repr__(self):
+        return "<FrictionQPotSpringBlock.detail.RandomNormalForcing_1>"
+
+
 class Ensemble:
     """``nrealisations`` independent systems in one device-resident handle.
 
@@ -142,7 +188,8 @@ class Ensemble:
     def __init__(self, potential, interactions, shape, *, m=1.0, eta=0.0, mu=1.0, kappa=0.0,
                  k1=0.0, k2=0.0, k_frame=1.0, dt=0.0, seed=0, distribution="random",
                  parameters=(), offset=-100.0, nchunk=5000, minimisation=0, nrealisations=1,
-                 seed_stride=0, device=-1, kernel=0, seed_first=0, seed_period=0):
+                 seed_stride=0, device=-1, kernel=0, seed_first=0, seed_period=0, forcing=None,
+                 seed_forcing_stride=1):
         self._h = C.c_void_p()
         self._par = _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
                             k2, k_frame, dt, seed, distribution, parameters, offset, nchunk,
@@ -155,6 +202,20 @@ class Ensemble:
         self._kind = (potential, interactions, int(minimisation))
         check(lib.fqsb_create(C.byref(self._par), C.byref(self._h)))
         self._chunk = _Chunk(self)
+        if forcing is not None:  # Line1d.h:316-318: External = RandomNormalForcing
+            mean, stddev, seed_forcing, dinc_init, dinc = forcing
+            arrs = []
+            for arr in (dinc_init, dinc):
+                arr = np.asarray(arr, dtype=np.int64)
+                if arr.shape == self._shape:  # one schedule shared by every realisation
+                    arr = np.broadcast_to(arr, self._full_shape)
+                if arr.shape != self._full_shape:
+                    raise RuntimeError("assertion failed (xt::has_shape(dinc, shape))")
+                arrs.append(np.ascontiguousarray(arr))
+            check(lib.fqsb_enable_random_forcing(
+                self._h, float(mean), float(stddev), int(seed_forcing), int(seed_forcing_stride),
+                arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[0].size))
+            self._external = _External(self)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -202,6 +263,14 @@ class Ensemble:
     @property
     def f_neighbours(self):
         raise RuntimeError("Deprecated, use 'f_interactions'")
+
+    @property
+    def external(self):
+        """Class adding external force (main.cpp:207); thermal systems only."""
+        ext = getattr(self, "_external", None)
+        if ext is None:
+            raise AttributeError("external: not a RandomForcing system")
+        return ext
 
     # ---- parameters (main.cpp:65-79)
     chunk = property(lambda self: self._chunk, doc="Chunk of random numbers")
@@ -354,7 +423,8 @@ class Ensemble:
     def __repr__(self):
         pot, inter, mini = self._kind
         return (f"<frictionqpotspringblock_b200 {pot}/{inter}"
-                f"{'/Nopassing' if mini else ''} shape={list(self._shape)} "
+                f"{'/Nopassing' if mini == 1 else ('/RandomForcing' if mini == 2 else '')} "
+                f"shape={list(self._shape)} "
                 f"nrealisations={self._R}>")
 
 

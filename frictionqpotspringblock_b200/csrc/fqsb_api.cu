@@ -84,6 +84,9 @@ struct fqsb_system {
     BlockedArgs bk;
     bool bk_ready;
     int bk_log_tiles;
+    // External = RandomNormalForcing (detail.h:881-1000): enabled by fqsb_enable_random_forcing
+    bool thermal;
+    Thermal th;
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -243,6 +246,21 @@ static int push_ctl(fqsb_system* s)
     return FQSB_OK;
 }
 
+// updated_inc() of a thermal system (detail.h:1369-1375): redraw the due blocks, refresh
+// System::m_f_thermal; the stored force arrays follow on the next getter
+static int thermal_update(fqsb_system* s, int inc_add, int only_running)
+{
+    if (!s->thermal) {
+        return FQSB_OK;
+    }
+    const unsigned threads = s->N >= 1024 ? 1024u : (unsigned)(((s->N + 31) / 32) * 32);
+    k_thermal_draw<<<(unsigned)s->R, threads, 0, s->stream>>>(s->P, s->S, s->th, inc_add,
+                                                              only_running);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FQSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -363,6 +381,8 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->lr_rowsum = 0.0;
     s->kernel_ms = 0.0;
     s->kernel_launches = 0;
+    s->thermal = false;
+    memset(&s->th, 0, sizeof s->th);
     memset(&s->F, 0, sizeof s->F);
     memset(&s->S, 0, sizeof s->S);
 
@@ -630,7 +650,15 @@ int fqsb_set_inc(fqsb_system* s, const int64_t* inc)
         s->h_ctl[r].qs_first = inc[r];
         s->h_ctl[r].qs_last = inc[r];
     }
-    return push_ctl(s);
+    TRY(push_ctl(s));
+    if (s->thermal) { // updated_inc(), detail.h:1246
+        TRY(thermal_update(s, 0, 0));
+        if (!s->forces_frozen) {
+            s->forces_valid = false;
+        }
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    return FQSB_OK;
 }
 
 int fqsb_set_t(fqsb_system* s, const double* t)
@@ -652,6 +680,7 @@ int fqsb_refresh(fqsb_system* s)
 {
     TRY(enter(s));
     TRY(align(s, nullptr));
+    TRY(thermal_update(s, 0, 0)); // updated_inc(), detail.h:1314
     invalidate_forces(s);
     return check_flags(s);
 }
@@ -832,8 +861,8 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
     if (mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N) {
         return false; // slab batches run on the streaming kernels
     }
-    if (s->lr_gemm) {
-        return false; // LongRange through the tensor-core GEMM (K7)
+    if (s->lr_gemm || s->thermal) {
+        return false; // LongRange through the tensor-core GEMM (K7); thermal: streaming kernel
     }
     if ((s->par.kernel & 15) == 2 || cfg->B == 0) {
         return false;
@@ -847,7 +876,8 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
 static bool use_blocked(const fqsb_system* s, int mode, bool overdamped)
 {
     const int sel = s->par.kernel & 15;
-    if (overdamped || mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N || s->lr_gemm) {
+    if (overdamped || mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N || s->lr_gemm ||
+        s->thermal) {
         return false;
     }
     if (!blocked_supported(s->P)) {
@@ -1051,7 +1081,8 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         s->last_kernel = overdamped ? "stream_nopassing"
                                     : (s->lr_gemm ? "stream_longrange_dmma" : stream_step_name(s->P));
         // fixed-step calls without a moving frame need no per-step decision on the device
-        const int finalise = (A.mode != MODE_FIXED || A.flow) ? 1 : 0;
+        // (thermal systems need Ctl::inc up to date ahead of every step)
+        const int finalise = (A.mode != MODE_FIXED || A.flow || s->thermal) ? 1 : 0;
         // upper bound on launches still useful (no-passing: launch l decides sweep l-1)
         i64 remaining = overdamped ? A.max_steps + 1 : A.max_steps;
         i64 launched = 0;
@@ -1061,6 +1092,9 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
                                           : (remaining < batch ? remaining : batch);
             CU(cudaEventRecord(s->ev0, s->stream));
             for (i64 b = 0; b < nb; ++b) {
+                if (s->thermal) { // m_inc++; updated_inc(): detail.h:1541-1544
+                    TRY(thermal_update(s, 1, 1));
+                }
                 cudaError_t e =
                     overdamped ? launch_stream_sweep(s->P, s->S, A, s->stream,
                                                      (int)((launched + b) & 1), launched + b == 0,
@@ -1234,6 +1268,9 @@ int fqsb_minimise(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_ite
     TRY(enter(s));
     if (!(tol < 1.0)) {
         return fail(FQSB_EASSERT, ASSERT_MSG("tol < 1.0")); // detail.h:1684
+    }
+    if (s->par.minimisation == FQSB_MIN_NONE) {
+        return fail(FQSB_EUNSUPPORTED, "Minimisation not implementated"); // detail.h:1691-1693
     }
     const bool overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
     if (overdamped && time_activity) {
@@ -1732,6 +1769,127 @@ int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n
     }
     TRY(reduce_to_host(s, what, direction, d_in));
     memcpy(out, s->h_out, (size_t)s->R * 4 * sizeof(double));
+    return FQSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// External = RandomNormalForcing (detail.h:881-1000); the thermal classes of Line1d.h:261-330,
+// 486-556 and Particles.h construct it right after the generator, before initSystem's refresh()
+// ---------------------------------------------------------------------------------------------
+int fqsb_enable_random_forcing(fqsb_system* s, double mean, double stddev, uint64_t seed_forcing,
+                               int64_t seed_forcing_stride, const int64_t* dinc_init,
+                               const int64_t* dinc, int64_t n)
+{
+    TRY(enter(s));
+    if (s->thermal) {
+        return fail(FQSB_EASSERT, "random forcing already enabled");
+    }
+    if (n != s->n) { // detail.h:978 has_shape
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(dinc, m_f_thermal.shape())"));
+    }
+    const bool combo_ok = s->P.pot == POT_CUSPY && (s->P.inter == INT_LAPLACE1D ||
+                                                    s->P.inter == INT_QUARTIC1D ||
+                                                    s->P.inter == INT_NONE);
+    if (!combo_ok || s->par.minimisation == FQSB_MIN_OVERDAMPED) {
+        return fail(FQSB_EUNSUPPORTED,
+                    "random forcing exists for Cuspy x {Laplace1d, Quartic1d, no interactions}");
+    }
+    Thermal& T = s->th;
+    T.mean = mean;
+    T.sigma_sqrt2 = stddev * std::sqrt(2.0);
+    TRY(dev_alloc(s, &T.state, (size_t)s->R));
+    TRY(dev_alloc(s, &T.next, (size_t)s->n));
+    {
+        i64* d = nullptr;
+        TRY(dev_alloc(s, &d, (size_t)s->n));
+        T.dinc = d;
+        CU(cudaMemcpyAsync(d, dinc, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice, s->stream));
+    }
+    TRY(dev_alloc(s, &T.f_ext, (size_t)s->n));
+    TRY(dev_alloc(s, &T.f_sys, (size_t)s->n));
+    std::vector<u64> st((size_t)s->R);
+    const u64 stride = seed_forcing_stride > 0 ? (u64)seed_forcing_stride : 1ULL;
+    for (i64 r = 0; r < s->R; ++r) { // m_rng.seed(seed): prrng's default initseq
+        st[(size_t)r] = pcg_seed_seq(seed_forcing + (u64)r * stride, FQSB_PCG_DEFAULT_INITSEQ,
+                                     &T.inc_rng);
+    }
+    CU(cudaMemcpyAsync(T.state, st.data(), (size_t)s->R * sizeof(u64), cudaMemcpyHostToDevice,
+                       s->stream));
+    CU(cudaMemcpyAsync(T.next, dinc_init, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
+                       s->stream));
+    CU(cudaMemsetAsync(T.f_ext, 0, (size_t)s->n * sizeof(double), s->stream));
+    CU(cudaMemsetAsync(T.f_sys, 0, (size_t)s->n * sizeof(double), s->stream));
+    s->S.f_thermal = T.f_sys;
+    s->P.thermal = 1;
+    s->thermal = true;
+    TRY(thermal_update(s, 0, 0)); // initSystem -> refresh() -> updated_inc(), detail.h:1138
+    invalidate_forces(s);
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+static int require_thermal(const fqsb_system* s, int64_t n, bool per_block)
+{
+    if (!s->thermal) {
+        return fail(FQSB_EASSERT, "not a RandomForcing system");
+    }
+    if (per_block && n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(arg, m_f_thermal.shape())"));
+    }
+    return FQSB_OK;
+}
+
+int fqsb_external_get_f_thermal(fqsb_system* s, double* out, int64_t n) // detail.h:967-970
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, n, true));
+    CU(cudaMemcpyAsync(out, s->th.f_ext, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_external_set_f_thermal(fqsb_system* s, const double* f, int64_t n) // detail.h:976-980
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, n, true));
+    CU(cudaMemcpyAsync(s->th.f_ext, f, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_external_get_next(fqsb_system* s, int64_t* out, int64_t n) // detail.h:986-989
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, n, true));
+    CU(cudaMemcpyAsync(out, s->th.next, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_external_set_next(fqsb_system* s, const int64_t* next, int64_t n) // detail.h:995-999
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, n, true));
+    CU(cudaMemcpyAsync(s->th.next, next, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_external_get_state(fqsb_system* s, uint64_t* out) // [R] detail.h:949-952
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, 0, false));
+    CU(cudaMemcpyAsync(out, s->th.state, (size_t)s->R * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return FQSB_OK;
+}
+
+int fqsb_external_set_state(fqsb_system* s, const uint64_t* state) // [R] detail.h:958-961
+{
+    TRY(enter(s));
+    TRY(require_thermal(s, 0, false));
+    CU(cudaMemcpyAsync(s->th.state, state, (size_t)s->R * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
     return FQSB_OK;
 }
 

@@ -66,6 +66,76 @@ __global__ void k_stream_settle_flags(const Par P, const State S)
 }
 
 // =============================================================================================
+// External = RandomNormalForcing: updated_inc() (detail.h:1369-1375 -> 931-943). Block p is
+// redrawn when inc >= next[p]; the k-th due block (in block order) takes the k-th next draw of
+// the realisation's single pcg32 stream. One CTA per realisation: ordered compaction (ballot +
+// scan of the warp counts) gives every due block its rank, an O(log rank) LCG jump gives it its
+// generator state; the stream then advances by the number of draws. `inc_add` = 1 when called
+// ahead of a time step (m_inc++ comes first, detail.h:1541-1544), 0 for refresh()/set_inc();
+// `only_running`: skip realisations whose stepping call has already ended.
+// normal(mu, sigma) = mu + sigma*sqrt(2)*erf_inv(2r - 1), r = next_double() (prrng; the device
+// uses CUDA's erfinv, <= 5 ulp from boost's long-double evaluation).
+// =============================================================================================
+__global__ void __launch_bounds__(1024) k_thermal_draw(const Par P, const State S, const Thermal T,
+                                                       int inc_add, int only_running)
+{
+    __shared__ int wcount[32];
+    __shared__ int wexcl[33];
+    const int r = blockIdx.x;
+    const Ctl& ctl = S.ctl[r];
+    if (only_running && ctl.status != ST_RUNNING) {
+        return;
+    }
+    const i64 inc = ctl.inc + inc_add;
+    const i64 base = (i64)r * P.N;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const u64 st0 = T.state[r];
+    u64 carry = 0;
+    for (i64 p0 = 0; p0 < P.N; p0 += blockDim.x) {
+        const i64 p = p0 + t;
+        const bool due = p < P.N && inc >= T.next[base + p];
+        const unsigned bal = __ballot_sync(0xffffffffu, due);
+        if (lane == 0) {
+            wcount[warp] = __popc(bal);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int c = lane < (int)(blockDim.x >> 5) ? wcount[lane] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) {
+                    incl += y;
+                }
+            }
+            wexcl[lane] = incl - c;
+            if (lane == 31) {
+                wexcl[32] = incl;
+            }
+        }
+        __syncthreads();
+        if (p < P.N) {
+            double val = T.f_ext[base + p];
+            if (due) {
+                const u64 rank = carry + (u64)wexcl[warp] + (u64)__popc(bal & ((1u << lane) - 1u));
+                const u64 st = pcg_advance_inc(st0, rank, T.inc_rng);
+                const double z = pcg_double(st);
+                val = T.mean + T.sigma_sqrt2 * erfinv(2.0 * z - 1.0);
+                T.f_ext[base + p] = val;
+                T.next[base + p] += T.dinc[base + p];
+            }
+            T.f_sys[base + p] = val; // std::copy(m_f_thermal..., f), detail.h:942
+        }
+        carry += (u64)wexcl[32];
+        __syncthreads();
+    }
+    if (t == 0 && carry) {
+        T.state[r] = pcg_advance_inc(st0, carry, T.inc_rng);
+    }
+}
+
+// =============================================================================================
 // construction, alignment, forces, reductions, chunk views
 // =============================================================================================
 
@@ -168,7 +238,12 @@ __global__ void k_forces(const Par P, const State S, const ForceArrays F, int ma
         if (mask & 8) {
             F.f_damp[g] = -P.eta * S.v[g];
         }
-        F.f[g] = F.f_frame[g] + F.f_pot[g] + F.f_int[g] + F.f_damp[g];
+        if (S.f_thermal) { // detail.h:1326-1329
+            F.f[g] = F.f_frame[g] + F.f_pot[g] + F.f_int[g] + F.f_damp[g] + S.f_thermal[g];
+        }
+        else {
+            F.f[g] = F.f_frame[g] + F.f_pot[g] + F.f_int[g] + F.f_damp[g];
+        }
     }
 }
 
@@ -210,6 +285,9 @@ __global__ void __launch_bounds__(256) k_reduce(const Par P, const State S, cons
             double fp = f_potential_rt(P, uc, S.yl[g], S.yr[g]);
             double ff = P.k_frame * (uf - uc);
             double f = ff + fp + fi + (-P.eta * S.v[g]);
+            if (S.f_thermal) {
+                f += S.f_thermal[g];
+            }
             acc[0] += f * f;
             acc[1] += ff * ff;
         }

@@ -23,7 +23,7 @@ struct Par {
     int pot, inter, rank, dist;
     int rows, cols;
     int consumes; // distribution consumes pcg32 draws (everything but delta)
-    int pad0;
+    int thermal;  // External = RandomNormalForcing (detail.h:881-1000): State::f_thermal is set
     i64 N; // blocks per realisation
     i64 R; // realisations
     double m, inv_m, eta, mu, kappa, k1, k2, k_frame, dt;
@@ -104,6 +104,21 @@ struct State {
     const double* pref;   // LongRange prefactor table [N] (detail.h:829-844)
     double* part;         // streaming path: per-CTA partial sums
     int tiles;            // streaming path: CTAs per realisation
+    const double* f_thermal; // System::m_f_thermal [R*N] (detail.h:1057), nullptr if athermal
+};
+
+// ---- External = RandomNormalForcing (detail.h:881-1000) ----------------------------------------
+// One sequential prrng::pcg32 stream per realisation (m_rng.seed(seed_forcing): prrng's default
+// initseq), consumed in block order by the blocks whose `next` increment has come.
+#define FQSB_PCG_DEFAULT_INITSEQ 0xda3e39cb94b95bdbULL
+struct Thermal {
+    double mean, sigma_sqrt2; // normal(mu, sigma) = mu + sigma*sqrt(2) * erf_inv(2r - 1)
+    u64 inc_rng;              // (initseq << 1) | 1
+    u64* state;               // [R] m_rng state
+    i64* next;                // [R*N] m_next
+    const i64* dinc;          // [R*N] m_dinc
+    double* f_ext;            // [R*N] RandomNormalForcing::m_f_thermal
+    double* f_sys;            // [R*N] System::m_f_thermal (the copy made by updated_inc)
 };
 
 // ---- K2b (fqsb_blocked.cuh): temporally blocked tiles of a long 1-D line ----------------------
@@ -176,6 +191,33 @@ __host__ __device__ inline u64 pcg_advance(u64 s, i64 distance)
         delta >>= 1ULL;
     }
     return acc_mult * s + acc_plus;
+}
+
+// the same jump for a stream with an arbitrary increment (the thermal forcing stream)
+__host__ __device__ inline u64 pcg_advance_inc(u64 s, u64 delta, u64 inc)
+{
+    u64 cur_mult = FQSB_PCG_MULT, cur_plus = inc, acc_mult = 1ULL, acc_plus = 0ULL;
+    while (delta > 0) {
+        if (delta & 1ULL) {
+            acc_mult *= cur_mult;
+            acc_plus = acc_plus * cur_mult + cur_plus;
+        }
+        cur_plus = (cur_mult + 1ULL) * cur_plus;
+        cur_mult *= cur_mult;
+        delta >>= 1ULL;
+    }
+    return acc_mult * s + acc_plus;
+}
+
+__host__ __device__ inline u64 pcg_seed_seq(u64 initstate, u64 initseq, u64* inc_out)
+{
+    const u64 inc = (initseq << 1u) | 1u;
+    u64 s = 0ULL;
+    s = s * FQSB_PCG_MULT + inc;
+    s += initstate;
+    s = s * FQSB_PCG_MULT + inc;
+    *inc_out = inc;
+    return s;
 }
 
 // ---- distributions -> yield spacing ------------------------------------
@@ -420,6 +462,28 @@ __device__ __forceinline__ double verlet_tail(const Par& P, double F, double& v,
     vv = vn + hdt * (an + aa);          // 1562
     f = F + meta * vv;                  // 1563
     aa = UNIT ? f : f * P.inv_m;        // 1565
+    v = vv;
+    a = aa;
+    return f;
+}
+
+// the same with External = RandomNormalForcing: f = f_frame + f_pot + f_int + f_damp + f_thermal
+// (detail.h:1326-1329, left to right)
+__device__ __forceinline__ double verlet_tail_thermal(const Par& P, double F, double fth, double& v,
+                                                      double& a)
+{
+    const double vn = v, an = a;
+    const double hdt = 0.5 * P.dt;
+    const double meta = -P.eta;
+    double vv = vn + P.dt * an;
+    double f = (F + meta * vv) + fth;
+    double aa = f * P.inv_m;
+    vv = vn + hdt * (an + aa);
+    f = (F + meta * vv) + fth;
+    aa = f * P.inv_m;
+    vv = vn + hdt * (an + aa);
+    f = (F + meta * vv) + fth;
+    aa = f * P.inv_m;
     v = vv;
     a = aa;
     return f;

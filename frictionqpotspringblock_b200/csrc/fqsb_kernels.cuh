@@ -1092,7 +1092,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
 
 // ---- generic fallback (2-D stencils, LongRange, odd N): one block per thread, neighbours'
 //      new positions recomputed from global memory (served by L1/L2)
-template <int POT, int INT>
+template <int POT, int INT, bool THERMAL = false>
 __global__ void __launch_bounds__(256)
     k_stream_step(const __grid_constant__ Par P, const __grid_constant__ State S,
                   const __grid_constant__ RunArgs A, const int flip, const int finalise)
@@ -1149,7 +1149,8 @@ __global__ void __launch_bounds__(256)
         double ff = P.k_frame * (uf - un);
         double F = ff + fp + fi;
         double v = vi[p], a = ai[p];
-        double f = verlet_tail(P, F, v, a);
+        double f = THERMAL ? verlet_tail_thermal(P, F, S.f_thermal[base + p], v, a)
+                           : verlet_tail(P, F, v, a);
         uo[p] = un;
         vo[p] = v;
         ao[p] = a;

@@ -53,9 +53,13 @@ cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
 }
 
 // tiles per realisation of the step kernel that launch_stream_step() picks
-static bool use_tiled_1d(const Par& P) { return P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0; }
+// (thermal systems -- External = RandomNormalForcing -- take the generic kernel)
+static bool use_tiled_1d(const Par& P)
+{
+    return !P.thermal && P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0;
+}
 
-static bool use_tiled_2d(const Par& P) { return P.rank == 2 && P.cols % 2 == 0; }
+static bool use_tiled_2d(const Par& P) { return !P.thermal && P.rank == 2 && P.cols % 2 == 0; }
 
 int stream_step_tiles(const Par& P, int generic_tiles)
 {
@@ -114,6 +118,21 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
         return cudaGetLastError();
     }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
+    if (P.thermal) { // Line1d.h:261-330, 486-556; Particles.h System_Cuspy_RandomForcing
+        switch (combo_of(P.pot, P.inter)) {
+        case 0:
+            k_stream_step<POT_CUSPY, INT_LAPLACE1D, true><<<grid, 256, 0, stream>>>(P, S, A, flip, finalise);
+            break;
+        case 1:
+            k_stream_step<POT_CUSPY, INT_QUARTIC1D, true><<<grid, 256, 0, stream>>>(P, S, A, flip, finalise);
+            break;
+        case 8:
+            k_stream_step<POT_CUSPY, INT_NONE, true><<<grid, 256, 0, stream>>>(P, S, A, flip, finalise);
+            break;
+        default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
 #define FQSB_STREAM(pot, inter) \
     k_stream_step<pot, inter><<<grid, 256, 0, stream>>>(P, S, A, flip, finalise); \
     break;

@@ -119,6 +119,14 @@ void mySystemNdDynamics(Binder& cls) // main.cpp:211-226
     cls.def("flowSteps", &System::flowSteps, py::arg("n"), py::arg("v_frame"));
 }
 
+template <class Binder, class S>
+void mySystemNdExternal(Binder& cls) // main.cpp:205-209
+{
+    cls.def_property_readonly(
+        "external", [](S& s) -> M::detail::RandomNormalForcing& { return s.external(); },
+        py::return_value_policy::reference_internal, "Class adding external force");
+}
+
 // constructor argument lists of main.cpp:493-520 etc.
 #define FQSB_COMMON_ARGS \
     py::arg("shape"), py::arg("seed"), py::arg("distribution"), py::arg("parameters"), \
@@ -132,6 +140,36 @@ PYBIND11_MODULE(_FrictionQPotSpringBlock, m)
     py::class_<System> base(m, "System");
     mySystemNd(base);
     mySystemNdAthermal(base);
+
+    { // main.cpp:246-276
+        py::module sm = m.def_submodule("detail", "detail");
+        using S = M::detail::RandomNormalForcing;
+        py::class_<S> cls(sm, "RandomNormalForcing_1");
+        cls.def_property("state", &S::state, &S::set_state, "State of RNG");
+        cls.def_property(
+            "f_thermal",
+            [](const S& s) {
+                const auto& v = s.f_thermal();
+                return py::array_t<double>(static_cast<py::ssize_t>(v.size()), v.data());
+            },
+            [](S& s, const py::array_t<double, py::array::c_style | py::array::forcecast>& a) {
+                s.set_f_thermal(as_vector(a));
+            },
+            "Random force");
+        cls.def_property(
+            "next",
+            [](const S& s) {
+                const auto& v = s.next();
+                return py::array_t<int64_t>(static_cast<py::ssize_t>(v.size()), v.data());
+            },
+            [](S& s, const py::array_t<int64_t, py::array::c_style | py::array::forcecast>& a) {
+                s.set_next(std::vector<int64_t>(a.data(), a.data() + a.size()));
+            },
+            "Next draw increment");
+        cls.def("__repr__", [](const S&) {
+            return "<FrictionQPotSpringBlock.detail.RandomNormalForcing_1>";
+        });
+    }
 
     {
         py::module sm = m.def_submodule("Line1d", "Line1d");
@@ -188,6 +226,31 @@ PYBIND11_MODULE(_FrictionQPotSpringBlock, m)
                     py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k2"), py::arg("k4"),
                     py::arg("k_frame"), py::arg("dt"), FQSB_COMMON_ARGS);
             mySystemNdDynamics(cls);
+        }
+        using Inc = const std::vector<int64_t>&;
+        { // main.cpp:570-622
+            using S = SM::System_Cuspy_Laplace_RandomForcing;
+            py::class_<S, System> cls(sm, "System_Cuspy_Laplace_RandomForcing");
+            cls.def(py::init<double, double, double, double, double, double, double, double,
+                             uint64_t, Inc, Inc, S1, uint64_t, Str, Par, double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k_interactions"),
+                    py::arg("k_frame"), py::arg("dt"), py::arg("mean"), py::arg("stddev"),
+                    py::arg("seed_forcing"), py::arg("dinc_init"), py::arg("dinc"),
+                    FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+            mySystemNdExternal<decltype(cls), S>(cls);
+        }
+        { // main.cpp:623-677
+            using S = SM::System_Cuspy_Quartic_RandomForcing;
+            py::class_<S, System> cls(sm, "System_Cuspy_Quartic_RandomForcing");
+            cls.def(py::init<double, double, double, double, double, double, double, double,
+                             double, uint64_t, Inc, Inc, S1, uint64_t, Str, Par, double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("a1"), py::arg("a2"),
+                    py::arg("k_frame"), py::arg("dt"), py::arg("mean"), py::arg("stddev"),
+                    py::arg("seed_forcing"), py::arg("dinc_init"), py::arg("dinc"),
+                    FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+            mySystemNdExternal<decltype(cls), S>(cls);
         }
         {
             py::class_<SM::System_Cuspy_LongRange, System> cls(sm, "System_Cuspy_LongRange");

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQSB_ABI_VERSION 2
+#define FQSB_ABI_VERSION 3
 
 typedef enum {
     FQSB_OK = 0,
@@ -59,7 +59,11 @@ typedef enum {
 } fqsb_interactions;
 
 /* ref: detail.h:1005-1020 (Overdamped = the "minimise_nopassing" of older releases) */
-typedef enum { FQSB_MIN_DYNAMIC = 0, FQSB_MIN_OVERDAMPED = 1 } fqsb_minimisation;
+typedef enum {
+    FQSB_MIN_DYNAMIC = 0,
+    FQSB_MIN_OVERDAMPED = 1,
+    FQSB_MIN_NONE = 2 /* thermal systems: minimise throws, ref: detail.h:1691-1693 */
+} fqsb_minimisation;
 
 /* ref: detail.h:31-66 (prrng::distribution) */
 typedef enum {
@@ -196,6 +200,26 @@ int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* valu
 /* signed well-index change since `i_n` summed per realisation (the examples' S) and the number
  * of blocks that changed (A): out_S [R], out_A [R] (either may be NULL) */
 int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A);
+
+/* thermal systems: External = RandomNormalForcing (ref: detail.h:881-1000; classes
+ * Line1d.h:261-330 System_Cuspy_Laplace_RandomForcing, Line1d.h:486-556
+ * System_Cuspy_Quartic_RandomForcing, Particles.h System_Cuspy_RandomForcing) ------------------
+ * Call once, right after fqsb_create (params.minimisation = FQSB_MIN_NONE): every block gets a
+ * force drawn from normal(mean, stddev) that is redrawn whenever inc >= next[p] (next starts at
+ * dinc_init[p] and then advances by dinc[p]); the draws of one realisation come, in block order,
+ * from ONE sequential prrng::pcg32(seed_forcing + r*seed_forcing_stride) stream (stride 0 is read
+ * as 1). dinc_init, dinc: [R*size]. The residual becomes f_frame + f_potential + f_interactions +
+ * f_damping + f_thermal (ref: detail.h:1326-1329). */
+int fqsb_enable_random_forcing(fqsb_system* s, double mean, double stddev, uint64_t seed_forcing,
+                               int64_t seed_forcing_stride, const int64_t* dinc_init,
+                               const int64_t* dinc, int64_t n);
+/* `system.external` (ref: python/main.cpp:250-275) */
+int fqsb_external_get_f_thermal(fqsb_system* s, double* out, int64_t n);      /* ref: 967-970 */
+int fqsb_external_set_f_thermal(fqsb_system* s, const double* f, int64_t n);  /* ref: 976-980 */
+int fqsb_external_get_next(fqsb_system* s, int64_t* out, int64_t n);          /* ref: 986-989 */
+int fqsb_external_set_next(fqsb_system* s, const int64_t* next, int64_t n);   /* ref: 995-999 */
+int fqsb_external_get_state(fqsb_system* s, uint64_t* out);                   /* [R] ref: 949-952 */
+int fqsb_external_set_state(fqsb_system* s, const uint64_t* state);           /* [R] ref: 958-961 */
 
 /* slab decomposition primitives (new surface; one very large line / interface over several GPUs,
  * driven by frictionqpotspringblock_b200/slab.py) ----------------------- */

@@ -48,6 +48,48 @@ inline void check(int rc)
     }
 }
 
+/** detail::RandomNormalForcing<1> (detail.h:881-1000) as seen through `system.external()`:
+ *  a view on the forcing state that lives on the device next to the system. */
+class RandomNormalForcing {
+    fqsb_system* m_h = nullptr;
+    mutable std::vector<double> m_f_thermal;
+    mutable std::vector<int64_t> m_next;
+
+public:
+    RandomNormalForcing() = default;
+    explicit RandomNormalForcing(fqsb_system* h) : m_h(h) {}
+
+    uint64_t state() const // detail.h:949-952
+    {
+        uint64_t x;
+        check(fqsb_external_get_state(m_h, &x));
+        return x;
+    }
+    void set_state(uint64_t state) { check(fqsb_external_set_state(m_h, &state)); } // 958-961
+    const std::vector<double>& f_thermal() const // detail.h:967-970
+    {
+        m_f_thermal.resize(static_cast<size_t>(fqsb_size(m_h)));
+        check(fqsb_external_get_f_thermal(m_h, m_f_thermal.data(),
+                                          static_cast<int64_t>(m_f_thermal.size())));
+        return m_f_thermal;
+    }
+    void set_f_thermal(const std::vector<double>& f_thermal) // detail.h:976-980
+    {
+        check(fqsb_external_set_f_thermal(m_h, f_thermal.data(),
+                                          static_cast<int64_t>(f_thermal.size())));
+    }
+    const std::vector<int64_t>& next() const // detail.h:986-989
+    {
+        m_next.resize(static_cast<size_t>(fqsb_size(m_h)));
+        check(fqsb_external_get_next(m_h, m_next.data(), static_cast<int64_t>(m_next.size())));
+        return m_next;
+    }
+    void set_next(const std::vector<int64_t>& next) // detail.h:995-999
+    {
+        check(fqsb_external_set_next(m_h, next.data(), static_cast<int64_t>(next.size())));
+    }
+};
+
 /** detail::System (detail.h:1046-2051) for one realisation, all work on the GPU. */
 class System {
 protected:
@@ -92,6 +134,20 @@ protected:
         m_par.kernel = 0;
         check(fqsb_create(&m_par, &m_h));
     }
+
+    // External = RandomNormalForcing (Line1d.h:316-318), before initSystem's refresh()
+    void initForcing(double mean, double stddev, uint64_t seed_forcing,
+                     const std::vector<int64_t>& dinc_init, const std::vector<int64_t>& dinc)
+    {
+        if (dinc_init.size() != dinc.size()) {
+            throw std::runtime_error("assertion failed (xt::has_shape(dinc_init, dinc.shape()))");
+        }
+        check(fqsb_enable_random_forcing(m_h, mean, stddev, seed_forcing, 1, dinc_init.data(),
+                                         dinc.data(), static_cast<int64_t>(dinc.size())));
+        m_external = RandomNormalForcing(m_h);
+    }
+
+    RandomNormalForcing m_external;
 
     const std::vector<double>& array(int which) const
     {
@@ -343,6 +399,60 @@ public:
                    0.0, a1, a2, k_frame, dt, seed, distribution, parameters, offset, nchunk);
     }
 };
+
+/** Thermal systems hide the athermal protocol (Line1d.h:321-329) */
+#define FQSB_HIDE_ATHERMAL \
+protected: \
+    using detail::System::eventDrivenStep; \
+    using detail::System::quasistaticActivityFirst; \
+    using detail::System::quasistaticActivityLast;
+
+/** Line1d.h:261-330 */
+class System_Cuspy_Laplace_RandomForcing : public detail::System {
+public:
+    System_Cuspy_Laplace_RandomForcing(double m, double eta, double mu, double k_interactions,
+                                       double k_frame, double dt, double mean, double stddev,
+                                       uint64_t seed_forcing,
+                                       const std::vector<int64_t>& dinc_init,
+                                       const std::vector<int64_t>& dinc,
+                                       const std::array<size_t, 1>& shape, uint64_t seed,
+                                       const std::string& distribution,
+                                       const std::vector<double>& parameters,
+                                       double offset = -100.0, size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_CUSPY, FQSB_INT_LAPLACE1D, FQSB_MIN_NONE, FQSB_SHAPE1, m, eta, mu, 0.0,
+                   k_interactions, 0.0, k_frame, dt, seed, distribution, parameters, offset,
+                   nchunk);
+        initForcing(mean, stddev, seed_forcing, dinc_init, dinc);
+    }
+    const detail::RandomNormalForcing& external() const { return m_external; } // detail.h:1218
+    detail::RandomNormalForcing& external() { return m_external; }
+    FQSB_HIDE_ATHERMAL
+};
+
+/** Line1d.h:486-556 */
+class System_Cuspy_Quartic_RandomForcing : public detail::System {
+public:
+    System_Cuspy_Quartic_RandomForcing(double m, double eta, double mu, double a1, double a2,
+                                       double k_frame, double dt, double mean, double stddev,
+                                       uint64_t seed_forcing,
+                                       const std::vector<int64_t>& dinc_init,
+                                       const std::vector<int64_t>& dinc,
+                                       const std::array<size_t, 1>& shape, uint64_t seed,
+                                       const std::string& distribution,
+                                       const std::vector<double>& parameters,
+                                       double offset = -100.0, size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_CUSPY, FQSB_INT_QUARTIC1D, FQSB_MIN_NONE, FQSB_SHAPE1, m, eta, mu, 0.0,
+                   a1, a2, k_frame, dt, seed, distribution, parameters, offset, nchunk);
+        initForcing(mean, stddev, seed_forcing, dinc_init, dinc);
+    }
+    const detail::RandomNormalForcing& external() const { return m_external; }
+    detail::RandomNormalForcing& external() { return m_external; }
+    FQSB_HIDE_ATHERMAL
+};
+
+#undef FQSB_HIDE_ATHERMAL
 
 /** Line1d.h:562-614 */
 class System_Cuspy_QuarticGradient : public detail::System {

@@ -166,6 +166,13 @@ struct orc_system {
     int64_t inc, qs_first, qs_last;
     double u_frame, inv_m;
     int err; /* sticky landscape error */
+    /* External = RandomNormalForcing<rank> (detail.h:881-1000); thermal == 0: External = void */
+    int thermal;
+    double th_mean, th_stddev;
+    uint64_t th_state, th_inc; /* prrng::pcg32 m_rng */
+    int64_t *th_next, *th_dinc;
+    double *th_f_ext; /* RandomNormalForcing::m_f_thermal */
+    double *f_thermal; /* System::m_f_thermal (copy made by updated_inc) */
 };
 
 static inline double blk_draw_fwd(const orc_system* s, uint64_t* st)
@@ -457,6 +464,12 @@ static void force_interactions(orc_system* s)
 /* detail.h:1321-1395 */
 static void compute_force(orc_system* s)
 {
+    if (s->thermal) { /* detail.h:1326-1329 */
+        for (int64_t p = 0; p < s->N; ++p) {
+            s->f[p] = s->f_frame[p] + s->f_pot[p] + s->f_int[p] + s->f_damp[p] + s->f_thermal[p];
+        }
+        return;
+    }
     for (int64_t p = 0; p < s->N; ++p) {
         s->f[p] = s->f_frame[p] + s->f_pot[p] + s->f_int[p] + s->f_damp[p];
     }
@@ -488,6 +501,101 @@ static void updated_u(orc_system* s)
 static void updated_v(orc_system* s)
 {
     compute_force_damping(s);
+    compute_force(s);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * RandomNormalForcing (detail.h:881-1000) on top of prrng::pcg32::normal, whose source is
+ * absent: normal(mu, sigma) = mu + sigma*sqrt(2) * erf_inv(2 r - 1), r = next_double(), with
+ * boost::math::erf_inv evaluated under boost's default policy (double promoted to long double).
+ * Restated as: solve erf(x) = z in 80-bit long double by Halley iterations on glibc's erfl /
+ * erfcl (accurate to ~1 ulp of the 64-bit mantissa), then round to double. Both are correctly
+ * rounded except when the exact value lies within ~2^-10 ulp of a rounding boundary.
+ * Pinned on examples/Line1d_System_Cuspy_Laplace_RandomForcing.h5 (5e6 draws).
+ * ---------------------------------------------------------------------------------------- */
+static double erf_inv_ld(double zd)
+{
+    if (zd == 0.0) {
+        return 0.0;
+    }
+    if (zd <= -1.0) {
+        return -INFINITY;
+    }
+    if (zd >= 1.0) {
+        return INFINITY;
+    }
+    const long double z = fabsl((long double)zd);
+    const long double q = 1.0L - z; /* exact: z is a double in (0, 1) */
+    const long double two_over_sqrtpi = 1.1283791670955125738961589031215452L;
+    /* starting point (Winitzki's approximation), good to ~2e-3 relative */
+    const long double a = 0.147L;
+    const long double ln = logl((1.0L - z) * (1.0L + z));
+    const long double t = 2.0L / (3.14159265358979323846264338327950288L * a) + 0.5L * ln;
+    long double x = sqrtl(sqrtl(t * t - ln / a) - t);
+    for (int it = 0; it < 6; ++it) {
+        /* residual in the better conditioned of the two forms */
+        long double r = (z < 0.5L) ? (erfl(x) - z) : (q - erfcl(x));
+        long double d = two_over_sqrtpi * expl(-x * x);
+        long double step = r / d;
+        step = step / (1.0L + x * step); /* Halley: f''/f' = -2x */
+        x -= step;
+        if (fabsl(step) < 1e-21L * x) {
+            break;
+        }
+    }
+    return (double)(zd < 0.0 ? -x : x);
+}
+
+static double pcg_normal(uint64_t* st, uint64_t inc, double mean, double stddev)
+{
+    double r = pcg_double_from_state(*st);
+    *st = pcg_next(*st, inc);
+    return mean + (stddev * sqrt(2.0)) * erf_inv_ld(2.0 * r - 1.0);
+}
+
+void orc_pcg32_normal(uint64_t initstate, uint64_t initseq, int64_t n, double mean,
+                      double stddev, double* out)
+{
+    uint64_t inc;
+    uint64_t s = pcg_seed(initstate, initseq, &inc);
+    for (int64_t k = 0; k < n; ++k) {
+        out[k] = pcg_normal(&s, inc, mean, stddev);
+    }
+}
+
+/* prrng::pcg32::randint(shape, high): unbiased bounded draw (pcg32 `boundedrand`) */
+void orc_pcg32_randint(uint64_t initstate, uint64_t initseq, int64_t n, uint32_t high,
+                       int64_t* out)
+{
+    uint64_t inc;
+    uint64_t s = pcg_seed(initstate, initseq, &inc);
+    const uint32_t threshold = (~high + 1u) % high;
+    for (int64_t k = 0; k < n; ++k) {
+        for (;;) {
+            uint32_t r = pcg_output(s);
+            s = pcg_next(s, inc);
+            if (r >= threshold) {
+                out[k] = (int64_t)(r % high);
+                break;
+            }
+        }
+    }
+}
+
+double orc_erf_inv(double z) { return erf_inv_ld(z); }
+
+/* detail.h:1369-1375 + 931-943 */
+static void updated_inc(orc_system* s)
+{
+    if (s->thermal) {
+        for (int64_t p = 0; p < s->N; ++p) {
+            if (s->inc >= s->th_next[p]) {
+                s->th_f_ext[p] = pcg_normal(&s->th_state, s->th_inc, s->th_mean, s->th_stddev);
+                s->th_next[p] += s->th_dinc[p];
+            }
+        }
+        memcpy(s->f_thermal, s->th_f_ext, (size_t)s->N * sizeof(double));
+    }
     compute_force(s);
 }
 
@@ -582,7 +690,72 @@ void orc_destroy(orc_system* s)
     free(s->f_frame);
     free(s->f_damp);
     free(s->pref);
+    free(s->th_next);
+    free(s->th_dinc);
+    free(s->th_f_ext);
+    free(s->f_thermal);
     free(s);
+}
+
+/* Line1d.h:293-319 (System_Cuspy_Laplace_RandomForcing) and siblings: the athermal system plus
+ * External = RandomNormalForcing; initSystem's refresh() already draws for dinc_init <= 0. */
+int orc_create_thermal(const orc_params* par, double mean, double stddev, uint64_t seed_forcing,
+                       const int64_t* dinc_init, const int64_t* dinc, orc_system** out)
+{
+    int rc = orc_create(par, out);
+    if (rc) {
+        return rc;
+    }
+    orc_system* s = *out;
+    const size_t N = (size_t)s->N;
+    s->thermal = 1;
+    s->th_mean = mean;
+    s->th_stddev = stddev;
+    /* m_rng.seed(seed): initseq = prrng's default stream */
+    s->th_state = pcg_seed(seed_forcing, 0xda3e39cb94b95bdbULL, &s->th_inc);
+    s->th_next = (int64_t*)malloc(N * sizeof(int64_t));
+    s->th_dinc = (int64_t*)malloc(N * sizeof(int64_t));
+    memcpy(s->th_next, dinc_init, N * sizeof(int64_t));
+    memcpy(s->th_dinc, dinc, N * sizeof(int64_t));
+    s->th_f_ext = (double*)calloc(N, sizeof(double));
+    s->f_thermal = (double*)calloc(N, sizeof(double));
+    updated_inc(s);
+    return ORC_OK;
+}
+
+int orc_thermal_get(const orc_system* s, double* f_thermal, int64_t* next, uint64_t* state)
+{
+    if (!s->thermal) {
+        return fail(ORC_EASSERT, "not a RandomForcing system");
+    }
+    if (f_thermal) {
+        memcpy(f_thermal, s->th_f_ext, (size_t)s->N * sizeof(double));
+    }
+    if (next) {
+        memcpy(next, s->th_next, (size_t)s->N * sizeof(int64_t));
+    }
+    if (state) {
+        *state = s->th_state;
+    }
+    return ORC_OK;
+}
+
+int orc_thermal_set(orc_system* s, const double* f_thermal, const int64_t* next,
+                    const uint64_t* state)
+{
+    if (!s->thermal) {
+        return fail(ORC_EASSERT, "not a RandomForcing system");
+    }
+    if (f_thermal) {
+        memcpy(s->th_f_ext, f_thermal, (size_t)s->N * sizeof(double));
+    }
+    if (next) {
+        memcpy(s->th_next, next, (size_t)s->N * sizeof(int64_t));
+    }
+    if (state) {
+        s->th_state = *state;
+    }
+    return ORC_OK;
 }
 
 int64_t orc_size(const orc_system* s) { return s->N; }
@@ -632,7 +805,7 @@ int orc_set_inc(orc_system* s, int64_t inc) /* detail.h:1241-1247 */
     s->inc = inc;
     s->qs_first = inc;
     s->qs_last = inc;
-    compute_force(s);
+    updated_inc(s);
     return ORC_OK;
 }
 
@@ -650,7 +823,7 @@ int orc_refresh(orc_system* s) /* detail.h:1310-1315 */
 {
     updated_u(s);
     updated_v(s);
-    compute_force(s);
+    updated_inc(s);
     return check_landscape(s);
 }
 
@@ -665,6 +838,10 @@ int orc_quench(orc_system* s) /* detail.h:1527-1532 */
 int orc_get(const orc_system* s, int which, double* out)
 {
     const double* src[] = {s->u, s->v, s->a, s->f, s->f_pot, s->f_frame, s->f_int, s->f_damp};
+    if (which == 8 && s->thermal) { /* System::m_f_thermal */
+        memcpy(out, s->f_thermal, (size_t)s->N * sizeof(double));
+        return ORC_OK;
+    }
     if (which < 0 || which > 7) {
         return fail(ORC_EASSERT, "bad array id");
     }
@@ -768,6 +945,9 @@ static int time_step(orc_system* s)
     double *u = s->u, *v = s->v, *a = s->a, *v_n = s->v_n, *a_n = s->a_n, *f = s->f;
 
     s->inc++;
+    if (s->thermal) { /* detail.h:1542-1544 */
+        updated_inc(s);
+    }
     memcpy(v_n, v, (size_t)N * sizeof(double));
     memcpy(a_n, a, (size_t)N * sizeof(double));
 
@@ -970,6 +1150,10 @@ int orc_minimise(orc_system* s, double tol, int64_t niter_tol, int64_t max_iter,
     int64_t step = 0;
     int rc = ORC_OK;
 
+    if (s->par.minimisation == ORC_MIN_NONE) { /* detail.h:1691-1693 */
+        free(res.r);
+        return fail(ORC_EUNSUPPORTED, "Minimisation not implementated");
+    }
     if (s->par.minimisation == ORC_MIN_OVERDAMPED) {
         if (time_activity) {
             free(res.r);

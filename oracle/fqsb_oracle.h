@@ -44,7 +44,7 @@ enum {
     ORC_INT_QUARTICGRADIENT2D = 6
 };
 /* minimisation (detail.h:1005-1020, 1691-1753) */
-enum { ORC_MIN_DYNAMIC = 0, ORC_MIN_OVERDAMPED = 1 };
+enum { ORC_MIN_DYNAMIC = 0, ORC_MIN_OVERDAMPED = 1, ORC_MIN_NONE = 2 };
 /* prrng::distribution (detail.h:31-66) */
 enum {
     ORC_DIST_RANDOM = 0,
@@ -136,7 +136,23 @@ int orc_chunk_state_at(orc_system* s, const int64_t* index, uint64_t* state);
 int orc_chunk_restore(orc_system* s, const uint64_t* state, const double* value,
                       const int64_t* index);
 
+/* External = RandomNormalForcing (detail.h:881-1000; Line1d.h:261-330, 486-556;
+ * Particles.h System_Cuspy_RandomForcing): the system of `par` plus a normally distributed force
+ * per block that is redrawn from ONE sequential pcg32(seed_forcing) stream, in block order,
+ * whenever inc >= next[p] (next starts at dinc_init and advances by dinc[p]). */
+int orc_create_thermal(const orc_params* par, double mean, double stddev, uint64_t seed_forcing,
+                       const int64_t* dinc_init, const int64_t* dinc, orc_system** out);
+/* external.f_thermal / external.next / external.state (python/main.cpp:255-268); NULL = skip */
+int orc_thermal_get(const orc_system* s, double* f_thermal, int64_t* next, uint64_t* state);
+int orc_thermal_set(orc_system* s, const double* f_thermal, const int64_t* next,
+                    const uint64_t* state);
+
 /* free-standing helpers used by the tests */
+void orc_pcg32_normal(uint64_t initstate, uint64_t initseq, int64_t n, double mean,
+                      double stddev, double* out);
+void orc_pcg32_randint(uint64_t initstate, uint64_t initseq, int64_t n, uint32_t high,
+                       int64_t* out);
+double orc_erf_inv(double z);
 void orc_pcg32_draws(uint64_t initstate, uint64_t initseq, int64_t n, double* out);
 double orc_draw_to_spacing(double r, int32_t distribution, const double* par);
 

@@ -125,6 +125,15 @@ def lib():
                      "orc_qs_first", "orc_qs_last"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_create.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_create_thermal.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_uint64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_thermal_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_thermal_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pcg32_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_double, C.c_double,
+                                       C.c_void_p]
+        L.orc_pcg32_randint.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]
+        L.orc_erf_inv.argtypes = [C.c_double]
+        L.orc_erf_inv.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -157,6 +166,23 @@ def make_params(potential, interactions, minimisation, shape, m, eta, mu, kappa,
 def pcg32_draws(initstate: int, n: int, initseq: int = 0) -> np.ndarray:
     out = np.empty(n, dtype=np.float64)
     lib().orc_pcg32_draws(int(initstate), int(initseq), n, out.ctypes.data)
+    return out
+
+
+PCG32_INITSEQ = 0xDA3E39CB94B95BDB  # prrng's default stream (App. A.1)
+
+
+def pcg32_normal(initstate: int, n: int, mean=0.0, stddev=1.0, initseq: int = PCG32_INITSEQ):
+    """prrng.pcg32(initstate).normal([n], mean, stddev)"""
+    out = np.empty(n, dtype=np.float64)
+    lib().orc_pcg32_normal(int(initstate), int(initseq), n, mean, stddev, out.ctypes.data)
+    return out
+
+
+def pcg32_randint(initstate: int, n: int, high: int, initseq: int = PCG32_INITSEQ):
+    """prrng.pcg32(initstate).randint([n], high)"""
+    out = np.empty(n, dtype=np.int64)
+    lib().orc_pcg32_randint(int(initstate), int(initseq), n, int(high), out.ctypes.data)
     return out
 
 
@@ -238,18 +264,72 @@ class _Chunk:
         self._start = index.reshape(self._s.shape).copy()
 
 
+class _External:
+    """detail::RandomNormalForcing as bound by python/main.cpp:250-275."""
+
+    def __init__(self, system):
+        self._s = system
+
+    @property
+    def f_thermal(self):
+        out = np.empty(self._s._shape, dtype=np.float64)
+        self._s._check(lib().orc_thermal_get(self._s._h, out.ctypes.data, None, None))
+        return out
+
+    @f_thermal.setter
+    def f_thermal(self, arg):
+        arg = np.ascontiguousarray(arg, dtype=np.float64)
+        if arg.shape != self._s._shape:
+            raise RuntimeError("assertion failed (xt::has_shape(f_thermal, m_f_thermal.shape()))")
+        self._s._check(lib().orc_thermal_set(self._s._h, arg.ctypes.data, None, None))
+
+    @property
+    def next(self):
+        out = np.empty(self._s._shape, dtype=np.int64)
+        self._s._check(lib().orc_thermal_get(self._s._h, None, out.ctypes.data, None))
+        return out
+
+    @next.setter
+    def next(self, arg):
+        arg = np.ascontiguousarray(arg, dtype=np.int64)
+        if arg.shape != self._s._shape:
+            raise RuntimeError("assertion failed (xt::has_shape(next, m_next.shape()))")
+        self._s._check(lib().orc_thermal_set(self._s._h, None, arg.ctypes.data, None))
+
+    @property
+    def state(self):
+        out = C.c_uint64()
+        self._s._check(lib().orc_thermal_get(self._s._h, None, None, C.byref(out)))
+        return out.value
+
+    @state.setter
+    def state(self, arg):
+        val = C.c_uint64(int(arg))
+        self._s._check(lib().orc_thermal_set(self._s._h, None, None, C.byref(val)))
+
+
 class System:
     """Generic oracle system (detail::System, detail.h:1046-2051)."""
 
     def __init__(self, potential, interactions, shape, *, m=1.0, eta=0.0, mu=1.0, kappa=0.0,
                  k1=0.0, k2=0.0, k_frame=1.0, dt=0.0, seed=0, distribution="random",
-                 parameters=(), offset=-100.0, nchunk=5000, minimisation=0):
+                 parameters=(), offset=-100.0, nchunk=5000, minimisation=0, forcing=None):
         self._par = make_params(potential, interactions, minimisation, shape, m, eta, mu, kappa,
                                 k1, k2, k_frame, dt, seed, distribution, parameters, offset, nchunk)
         self._shape = tuple(int(i) for i in shape)
         self._nchunk = int(nchunk)
         self._h = C.c_void_p()
-        self._check(lib().orc_create(C.byref(self._par), C.byref(self._h)))
+        if forcing is None:
+            self._check(lib().orc_create(C.byref(self._par), C.byref(self._h)))
+        else:  # Line1d.h:293-319: External = RandomNormalForcing
+            mean, stddev, seed_forcing, dinc_init, dinc = forcing
+            dinc_init = np.ascontiguousarray(dinc_init, dtype=np.int64)
+            dinc = np.ascontiguousarray(dinc, dtype=np.int64)
+            assert dinc_init.shape == self._shape and dinc.shape == self._shape
+            self._check(lib().orc_create_thermal(
+                C.byref(self._par), float(mean), float(stddev), int(seed_forcing),
+                dinc_init.ctypes.data, dinc.ctypes.data, C.byref(self._h)))
+            self.external = _External(self)
         self._chunk = _Chunk(self)
 
     def __del__(self):
@@ -372,10 +452,14 @@ Line2d = _Namespace()
 Particles = _Namespace()
 
 
-def _mk(potential, interactions, k1name=None, k2name=None, kappa=False, minimisation=0):
+def _mk(potential, interactions, k1name=None, k2name=None, kappa=False, minimisation=0,
+        forcing=False):
     def ctor(**kw):
         kw = dict(kw)
         com = _common(kw)
+        if forcing:
+            com["forcing"] = (kw.pop("mean"), kw.pop("stddev"), kw.pop("seed_forcing"),
+                              kw.pop("dinc_init"), kw.pop("dinc"))
         k1 = kw.pop(k1name) if k1name else 0.0
         k2 = kw.pop(k2name) if k2name else 0.0
         kap = kw.pop("kappa") if kappa else 0.0
@@ -394,8 +478,14 @@ Line1d.System_Smooth_Laplace = _mk("Smooth", "Laplace1d", "k_interactions")
 Line1d.System_Cuspy_Quartic = _mk("Cuspy", "Quartic1d", "a1", "a2")
 Line1d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient1d", "k2", "k4")
 Line1d.System_Cuspy_LongRange = _mk("Cuspy", "LongRange1d", "k_interactions", "alpha")
+# Line1d.h:261-330, 486-556 (thermal: External = RandomNormalForcing, Minimisation = None)
+Line1d.System_Cuspy_Laplace_RandomForcing = _mk("Cuspy", "Laplace1d", "k_interactions",
+                                                minimisation=2, forcing=True)
+Line1d.System_Cuspy_Quartic_RandomForcing = _mk("Cuspy", "Quartic1d", "a1", "a2",
+                                                minimisation=2, forcing=True)
 # Particles.h:93-135 (no interactions)
 Particles.System_Cuspy = _mk("Cuspy", "None")
+Particles.System_Cuspy_RandomForcing = _mk("Cuspy", "None", minimisation=2, forcing=True)
 # Line2d.h:77-162 (+ the new 2-D no-passing system)
 Line2d.System_Cuspy_Laplace = _mk("Cuspy", "Laplace2d", "k_interactions")
 Line2d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient2d", "k2", "k4")

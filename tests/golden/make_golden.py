@@ -34,7 +34,20 @@ def read(name: str, n: int):
     return x_frame, f_frame, S
 
 
+def read_thermal():
+    """examples/Line1d_System_Cuspy_Laplace_RandomForcing.h5: x_frame, f_frame, t_insta (500)."""
+    buf = (REF / "Line1d_System_Cuspy_Laplace_RandomForcing.h5").read_bytes()
+    assert buf[:8] == b"\x89HDF\r\n\x1a\n"
+    return (np.frombuffer(buf, "<f8", 500, 2048), np.frombuffer(buf, "<f8", 500, 6048),
+            np.frombuffer(buf, "<f8", 500, 10048))
+
+
 if __name__ == "__main__":
+    x_frame, f_frame, t_insta = read_thermal()
+    assert np.allclose(np.diff(x_frame), 5.0) and np.all(t_insta > 0)
+    np.savez_compressed(OUT / "Line1d_System_Cuspy_Laplace_RandomForcing.npz", x_frame=x_frame,
+                        f_frame=f_frame, t_insta=t_insta)
+    print("Line1d_System_Cuspy_Laplace_RandomForcing", 500, "t_insta[-1] =", t_insta[-1])
     for name, n in LAYOUT.items():
         x_frame, f_frame, S = read(name, n)
         assert np.all(np.diff(x_frame) >= 0) and np.all(np.isfinite(f_frame))

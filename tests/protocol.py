@@ -66,3 +66,35 @@ def check(golden, u_frame, f_frame, S):
     assert np.all(S == golden["S"][:n])
     assert np.allclose(u_frame, golden["x_frame"][:n])
     assert np.allclose(f_frame, golden["f_frame"][:n])
+
+
+# ---- thermal example (/root/reference/examples/Line1d_System_Cuspy_Laplace_RandomForcing.py)
+def make_thermal(ns1d, randint, **extra):
+    """The athermal system minimised first, then the thermal system started from its slips.
+    `randint(initstate, n, high)` = prrng.pcg32(initstate).randint([n], high)."""
+    athermal = ns1d.System_Cuspy_Laplace(k_interactions=1.0, **BASE, **extra)
+    athermal.minimise()
+    system = ns1d.System_Cuspy_Laplace_RandomForcing(
+        k_interactions=1.0, mean=0.0, stddev=0.05, seed_forcing=0,
+        dinc_init=randint(0, N, 100), dinc=100 * np.ones(N, dtype=np.int64), **BASE, **extra)
+    system.u = np.copy(athermal.u)
+    return system
+
+
+def run_thermal(system, nout, dinc=1000, delta_gamma=5e-2):
+    ret_u_frame = np.empty([nout], dtype=float)
+    ret_f_frame = np.empty([nout], dtype=float)
+    ret_t_insta = np.empty([nout], dtype=float)
+    for iout in range(nout):
+        system.flowSteps(dinc, delta_gamma)
+        ret_u_frame[iout] = system.u_frame
+        ret_f_frame[iout] = np.mean(system.f_frame)
+        ret_t_insta[iout] = system.temperature
+    return ret_u_frame, ret_f_frame, ret_t_insta
+
+
+def check_thermal(golden, u_frame, f_frame, t_insta):
+    n = len(u_frame)
+    assert np.allclose(u_frame, golden["x_frame"][:n])
+    assert np.allclose(f_frame, golden["f_frame"][:n])
+    assert np.allclose(t_insta, golden["t_insta"][:n])

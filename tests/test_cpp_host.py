@@ -56,8 +56,10 @@ def test_pybind_module_builds_and_refuses_without_gpu():
     assert P.version() == "0.1.0"
     for name in ("System_Cuspy_Laplace", "System_Cuspy_Laplace_Nopassing",
                  "System_SemiSmooth_Laplace", "System_Smooth_Laplace", "System_Cuspy_Quartic",
-                 "System_Cuspy_QuarticGradient", "System_Cuspy_LongRange"):
+                 "System_Cuspy_QuarticGradient", "System_Cuspy_LongRange",
+                 "System_Cuspy_Laplace_RandomForcing", "System_Cuspy_Quartic_RandomForcing"):
         assert hasattr(P.Line1d, name)
+    assert hasattr(P.detail, "RandomNormalForcing_1")
     assert hasattr(P.Line2d, "System_Cuspy_Laplace")
     import frictionqpotspringblock_b200 as F
 
@@ -97,3 +99,26 @@ def test_pybind_module_reproduces_golden(golden_dir):
 
     protocol.check(golden, *protocol.run(Wrapped(), 60))
     del system_proxy
+
+
+@pytest.mark.gpu
+def test_pybind_thermal_system_matches_ctypes_surface():
+    """System_Cuspy_Laplace_RandomForcing through include/fqsb.hpp + pybind == ctypes package."""
+    import frictionqpotspringblock_b200 as F
+
+    P = _pybind()
+    N = 50
+    kw = dict(m=1.0, eta=0.3, mu=1.0, k_interactions=1.0, k_frame=1.0 / N, dt=0.1, mean=0.0,
+              stddev=0.1, seed_forcing=4, dinc_init=np.arange(N) % 5, dinc=3 * np.ones(N, dtype=int),
+              shape=[N], seed=1, distribution="random", parameters=[2.0], offset=-50)
+    a = P.Line1d.System_Cuspy_Laplace_RandomForcing(**kw)
+    b = F.Line1d.System_Cuspy_Laplace_RandomForcing(**kw)
+    for s in (a, b):
+        s.flowSteps(40, 0.1)
+    assert np.array_equal(a.u, b.u) and np.array_equal(a.v, b.v)
+    assert np.array_equal(a.external.f_thermal, b.external.f_thermal)
+    assert np.array_equal(a.external.next, b.external.next)
+    assert a.external.state == b.external.state
+    assert repr(a.external) == "<FrictionQPotSpringBlock.detail.RandomNormalForcing_1>"
+    with pytest.raises(RuntimeError, match="Minimisation not implementated"):
+        a.minimise()
