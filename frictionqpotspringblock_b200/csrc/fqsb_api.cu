@@ -870,6 +870,17 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
     return resident_smem(s->P, *cfg) <= 227 * 1024;
 }
 
+// K2t: fixed-step calls (timeSteps / flowSteps) of a thermal system whose line fits one CTA
+static bool use_resident_thermal(const fqsb_system* s, ResidentCfg* cfg, int mode)
+{
+    if (!s->thermal || mode != MODE_FIXED || (s->par.kernel & 15) == 2 || s->own_lo != 0 ||
+        s->own_hi != s->N) {
+        return false;
+    }
+    *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
+    return cfg->B != 0 && resident_thermal_smem(s->P, *cfg) <= 227 * 1024;
+}
+
 // K2b: 1-D nearest-neighbour lines beyond one CTA take the temporally blocked kernel
 // (par.kernel: low 4 bits 0 = auto, 3 = force; bits 8..15 steps per launch, bits 16..31 owned
 // blocks per tile -- both 0 = planner's choice)
@@ -1044,14 +1055,18 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
     if (sel != 1 && sel != 2 && use_blocked(s, A.mode, overdamped)) {
         TRY(run_blocked(s, A));
     }
-    else if (use_resident(s, &cfg, A.mode)) {
-        s->last_kernel = overdamped ? "resident_nopassing" : "resident";
+    else if (use_resident(s, &cfg, A.mode) || use_resident_thermal(s, &cfg, A.mode)) {
+        const bool thermal = s->thermal;
+        s->last_kernel = thermal ? "resident_thermal"
+                                 : (overdamped ? "resident_nopassing" : "resident");
         const i64 chunk = (i64)1 << 20;
         for (;;) {
             A.launch_steps = A.max_steps < chunk ? A.max_steps : chunk;
             CU(cudaEventRecord(s->ev0, s->stream));
-            cudaError_t e = overdamped ? launch_resident_nopassing(cfg, s->P, s->S, A, s->stream)
-                                       : launch_resident(cfg, s->P, s->S, A, s->stream);
+            cudaError_t e =
+                thermal ? launch_resident_thermal(cfg, s->P, s->S, A, s->th, s->stream)
+                        : (overdamped ? launch_resident_nopassing(cfg, s->P, s->S, A, s->stream)
+                                      : launch_resident(cfg, s->P, s->S, A, s->stream));
             if (e != cudaSuccess) {
                 return cuda_fail(e, "resident kernel launch");
             }

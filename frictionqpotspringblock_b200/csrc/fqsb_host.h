@@ -97,6 +97,10 @@ cudaError_t launch_blocked_fixed_done(const Par& P, const State& S, i64 nsteps, 
                                       cudaStream_t stream);
 cudaError_t launch_blocked_settle(const Par& P, const State& S, const BlockedArgs& K,
                                   cudaStream_t stream);
+// defined in fqsb_thermal.cu: K2t, the resident kernel of the thermal systems (fixed-step calls)
+size_t resident_thermal_smem(const Par& P, const ResidentCfg& c);
+cudaError_t launch_resident_thermal(const ResidentCfg& cfg, const Par& P, const State& S,
+                                    const RunArgs& A, const Thermal& TH, cudaStream_t stream);
 // defined in fqsb_stream.cu
 // `flip`: parity of the launch within the call (which buffer set is the input);
 // `finalise`: run the per-step stop decision (stop modes and flowSteps)

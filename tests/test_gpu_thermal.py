@@ -75,15 +75,17 @@ def test_reference_test_interactions():
     ("Line1d.System_Cuspy_Quartic_RandomForcing", dict(a1=1.0, a2=0.7)),
     ("Particles.System_Cuspy_RandomForcing", dict()),
 ])
-@pytest.mark.parametrize("N", [7, 300, 2500])
-def test_thermal_steps_match_oracle(cls, extra, N):
+@pytest.mark.parametrize("N", [7, 300, 1500, 2500])
+@pytest.mark.parametrize("kernel", [0, 2], ids=["resident", "stream"])
+def test_thermal_steps_match_oracle(cls, extra, N, kernel):
     """timeSteps / flowSteps with blocks redrawn on ragged schedules (several draws per step,
-    blocks due at construction, N beyond one scan chunk)."""
+    blocks due at construction, N beyond one scan chunk), on the resident kernel (K2t, every
+    blocks-per-thread configuration) and on the streaming path."""
     F = product()
     module, name = cls.split(".")
     kw = dict(shape=[N], k_frame=1.0 / N, **extra, **PHYS, **forcing(N))
     o = getattr(getattr(orc, module), name)(**kw)
-    p = getattr(getattr(F, module), name)(**kw)
+    p = getattr(getattr(F, module), name)(kernel=kernel, **kw)
     assert_same_thermal_state(o, p)  # the draws of initSystem's refresh() (dinc_init == 0)
     for s in (o, p):
         s.u_frame = 0.7
@@ -95,7 +97,51 @@ def test_thermal_steps_match_oracle(cls, extra, N):
     assert_same_thermal_state(o, p)
     assert np.isclose(o.temperature, p.temperature, rtol=1e-12, atol=0)
     assert np.isclose(o.residual, p.residual, rtol=1e-12, atol=0)
-    assert p.last_kernel == "stream"
+    assert p.last_kernel == ("stream" if kernel == 2 else "resident_thermal")
+
+
+@pytest.mark.parametrize("kernel", [0, 2], ids=["resident", "stream"])
+def test_thermal_extreme_schedules(kernel):
+    """schedule entries beyond the on-chip 31-bit window: never due, always due, huge period"""
+    F = product()
+    N = 96
+    f = forcing(N)
+    f["dinc_init"][:8] = 2**40      # never due
+    f["dinc_init"][8:16] = -(2**35)  # overdue for the whole run: redrawn every step
+    f["dinc"][16:24] = 2**36         # drawn once, then never again
+    f["dinc_init"][16:24] = 3
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, **PHYS, **f)
+    o = orc.Line1d.System_Cuspy_Laplace_RandomForcing(**kw)
+    p = F.Line1d.System_Cuspy_Laplace_RandomForcing(kernel=kernel, **kw)
+    for n in (2, 30):
+        for s in (o, p):
+            s.timeSteps(n)
+        assert_same_thermal_state(o, p)
+
+
+def test_thermal_resident_equals_streaming_bitwise():
+    """both device paths draw through the same erfinv: identical bits, sparse schedule
+    (dinc = 100 as in the reference's example) over several launches"""
+    F = product()
+    N = 1000
+    rng = np.random.default_rng(1)
+    f = dict(mean=0.0, stddev=0.05, seed_forcing=0, dinc_init=rng.integers(0, 100, N),
+             dinc=100 * np.ones(N, dtype=np.int64))
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, **PHYS, **f)
+    a = F.Line1d.System_Cuspy_Laplace_RandomForcing(kernel=0, **kw)
+    b = F.Line1d.System_Cuspy_Laplace_RandomForcing(kernel=2, **kw)
+    for n in (1, 250, 333):
+        for s in (a, b):
+            s.flowSteps(n, 5e-2)
+        for name in ("u", "v", "a", "f"):
+            assert np.array_equal(getattr(a, name), getattr(b, name)), name
+        assert np.array_equal(a.external.f_thermal, b.external.f_thermal)
+        assert np.array_equal(a.external.next, b.external.next)
+        assert a.external.state == b.external.state and a.inc == b.inc
+    assert (a.last_kernel, b.last_kernel) == ("resident_thermal", "stream")
+    # timeStepsUntilEvent is a stop mode: streaming path on both
+    assert a.timeStepsUntilEvent() == b.timeStepsUntilEvent()
+    assert np.array_equal(a.u, b.u)
 
 
 def test_external_setters_and_set_inc():
