@@ -469,6 +469,7 @@ __device__ __forceinline__ double verlet_tail(const Par& P, double F, double& v,
 
 // the same with External = RandomNormalForcing: f = f_frame + f_pot + f_int + f_damp + f_thermal
 // (detail.h:1326-1329, left to right)
+template <bool UNIT = false>
 __device__ __forceinline__ double verlet_tail_thermal(const Par& P, double F, double fth, double& v,
                                                       double& a)
 {
@@ -477,13 +478,13 @@ __device__ __forceinline__ double verlet_tail_thermal(const Par& P, double F, do
     const double meta = -P.eta;
     double vv = vn + P.dt * an;
     double f = (F + meta * vv) + fth;
-    double aa = f * P.inv_m;
+    double aa = UNIT ? f : f * P.inv_m;
     vv = vn + hdt * (an + aa);
     f = (F + meta * vv) + fth;
-    aa = f * P.inv_m;
+    aa = UNIT ? f : f * P.inv_m;
     vv = vn + hdt * (an + aa);
     f = (F + meta * vv) + fth;
-    aa = f * P.inv_m;
+    aa = UNIT ? f : f * P.inv_m;
     v = vv;
     a = aa;
     return f;

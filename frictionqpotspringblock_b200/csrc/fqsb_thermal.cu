@@ -6,22 +6,37 @@ namespace fqsb {
 
 size_t resident_thermal_smem(const Par& P, const ResidentCfg& c)
 {
+    // us[2][N+2], fth[N], fnew[2][N], jump tables, nrel[N], dincs[N], bw[2][K], dl[N] (u16)
     const size_t n = (size_t)P.N, k = (size_t)c.B * (size_t)(c.T / 32);
-    return (2 * (n + 2) + 2 * n + 2 * FQSB_TH_JUMPS) * 8 + (2 * n + 2 * k) * sizeof(int);
+    return (2 * (n + 2) + 3 * n + 2 * FQSB_TH_JUMPS) * 8 + (2 * n + 2 * k) * sizeof(int) + n * 2;
+}
+
+template <int INT, int B, int T, bool FULL, bool UNIT>
+static cudaError_t launch_k(size_t smem, const Par& P, const State& S, const RunArgs& A,
+                            const Thermal& TH, cudaStream_t stream)
+{
+    auto kernel = k_resident_thermal<INT, B, T, FULL, UNIT>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    kernel<<<(unsigned)P.R, T + 32, smem, stream>>>(P, S, A, TH); // + the producer warp
+    return cudaGetLastError();
 }
 
 template <int INT, int B, int T>
 static cudaError_t launch_one(size_t smem, const Par& P, const State& S, const RunArgs& A,
                               const Thermal& TH, cudaStream_t stream)
 {
-    auto kernel = k_resident_thermal<INT, B, T>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) {
-        return e;
+    const bool full = (i64)B * T == P.N;
+    const bool unit = unit_parameters(P);
+    if (full) {
+        return unit ? launch_k<INT, B, T, true, true>(smem, P, S, A, TH, stream)
+                    : launch_k<INT, B, T, true, false>(smem, P, S, A, TH, stream);
     }
-    kernel<<<(unsigned)P.R, T, smem, stream>>>(P, S, A, TH);
-    return cudaGetLastError();
+    return unit ? launch_k<INT, B, T, false, true>(smem, P, S, A, TH, stream)
+                : launch_k<INT, B, T, false, false>(smem, P, S, A, TH, stream);
 }
 
 template <int INT>
