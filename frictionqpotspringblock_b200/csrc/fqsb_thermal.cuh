@@ -241,11 +241,13 @@ __global__ void __launch_bounds__(T + 32)
     };
 
     // ---- well search, forces at the new positions, Verlet tail with the random force
-    auto phase2 = [&](const int ocur) {
-        const double* ucur = us + ocur;
+    // (with the producer warp the register budget is 96: the B = 8 configuration runs its blocks
+    // in two groups of four so that the temporaries of only four force chains are live)
+    constexpr int G = B > 4 ? 4 : B;
+    auto phase2_group = [&](const double* ucur, const int j0) {
         auto U = [&](int q) { return ucur[q + 1]; };
 #pragma unroll
-        for (int j = 0; j < B; ++j) {
+        for (int j = j0; j < j0 + G; ++j) {
             const int p = t + j * T;
             const int pc = (FULL || p < N) ? p : N - 1;
             const double uc = ucur[pc + 1];
@@ -262,6 +264,16 @@ __global__ void __launch_bounds__(T + 32)
             const double ff = P.k_frame * (uf - uc);
             const double F = ff + fp + fi;
             verlet_tail_thermal<UNIT>(P, F, fth[pc], v[j], a[j]);
+        }
+    };
+    auto phase2 = [&](const int ocur) {
+        const double* ucur = us + ocur;
+#pragma unroll
+        for (int j0 = 0; j0 < B; j0 += G) {
+            phase2_group(ucur, j0);
+            if (j0 + G < B) {
+                asm volatile("" ::: "memory"); // keep the groups apart
+            }
         }
     };
 

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_thermal.py tests/test_cpp_host.py -x -q > gpurun_out/pytest_thermal.log 2>&1; echo rc=$? >> gpurun_out/pytest_thermal.log)
 timeout 200 python tools/thermal_bench.py > gpurun_out/thermal_bench.log 2>&1
-tail -30 gpurun_out/pytest_thermal.log; cat gpurun_out/thermal_bench.log
+cat gpurun_out/thermal_bench.log
+(timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log)
+tail -5 gpurun_out/pytest.log
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json
