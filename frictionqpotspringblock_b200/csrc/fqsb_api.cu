@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -451,6 +452,31 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
         TRY(dev_alloc(s, &S.ctl, (size_t)s->R));
         TRY(dev_alloc(s, &S.err, 2));
         S.tiles = (int)grid_for(s->N);
+        if (P.rank == 2) {
+            // k_stream_2d: 2 CTAs per SM (126 registers), 2 halo rows of u,v,a = 0.75 rows of
+            // traffic per band; k_stream_np_2d: FQSB_S2_NP_CTAS CTAs per SM, 2 halo rows of u = 0.5 rows
+            int sms = 148;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            P.s2_ty = plan_band_rows(P, 2 * sms, 0.75, S.tiles);
+            int np_ctas = FQSB_S2_NP_CTAS;
+            if (const char* e = std::getenv("FQSB_S2_NP_CTAS")) {
+                np_ctas = std::atoi(e) >= 2 && std::atoi(e) <= 4 ? std::atoi(e) : np_ctas;
+            }
+            P.s2_ty_np = plan_band_rows(P, np_ctas * sms, 0.5, S.tiles);
+            // tuning knobs (tools/line2d.py): rows per CTA forced from the environment
+            if (const char* e = std::getenv("FQSB_S2_TY")) {
+                const int ty = std::atoi(e);
+                if (ty >= 1 && ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + ty - 1) / ty) <= S.tiles) {
+                    P.s2_ty = ty;
+                }
+            }
+            if (const char* e = std::getenv("FQSB_S2_TY_NP")) {
+                const int ty = std::atoi(e);
+                if (ty >= 1 && ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + ty - 1) / ty) <= S.tiles) {
+                    P.s2_ty_np = ty;
+                }
+            }
+        }
         TRY(dev_alloc(s, &s->d_red, (size_t)s->R * S.tiles * FQSB_NPART));
         S.part = s->d_red;
         TRY(dev_alloc(s, &s->d_out, (size_t)s->R * 4));

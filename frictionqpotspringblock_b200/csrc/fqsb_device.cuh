@@ -24,6 +24,9 @@ struct Par {
     int rows, cols;
     int consumes; // distribution consumes pcg32 draws (everything but delta)
     int thermal;  // External = RandomNormalForcing (detail.h:881-1000): State::f_thermal is set
+    // rows per CTA of the 2-D row-marching kernels (Verlet step / no-passing sweep), chosen per
+    // handle so that the grid fills whole waves of resident CTAs (plan_band_rows)
+    int s2_ty, s2_ty_np;
     i64 N; // blocks per realisation
     i64 R; // realisations
     double m, inv_m, eta, mu, kappa, k1, k2, k_frame, dt;

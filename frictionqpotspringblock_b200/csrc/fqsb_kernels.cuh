@@ -897,20 +897,33 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
 }
 
 // ---- 2-D stencils (5- and 9-point): row-marching strips ---------------------------------------
-// A CTA owns a strip of FQSB_S2_TX columns and marches over FQSB_S2_TY rows. The new positions
+// A CTA owns a strip of FQSB_S2_TX columns and marches over Par::s2_ty rows (a per-handle choice:
+// with a fixed 32 rows the 4096 x 4096 interface of config #5 made 1024 CTAs = 3.46 waves of the
+// 296 resident ones, i.e. the last wave ran at 46 % occupancy). The new positions
 // of rows i-1, i, i+1 live in a 4-slot ring in shared memory (one barrier per row); every cell's
 // u,v,a,y_l,y_r is loaded exactly once (plus the 2 halo rows per strip and 2 halo columns per
 // row), as double2, one row ahead of its use.
 #define FQSB_S2_THREADS 256
 #define FQSB_S2_TX (2 * FQSB_S2_THREADS)
-#define FQSB_S2_TY 32
+#define FQSB_S2_TY 32 // default rows per CTA (Par::s2_ty == 0)
+// resident CTAs per SM of the no-passing sweep kernel. With 4 (64 registers) the three rows of
+// look-ahead spilled to local memory and the kernel stalled on those reloads (ncu: long
+// scoreboard 9.7 of 16 stall cycles per issue, 27 % of the DRAM peak).
+#ifndef FQSB_S2_NP_CTAS
+#define FQSB_S2_NP_CTAS 2
+#endif
+#ifndef FQSB_S2_NP_DU
+#define FQSB_S2_NP_DU 3 // rows of slips in flight ahead of the row being swept (4 / 3: slower)
+#define FQSB_S2_NP_DW 2 // rows of wells in flight
+#endif
 
 template <int INT, bool UNIT>
 __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
     k_stream_2d(const __grid_constant__ Par P, const __grid_constant__ State S,
                 const __grid_constant__ RunArgs A, const int flip, const int finalise)
 {
-    constexpr int TX = FQSB_S2_TX, TY = FQSB_S2_TY;
+    constexpr int TX = FQSB_S2_TX;
+    const int TY = P.s2_ty > 0 ? P.s2_ty : FQSB_S2_TY;
     __shared__ __align__(16) double sun[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
     __shared__ double scratch[32 * 5];
     __shared__ int iscratch[32 * 4];
@@ -1334,13 +1347,14 @@ __global__ void __launch_bounds__(256)
 
 // ---- no-passing sweep on a 2-D lattice: row-marching strips like k_stream_2d (u only) -----------
 // Same fused launch semantics as k_stream_np (residual of the input configuration + next sweep).
-template <int UNUSED> // (a template only to get weak linkage from a header)
-__global__ void __launch_bounds__(FQSB_S2_THREADS, 4)
+template <int CTAS> // resident CTAs per SM the register budget is sized for
+__global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
     k_stream_np_2d(const __grid_constant__ Par P, const __grid_constant__ State S,
                    const __grid_constant__ RunArgs A, const int flip, const int first,
                    const int do_sweep)
 {
-    constexpr int TX = FQSB_S2_TX, TY = FQSB_S2_TY;
+    constexpr int TX = FQSB_S2_TX;
+    const int TY = P.s2_ty_np > 0 ? P.s2_ty_np : FQSB_S2_TY;
     __shared__ __align__(16) double su[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
     __shared__ double scratch[32 * 2];
     __shared__ int s_last;
@@ -1390,45 +1404,64 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 4)
         }
     };
 
-    // software pipeline: slips are loaded three rows ahead, wells two rows ahead of their use
-    // (a sweep moves only 32 B per block, so one row of look-ahead leaves too little in flight)
-    Row top, cur, nxt, nn, n3;
-    top.u = cur.u = nxt.u = nn.u = n3.u = make_double2(0.0, 0.0);
-    top.h = cur.h = nxt.h = nn.h = n3.h = 0.0;
-    double2 l2 = make_double2(0.0, 0.0), r2 = l2, l2n = l2, r2n = l2, l2nn = l2, r2nn = l2;
+    // software pipeline in registers: slips are loaded DU rows ahead, wells DW rows ahead of their
+    // use (a sweep moves only 32 B per block, so a shallow look-ahead leaves too little in
+    // flight). q[k] = slips of row i + k, wl/wr[k] = wells of row i + k.
+    constexpr int DU = FQSB_S2_NP_DU, DW = FQSB_S2_NP_DW;
+    Row q[DU + 1];
+    double2 wlq[DW + 1], wrq[DW + 1];
+#pragma unroll
+    for (int k = 0; k <= DU; ++k) {
+        q[k].u = make_double2(0.0, 0.0);
+        q[k].h = 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k <= DW; ++k) {
+        wlq[k] = wrq[k] = make_double2(0.0, 0.0);
+    }
     auto load_wells = [&](int gr, double2& l, double2& rr) {
         if (act && gr < row0 + nrow) {
             l = *reinterpret_cast<const double2*>(S.yl + base + (i64)gr * C_ + col);
             rr = *reinterpret_cast<const double2*>(S.yr + base + (i64)gr * C_ + col);
         }
     };
-    load_row(row0 - 1, top);
-    load_row(row0, cur);
-    load_row(row0 + 1, nxt);
-    load_row(row0 + 2, nn);
-    load_wells(row0, l2, r2);
-    load_wells(row0 + 1, l2n, r2n);
-    publish(top, (row0 + 3) & 3);
-    publish(cur, row0 & 3);
+    {
+        Row top;
+        top.u = make_double2(0.0, 0.0);
+        top.h = 0.0;
+        load_row(row0 - 1, top);
+#pragma unroll
+        for (int k = 0; k < DU; ++k) {
+            if (k <= nrow) {
+                load_row(row0 + k, q[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DW; ++k) {
+            load_wells(row0 + k, wlq[k], wrq[k]);
+        }
+        publish(top, (row0 + 3) & 3);
+        publish(q[0], row0 & 3);
+    }
 
     double acc[2] = {0.0, 0.0};
     int underflow = 0;
     bool nan = false;
     for (int i = row0; i < row0 + nrow; ++i) {
-        if (i + 3 <= row0 + nrow) {
-            load_row(i + 3, n3);
+        if (i + DU <= row0 + nrow) {
+            load_row(i + DU, q[DU]);
         }
-        load_wells(i + 2, l2nn, r2nn);
-        publish(nxt, (i + 1) & 3);
+        load_wells(i + DW, wlq[DW], wrq[DW]);
+        publish(q[1], (i + 1) & 3);
         const i64 rowoff = (i64)i * C_;
         __syncthreads();
         if (act) {
             const double* up = &su[(i + 3) & 3][2];
             const double* mid = &su[i & 3][2];
             const double* dn = &su[(i + 1) & 3][2];
-            double ucv[2] = {cur.u.x, cur.u.y};
-            double wl[2] = {l2.x, l2.y};
-            double wr[2] = {r2.x, r2.y};
+            double ucv[2] = {q[0].u.x, q[0].u.y};
+            double wl[2] = {wlq[0].x, wlq[0].y};
+            double wr[2] = {wrq[0].x, wrq[0].y};
             double out[2];
             const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi;
 #pragma unroll
@@ -1485,13 +1518,15 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 4)
                 *reinterpret_cast<double2*>(unew + rowoff + col) = make_double2(out[0], out[1]);
             }
         }
-        cur = nxt;
-        nxt = nn;
-        nn = n3;
-        l2 = l2n;
-        r2 = r2n;
-        l2n = l2nn;
-        r2n = r2nn;
+#pragma unroll
+        for (int k = 0; k < DU; ++k) {
+            q[k] = q[k + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < DW; ++k) {
+            wlq[k] = wlq[k + 1];
+            wrq[k] = wrq[k + 1];
+        }
     }
     if (underflow) {
         S.err[0] = 1;

@@ -1,4 +1,7 @@
 // fqsb_stream.cu -- instantiation unit of the streaming kernels + kernel dispatch tables.
+#include <cmath>
+#include <cstdlib>
+
 #include "fqsb_host.h"
 #include "fqsb_kernels.cuh"
 
@@ -67,9 +70,45 @@ int stream_step_tiles(const Par& P, int generic_tiles)
         return (int)((P.N + FQSB_ST_TILE - 1) / FQSB_ST_TILE);
     }
     if (use_tiled_2d(P)) {
-        return ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + FQSB_S2_TY - 1) / FQSB_S2_TY);
+        const int ty = P.s2_ty > 0 ? P.s2_ty : FQSB_S2_TY;
+        return ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + ty - 1) / ty);
     }
     return generic_tiles;
+}
+
+// CTAs per realisation of the tiled 2-D no-passing sweep
+static int stream_sweep_tiles(const Par& P)
+{
+    const int ty = P.s2_ty_np > 0 ? P.s2_ty_np : FQSB_S2_TY;
+    return ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + ty - 1) / ty);
+}
+
+// Rows per CTA of the row-marching 2-D kernels: the grid (strips x bands x realisations) should
+// fill whole waves of the `resident` CTAs the device holds at once, at the price of 2 halo rows
+// per band (`halo` = their relative cost per row of a band). At most `max_tiles` CTAs per
+// realisation (the size of the per-CTA partial-sum buffer).
+int plan_band_rows(const Par& P, int resident, double halo, int max_tiles)
+{
+    if (P.rank != 2) {
+        return 0;
+    }
+    const int strips = (P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX;
+    int best = FQSB_S2_TY;
+    double best_cost = 1e300;
+    for (int ty = 8; ty <= 128; ++ty) {
+        const int bands = (P.rows + ty - 1) / ty;
+        if (strips * bands > max_tiles) {
+            continue;
+        }
+        const double n = (double)strips * bands * (double)P.R;
+        const double waves = n / resident;
+        const double cost = std::ceil(waves) / waves * (1.0 + halo / ty);
+        if (cost < best_cost - 1e-12) {
+            best_cost = cost;
+            best = ty;
+        }
+    }
+    return best;
 }
 
 const char* stream_step_name(const Par& P)
@@ -155,8 +194,20 @@ cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
                                 cudaStream_t stream, int flip, int first, int do_sweep)
 {
     if (use_tiled_2d(P)) {
-        dim3 grid2((unsigned)stream_step_tiles(P, 0), (unsigned)P.R);
-        k_stream_np_2d<0><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
+        dim3 grid2((unsigned)stream_sweep_tiles(P), (unsigned)P.R);
+        static const int ctas = [] { // tuning knob (tools/line2d.py)
+            const char* e = std::getenv("FQSB_S2_NP_CTAS");
+            return e ? std::atoi(e) : FQSB_S2_NP_CTAS;
+        }();
+        if (ctas == 4) {
+            k_stream_np_2d<4><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
+        }
+        else if (ctas == 3) {
+            k_stream_np_2d<3><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
+        }
+        else {
+            k_stream_np_2d<2><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
+        }
         return cudaGetLastError();
     }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);

@@ -1,6 +1,3 @@
 mkdir -p gpurun_out
-timeout 200 python tools/thermal_bench.py > gpurun_out/thermal_bench.log 2>&1
-cat gpurun_out/thermal_bench.log
-(timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log)
-tail -5 gpurun_out/pytest.log
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 600 gpurun_out/bench.json
+for ty in 8 14 28 56 113; do echo "NP TY=$ty"; FQSB_S2_TY_NP=$ty timeout 120 python tools/line2d.py 2>&1 | grep "fixed point"; done > gpurun_out/np_ty.log 2>&1
+cat gpurun_out/np_ty.log

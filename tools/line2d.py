@@ -36,3 +36,9 @@ dt = time.perf_counter() - t0
 print(f"{s.last_kernel}: no-passing sweeps: ret={ret} launches={s.last_kernel_launches} "
       f"{s.last_kernel_seconds / max(1, s.last_kernel_launches) * 1e6:.1f} us/sweep "
       f"({n * s.last_kernel_launches / s.last_kernel_seconds:.3e} block-updates/s)")
+# steady state: sweeps at the fixed point move (almost) no block between wells, so they show the
+# streaming rate of the kernel itself (32 B per block-update)
+s.minimise(tol=1e-300, max_iter=60, max_iter_is_error=False)
+per = s.last_kernel_seconds / max(1, s.last_kernel_launches)
+print(f"{s.last_kernel}: sweeps at the fixed point: {s.last_kernel_launches} launches, "
+      f"{per * 1e6:.1f} us/sweep = {n / per:.3e} block-updates/s = {32 * n / per / 1e9:.0f} GB/s")
