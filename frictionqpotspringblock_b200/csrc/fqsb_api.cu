@@ -462,6 +462,9 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
             if (const char* e = std::getenv("FQSB_S2_NP_CTAS")) {
                 np_ctas = std::atoi(e) >= 2 && std::atoi(e) <= 4 ? std::atoi(e) : np_ctas;
             }
+            if (const char* e = std::getenv("FQSB_S2_NP_BULK_VARIANT")) {
+                np_ctas = (std::atoi(e) == 1 || std::atoi(e) == 3) ? 3 : 2;
+            }
             P.s2_ty_np = plan_band_rows(P, np_ctas * sms, 0.5, S.tiles);
             // tuning knobs (tools/line2d.py): rows per CTA forced from the environment
             if (const char* e = std::getenv("FQSB_S2_TY")) {

@@ -493,6 +493,61 @@ __device__ __forceinline__ double verlet_tail_thermal(const Par& P, double F, do
     return f;
 }
 
+// ---- bulk asynchronous copies (the TMA engine: cp.async.bulk global -> shared, completion on an
+//      mbarrier by byte count). Used by the row-marching 2-D kernels to stage whole rows in shared
+//      memory several rows ahead of their use without spending registers on the look-ahead.
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(u64* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+// make freshly initialised mbarriers visible to the async proxy
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// one arrival that also announces `bytes` of pending bulk-copy traffic for the current phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+// bytes: multiple of 16; dst and src 16-byte aligned
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, u64* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(u64* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0u;
+}
+
+__device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
 // ---- GooseFEM::Iterate::StopList held in the lanes of a warp -----------
 // lane l < n holds entry l as the pair (num, den), residual_l^2 = num / den; entries start at
 // +inf. The criterion only COMPARES residuals (detail.h:1615,1748,1780,1874):

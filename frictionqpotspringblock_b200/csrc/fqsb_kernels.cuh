@@ -1551,4 +1551,220 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
     np_finalise(P, S, A, r, flip, first, do_sweep);
 }
 
+// ---- no-passing sweep on a 2-D lattice, rows staged in shared memory by the TMA engine ----------
+// Same arithmetic and launch semantics as k_stream_np_2d. Instead of holding the look-ahead in
+// registers (3 rows of slips + 2 rows of wells per thread: 128 registers at 2 CTAs per SM, and
+// still only ~57 KB in flight per SM), one thread issues cp.async.bulk copies of whole rows
+// (slips, y_l, y_r of the strip: 3 x 4 KB) into a ring of S stages, S-3 rows ahead of their use;
+// each stage completes on its own mbarrier. The staged slips ARE the stencil source: row i reads
+// rows i-1, i, i+1 of the ring (the periodic halo columns are added by two threads), so the
+// separate ring of published rows and its stores disappear too. A stage is refilled after the
+// barrier that follows its last use (row q is read by rows q-1, q, q+1).
+#define FQSB_S2_BULK_STAGES 8
+
+struct BulkStage {
+    double u[FQSB_S2_TX + 4]; // [1] left halo, [2 .. 2 + cnt) the strip, [2 + cnt] right halo
+    double yl[FQSB_S2_TX];
+    double yr[FQSB_S2_TX];
+};
+
+inline size_t stream_np_2d_bulk_smem(int stages) { return sizeof(BulkStage) * (size_t)stages; }
+
+template <int NS, int CTAS> // stages of the ring, resident CTAs per SM
+__global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
+    k_stream_np_2d_bulk(const __grid_constant__ Par P, const __grid_constant__ State S,
+                        const __grid_constant__ RunArgs A, const int flip, const int first,
+                        const int do_sweep)
+{
+    constexpr int TX = FQSB_S2_TX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BulkStage* stage = reinterpret_cast<BulkStage*>(smem_raw);
+    __shared__ __align__(8) u64 full[NS];
+    __shared__ double scratch[32 * 2];
+    __shared__ int s_last;
+    const int TY = P.s2_ty_np > 0 ? P.s2_ty_np : FQSB_S2_TY;
+    const int t = threadIdx.x;
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    if (ctl.status != ST_RUNNING) {
+        return;
+    }
+    const int R_ = P.rows, C_ = P.cols;
+    const int strips = (C_ + TX - 1) / TX;
+    const int strip = blockIdx.x % strips, band = blockIdx.x / strips;
+    const int c0 = strip * TX, row0 = band * TY;
+    const int cnt = C_ - c0 < TX ? C_ - c0 : TX;
+    const int nrow = R_ - row0 < TY ? R_ - row0 : TY;
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ uold = (flip ? S.u2 : S.u) + base;
+    double* __restrict__ unew = (flip ? S.u : S.u2) + base;
+    const bool act = 2 * t < cnt;
+    const int col = c0 + 2 * t;
+    const int hcol = t == 0 ? (c0 == 0 ? C_ - 1 : c0 - 1) : (c0 + cnt == C_ ? 0 : c0 + cnt);
+    const double uf = S.u_frame[r];
+    const double k = P.k1, kf = P.k_frame, mu = P.mu;
+    const double denom = 4 * k + kf + mu;
+    const double rdenom = 1.0 / denom;
+    const unsigned row_bytes = (unsigned)cnt * 8u;
+
+    // band row rr = -1 .. nrow (global row row0 + rr, wrapped) lives in stage (rr + 1) % NS
+    auto wrapped = [&](int rr) {
+        const int gr = row0 + rr;
+        return gr < 0 ? gr + R_ : (gr >= R_ ? gr - R_ : gr);
+    };
+    auto issue = [&](int rr) { // one thread: slips of row rr, and its wells if it is swept here
+        BulkStage& st = stage[(rr + 1) % NS];
+        u64* bar = &full[(rr + 1) % NS];
+        const i64 off = (i64)wrapped(rr) * C_ + c0;
+        const bool wells = rr >= 0 && rr < nrow;
+        mbar_arrive_expect_tx(bar, wells ? 3u * row_bytes : row_bytes);
+        bulk_copy_g2s(&st.u[2], uold + off, row_bytes, bar);
+        if (wells) {
+            bulk_copy_g2s(st.yl, S.yl + base + off, row_bytes, bar);
+            bulk_copy_g2s(st.yr, S.yr + base + off, row_bytes, bar);
+        }
+    };
+    if (t == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1u);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int rr = -1; rr < NS - 1 && rr <= nrow; ++rr) {
+            issue(rr);
+        }
+    }
+    // halo columns of the rows: two threads, plain loads two rows ahead
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    if (t < 2) {
+        h0 = uold[(i64)wrapped(-1) * C_ + hcol];
+        h1 = uold[(i64)wrapped(0) * C_ + hcol];
+        if (1 <= nrow) {
+            h2 = uold[(i64)wrapped(1) * C_ + hcol];
+        }
+    }
+    const int hidx = t == 0 ? 1 : 2 + cnt;
+    // rows -1 and 0 must be complete (with halos) before the first row is swept
+    mbar_wait(&full[0], 0u);
+    mbar_wait(&full[1 % NS], 0u);
+    if (t < 2) {
+        stage[0].u[hidx] = h0;
+        stage[1 % NS].u[hidx] = h1;
+    }
+
+    double acc[2] = {0.0, 0.0};
+    int underflow = 0;
+    bool nan = false;
+    for (int i = 0; i < nrow; ++i) {
+        const int sm = (i + 1) % NS, sp = (i + 2) % NS, su_ = i % NS;
+        double h3 = 0.0;
+        if (t < 2 && i + 2 <= nrow) {
+            h3 = uold[(i64)wrapped(i + 2) * C_ + hcol];
+        }
+        // row i+1 landed? (fill number (i + 2) / NS of its stage)
+        mbar_wait(&full[sp], (unsigned)(((i + 2) / NS) & 1));
+        if (t < 2) {
+            stage[sp].u[hidx] = h2;
+        }
+        __syncthreads(); // halos of row i+1 visible; every thread is done with row i-1
+        if (t == 0 && i >= 1) {
+            const int rr = i - 2 + NS; // refill the stage of row i-2 (last read by row i-1)
+            if (rr <= nrow) {
+                issue(rr);
+            }
+        }
+        const i64 rowoff = (i64)(row0 + i) * C_;
+        if (act) {
+            const double* up = &stage[su_].u[2];
+            const double* mid = &stage[sm].u[2];
+            const double* dn = &stage[sp].u[2];
+            const double2 ucp = *reinterpret_cast<const double2*>(&mid[2 * t]);
+            const double2 wlp = *reinterpret_cast<const double2*>(&stage[sm].yl[2 * t]);
+            const double2 wrp = *reinterpret_cast<const double2*>(&stage[sm].yr[2 * t]);
+            double ucv[2] = {ucp.x, ucp.y};
+            double wl[2] = {wlp.x, wlp.y};
+            double wr[2] = {wrp.x, wrp.y};
+            double out[2];
+            const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lc = 2 * t + e;
+                const double uc = ucv[e];
+                const double a = up[lc], b = dn[lc], c = mid[lc - 1], d = mid[lc + 1];
+                const double uneigh = a + b + c + d;       // detail.h:1715-1723 (2-D)
+                const double lap = a + b + c + d - 4 * uc; // detail.h:557-582
+                {
+                    double umin = 0.5 * (wl[e] + wr[e]);
+                    double ff = kf * (uf - uc);
+                    double fp = mu * (umin - uc);
+                    double fi = lap * k;
+                    double f = fp + fi + ff;
+                    acc[0] += own ? f * f : 0.0;
+                    acc[1] += own ? ff * ff : 0.0;
+                    nan |= uc != uc;
+                }
+                double un = uc;
+                if (do_sweep) {
+                    int total = 0;
+                    u64 st = 0;
+                    i64 i0 = 0;
+                    bool loaded = false;
+                    const i64 gp = base + rowoff + col + e;
+                    for (;;) { // detail.h:1728-1738
+                        double umin = 0.5 * (wl[e] + wr[e]);
+                        un = div_by_invariant(k * uneigh + kf * uf + mu * umin, denom, rdenom);
+                        if (!(un > wr[e] || !(un > wl[e])) || un != un) {
+                            break;
+                        }
+                        if (!loaded) {
+                            st = S.rng[gp];
+                            i0 = S.idx[gp];
+                            loaded = true;
+                        }
+                        int moved = well_align(P, un, wl[e], wr[e], st, i0 + total, &underflow);
+                        total += moved;
+                        if (moved == 0) {
+                            break;
+                        }
+                    }
+                    if (loaded) {
+                        S.rng[gp] = st;
+                        S.idx[gp] = i0 + total;
+                        S.yl[gp] = wl[e];
+                        S.yr[gp] = wr[e];
+                    }
+                }
+                out[e] = un;
+            }
+            if (do_sweep) {
+                *reinterpret_cast<double2*>(unew + rowoff + col) = make_double2(out[0], out[1]);
+            }
+        }
+        h2 = h3;
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+    if (nan) {
+        S.err[1] = 1;
+    }
+    block_sum<2>(acc, scratch);
+    double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
+    if (threadIdx.x == 0) {
+        part[0] = acc[0];
+        part[1] = acc[1];
+        __threadfence();
+        unsigned int ticket = atomicAdd(&ctl.count, 1u);
+        s_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 32) {
+        return;
+    }
+    __threadfence();
+    np_finalise(P, S, A, r, flip, first, do_sweep);
+}
+
 } // namespace fqsb
