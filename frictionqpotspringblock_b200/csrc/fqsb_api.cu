@@ -458,14 +458,7 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
             int sms = 148;
             CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             P.s2_ty = plan_band_rows(P, 2 * sms, 0.75, S.tiles);
-            int np_ctas = FQSB_S2_NP_CTAS;
-            if (const char* e = std::getenv("FQSB_S2_NP_CTAS")) {
-                np_ctas = std::atoi(e) >= 2 && std::atoi(e) <= 4 ? std::atoi(e) : np_ctas;
-            }
-            if (const char* e = std::getenv("FQSB_S2_NP_BULK_VARIANT")) {
-                np_ctas = (std::atoi(e) == 1 || std::atoi(e) == 3) ? 3 : 2;
-            }
-            P.s2_ty_np = plan_band_rows(P, np_ctas * sms, 0.5, S.tiles);
+            P.s2_ty_np = plan_band_rows(P, FQSB_S2_NP_CTAS * sms, 0.5, S.tiles);
             // tuning knobs (tools/line2d.py): rows per CTA forced from the environment
             if (const char* e = std::getenv("FQSB_S2_TY")) {
                 const int ty = std::atoi(e);

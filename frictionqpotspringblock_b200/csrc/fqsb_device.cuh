@@ -542,6 +542,11 @@ __device__ __forceinline__ bool mbar_try_wait(u64* bar, unsigned parity)
     return ok != 0u;
 }
 
+__device__ __forceinline__ void mbar_arrive(u64* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(u64* bar, unsigned parity)
 {
     while (!mbar_try_wait(bar, parity)) {

@@ -1560,6 +1560,11 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
 // rows i-1, i, i+1 of the ring (the periodic halo columns are added by two threads), so the
 // separate ring of published rows and its stores disappear too. A stage is refilled after the
 // barrier that follows its last use (row q is read by rows q-1, q, q+1).
+// Measured on 4096 x 4096 (tools/line2d.py, sweeps at the fixed point): 135 -> 106 us per sweep.
+// Neither more stages, nor a third CTA per SM (5 stages), nor a fully barrier-free variant (warp-
+// specialised producer + per-stage empty/full mbarriers, halo columns as 16-byte bulk copies)
+// moved it further (106-114 us): at 5.0 TB/s the sweep sits on the same DRAM plateau as the
+// register-staged 2-D Verlet step (5.3 TB/s).
 #define FQSB_S2_BULK_STAGES 8
 
 struct BulkStage {
@@ -1686,57 +1691,59 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
             double ucv[2] = {ucp.x, ucp.y};
             double wl[2] = {wlp.x, wlp.y};
             double wr[2] = {wrp.x, wrp.y};
-            double out[2];
+            double out[2], uneigh[2];
             const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi;
+            // straight-line part for both cells (their chains interleave): residual of the
+            // input configuration and the common case of the sweep, the block stays in its well
+            unsigned hop = 0u;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int lc = 2 * t + e;
                 const double uc = ucv[e];
                 const double a = up[lc], b = dn[lc], c = mid[lc - 1], d = mid[lc + 1];
-                const double uneigh = a + b + c + d;       // detail.h:1715-1723 (2-D)
+                uneigh[e] = a + b + c + d;                 // detail.h:1715-1723 (2-D)
                 const double lap = a + b + c + d - 4 * uc; // detail.h:557-582
-                {
-                    double umin = 0.5 * (wl[e] + wr[e]);
-                    double ff = kf * (uf - uc);
-                    double fp = mu * (umin - uc);
-                    double fi = lap * k;
-                    double f = fp + fi + ff;
-                    acc[0] += own ? f * f : 0.0;
-                    acc[1] += own ? ff * ff : 0.0;
-                    nan |= uc != uc;
-                }
-                double un = uc;
-                if (do_sweep) {
-                    int total = 0;
-                    u64 st = 0;
-                    i64 i0 = 0;
-                    bool loaded = false;
+                const double umin = 0.5 * (wl[e] + wr[e]);
+                const double ff = kf * (uf - uc);
+                const double fp = mu * (umin - uc);
+                const double fi = lap * k;
+                const double f = fp + fi + ff;
+                acc[0] += own ? f * f : 0.0;
+                acc[1] += own ? ff * ff : 0.0;
+                nan |= uc != uc;
+                const double un = div_by_invariant(k * uneigh[e] + kf * uf + mu * umin, denom, rdenom);
+                out[e] = do_sweep ? un : uc;
+                hop |= (do_sweep && (un > wr[e] || !(un > wl[e])) && !(un != un)) ? (1u << e) : 0u;
+            }
+            if (hop) { // rare: a block leaves its well, detail.h:1728-1738
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (!((hop >> e) & 1u)) {
+                        continue;
+                    }
                     const i64 gp = base + rowoff + col + e;
-                    for (;;) { // detail.h:1728-1738
-                        double umin = 0.5 * (wl[e] + wr[e]);
-                        un = div_by_invariant(k * uneigh + kf * uf + mu * umin, denom, rdenom);
-                        if (!(un > wr[e] || !(un > wl[e])) || un != un) {
-                            break;
-                        }
-                        if (!loaded) {
-                            st = S.rng[gp];
-                            i0 = S.idx[gp];
-                            loaded = true;
-                        }
+                    u64 st = S.rng[gp];
+                    const i64 i0 = S.idx[gp];
+                    int total = 0;
+                    double un = out[e];
+                    for (;;) {
                         int moved = well_align(P, un, wl[e], wr[e], st, i0 + total, &underflow);
                         total += moved;
                         if (moved == 0) {
                             break;
                         }
+                        double umin = 0.5 * (wl[e] + wr[e]);
+                        un = div_by_invariant(k * uneigh[e] + kf * uf + mu * umin, denom, rdenom);
+                        if (!(un > wr[e] || !(un > wl[e])) || un != un) {
+                            break;
+                        }
                     }
-                    if (loaded) {
-                        S.rng[gp] = st;
-                        S.idx[gp] = i0 + total;
-                        S.yl[gp] = wl[e];
-                        S.yr[gp] = wr[e];
-                    }
+                    S.rng[gp] = st;
+                    S.idx[gp] = i0 + total;
+                    S.yl[gp] = wl[e];
+                    S.yr[gp] = wr[e];
+                    out[e] = un;
                 }
-                out[e] = un;
             }
             if (do_sweep) {
                 *reinterpret_cast<double2*>(unew + rowoff + col) = make_double2(out[0], out[1]);

@@ -195,48 +195,24 @@ cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
 {
     if (use_tiled_2d(P)) {
         dim3 grid2((unsigned)stream_sweep_tiles(P), (unsigned)P.R);
-        static const int ctas = [] { // tuning knob (tools/line2d.py)
-            const char* e = std::getenv("FQSB_S2_NP_CTAS");
-            return e ? std::atoi(e) : FQSB_S2_NP_CTAS;
-        }();
         static const bool bulk = [] { // 0: register-staged look-ahead instead of the TMA engine
             const char* e = std::getenv("FQSB_S2_NP_BULK");
             return e ? std::atoi(e) != 0 : true;
         }();
         if (bulk) {
-            static const int variant = [] { // tuning knob: stages x resident CTAs
-                const char* e = std::getenv("FQSB_S2_NP_BULK_VARIANT");
-                return e ? std::atoi(e) : 0;
-            }();
-#define FQSB_NP_BULK(ns, c) \
-    { \
-        static const cudaError_t attr = cudaFuncSetAttribute( \
-            k_stream_np_2d_bulk<ns, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-            (int)stream_np_2d_bulk_smem(ns)); \
-        if (attr != cudaSuccess) { \
-            return attr; \
-        } \
-        k_stream_np_2d_bulk<ns, c><<<grid2, FQSB_S2_THREADS, stream_np_2d_bulk_smem(ns), stream>>>( \
-            P, S, A, flip, first, do_sweep); \
-        return cudaGetLastError(); \
-    }
-            switch (variant) {
-            case 1: FQSB_NP_BULK(5, 3)
-            case 2: FQSB_NP_BULK(6, 2)
-            case 3: FQSB_NP_BULK(4, 3)
-            default: FQSB_NP_BULK(FQSB_S2_BULK_STAGES, 2)
+            constexpr int NS = FQSB_S2_BULK_STAGES;
+            static const cudaError_t attr = cudaFuncSetAttribute(
+                k_stream_np_2d_bulk<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                (int)stream_np_2d_bulk_smem(NS));
+            if (attr != cudaSuccess) {
+                return attr;
             }
-#undef FQSB_NP_BULK
+            k_stream_np_2d_bulk<NS, 2><<<grid2, FQSB_S2_THREADS, stream_np_2d_bulk_smem(NS), stream>>>(
+                P, S, A, flip, first, do_sweep);
+            return cudaGetLastError();
         }
-        if (ctas == 4) {
-            k_stream_np_2d<4><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
-        }
-        else if (ctas == 3) {
-            k_stream_np_2d<3><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
-        }
-        else {
-            k_stream_np_2d<2><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first, do_sweep);
-        }
+        k_stream_np_2d<FQSB_S2_NP_CTAS><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first,
+                                                                             do_sweep);
         return cudaGetLastError();
     }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
