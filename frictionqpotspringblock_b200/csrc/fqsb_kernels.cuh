@@ -1774,4 +1774,231 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
     np_finalise(P, S, A, r, flip, first, do_sweep);
 }
 
+// ---- 2-D velocity-Verlet step with rows staged in shared memory by the TMA engine --------------
+// Same arithmetic as k_stream_2d. The raw state of a row (u, v, a, y_l, y_r of the strip: 5 x 4 KB)
+// is brought into a ring of NS stages by cp.async.bulk copies that one thread issues NS-2 rows
+// ahead; each stage completes on its own mbarrier. Row q's stage is read when the new positions
+// of row q are computed (iteration q-1) and by the Verlet tail of row q (iteration q), and is
+// refilled after the barrier of iteration q+1. The look-ahead costs no registers (k_stream_2d
+// holds three rows of u, v, a in registers: 126 registers per thread).
+struct VerletStage {
+    double u[FQSB_S2_TX];
+    double v[FQSB_S2_TX];
+    double a[FQSB_S2_TX];
+    double yl[FQSB_S2_TX];
+    double yr[FQSB_S2_TX];
+};
+
+inline size_t stream_2d_bulk_smem(int stages) { return sizeof(VerletStage) * (size_t)stages; }
+
+template <int INT, bool UNIT, int NS>
+__global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
+    k_stream_2d_bulk(const __grid_constant__ Par P, const __grid_constant__ State S,
+                     const __grid_constant__ RunArgs A, const int flip, const int finalise)
+{
+    constexpr int TX = FQSB_S2_TX;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    VerletStage* stage = reinterpret_cast<VerletStage*>(smem_raw);
+    __shared__ __align__(16) double sun[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
+    __shared__ __align__(8) u64 full[NS];
+    __shared__ double scratch[32 * 5];
+    __shared__ int iscratch[32 * 4];
+    __shared__ int s_last;
+    const int TY = P.s2_ty > 0 ? P.s2_ty : FQSB_S2_TY;
+    const int t = threadIdx.x;
+    const int r = blockIdx.y;
+    Ctl& ctl = S.ctl[r];
+    const int status = ctl.status;
+    const int R_ = P.rows, C_ = P.cols;
+    const int strips = (C_ + TX - 1) / TX;
+    const int strip = blockIdx.x % strips, band = blockIdx.x / strips;
+    const int c0 = strip * TX, row0 = band * TY;
+    const int cnt = C_ - c0 < TX ? C_ - c0 : TX; // columns of this strip (even)
+    const int nrow = R_ - row0 < TY ? R_ - row0 : TY;
+    const i64 base = (i64)r * P.N;
+    const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
+    const double* __restrict__ vi = (flip ? S.v2 : S.v) + base;
+    const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
+    double* __restrict__ uo = (flip ? S.u : S.u2) + base;
+    double* __restrict__ vo = (flip ? S.v : S.v2) + base;
+    double* __restrict__ ao = (flip ? S.a : S.a2) + base;
+    const double c2 = 0.5 * P.dt * P.dt;
+    const bool act = 2 * t < cnt;
+    const int col = c0 + 2 * t;
+    const int hcol = t == 0 ? (c0 == 0 ? C_ - 1 : c0 - 1) : (c0 + cnt == C_ ? 0 : c0 + cnt);
+    const int hidx = t == 0 ? 1 : 2 + cnt;
+    double uf = S.u_frame[r];
+    if (A.flow) {
+        uf += A.v_frame * P.dt;
+    }
+    if (status != ST_RUNNING) {
+        return;
+    }
+    const unsigned row_bytes = (unsigned)cnt * 8u;
+    auto wrapped = [&](int rr) {
+        const int gr = row0 + rr;
+        return gr < 0 ? gr + R_ : (gr >= R_ ? gr - R_ : gr);
+    };
+    // band row rr = -1 .. nrow lives in stage (rr + 1) % NS
+    auto issue = [&](int rr) {
+        VerletStage& st = stage[(rr + 1) % NS];
+        u64* bar = &full[(rr + 1) % NS];
+        const i64 off = (i64)wrapped(rr) * C_ + c0;
+        const bool wells = rr >= 0 && rr < nrow;
+        mbar_arrive_expect_tx(bar, (wells ? 5u : 3u) * row_bytes);
+        bulk_copy_g2s(st.u, ui + off, row_bytes, bar);
+        bulk_copy_g2s(st.v, vi + off, row_bytes, bar);
+        bulk_copy_g2s(st.a, ai + off, row_bytes, bar);
+        if (wells) {
+            bulk_copy_g2s(st.yl, S.yl + base + off, row_bytes, bar);
+            bulk_copy_g2s(st.yr, S.yr + base + off, row_bytes, bar);
+        }
+    };
+    if (t == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1u);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+        for (int rr = -1; rr < NS - 1 && rr <= nrow; ++rr) {
+            issue(rr);
+        }
+    }
+    // new position (detail.h:1549) of this thread's halo column in band row rr: plain loads
+    auto halo_position = [&](int rr) {
+        const i64 q = (i64)wrapped(rr) * C_ + hcol;
+        return ui[q] + P.dt * vi[q] + c2 * ai[q];
+    };
+    // new positions of band row rr from its stage -> ring slot; returns the own pair
+    auto positions = [&](int rr, double2& un) {
+        const VerletStage& st = stage[(rr + 1) % NS];
+        if (act) {
+            const double2 u2 = *reinterpret_cast<const double2*>(&st.u[2 * t]);
+            const double2 v2 = *reinterpret_cast<const double2*>(&st.v[2 * t]);
+            const double2 a2 = *reinterpret_cast<const double2*>(&st.a[2 * t]);
+            un.x = u2.x + P.dt * v2.x + c2 * a2.x;
+            un.y = u2.y + P.dt * v2.y + c2 * a2.y;
+            *reinterpret_cast<double2*>(&sun[(row0 + rr) & 3][2 + 2 * t]) = un;
+        }
+    };
+    double hp0 = 0.0, hp1 = 0.0, hp2 = 0.0; // halo positions of rows i, i+1, i+2 (threads 0, 1)
+    if (t < 2) {
+        hp0 = halo_position(-1);
+        hp1 = halo_position(0);
+        hp2 = halo_position(1);
+    }
+    double2 un_c = make_double2(0.0, 0.0), un_n = un_c, un_dummy = un_c;
+    mbar_wait(&full[0], 0u);
+    mbar_wait(&full[1 % NS], 0u);
+    positions(-1, un_dummy);
+    positions(0, un_c);
+    if (t < 2) {
+        sun[(row0 + 3) & 3][hidx] = hp0;
+        sun[row0 & 3][hidx] = hp1;
+    }
+
+    double acc[2] = {0.0, 0.0};
+    int hops = 0, dS = 0, dA = 0, underflow = 0;
+    bool nan = false;
+    for (int i = 0; i < nrow; ++i) {
+        const int gi = row0 + i;
+        double hp3 = 0.0;
+        if (t < 2 && i + 2 <= nrow) {
+            hp3 = halo_position(i + 2);
+        }
+        // row i+1 landed? (fill number (i + 2) / NS of its stage)
+        mbar_wait(&full[(i + 2) % NS], (unsigned)(((i + 2) / NS) & 1));
+        positions(i + 1, un_n);
+        if (t < 2) {
+            sun[(gi + 1) & 3][hidx] = hp2;
+        }
+        __syncthreads(); // positions of row i+1 visible; every thread is done with row i-1
+        if (t == 0) {
+            const int rr = i - 1 + NS; // refill the stage of row i-1 (row -1: read in the prologue)
+            if (rr <= nrow) {
+                issue(rr);
+            }
+        }
+        const i64 rowoff = (i64)gi * C_;
+        if (act) {
+            const VerletStage& st = stage[(i + 1) % NS];
+            const double* up = &sun[(gi + 3) & 3][2]; // row i-1
+            const double* mid = &sun[gi & 3][2];
+            const double* dn = &sun[(gi + 1) & 3][2];
+            const double2 v_c = *reinterpret_cast<const double2*>(&st.v[2 * t]);
+            const double2 a_c = *reinterpret_cast<const double2*>(&st.a[2 * t]);
+            const double2 l2 = *reinterpret_cast<const double2*>(&st.yl[2 * t]);
+            const double2 r2 = *reinterpret_cast<const double2*>(&st.yr[2 * t]);
+            double uc[2] = {un_c.x, un_c.y};
+            double wl[2] = {l2.x, l2.y};
+            double wr[2] = {r2.x, r2.y};
+            double vv[2] = {v_c.x, v_c.y};
+            double aa[2] = {a_c.x, a_c.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (uc[e] > wr[e] || !(uc[e] > wl[e])) { // rare: well change, detail.h:144
+                    const i64 gp = base + rowoff + col + e;
+                    u64 st_ = S.rng[gp];
+                    i64 i_before = S.idx[gp];
+                    int moved = well_align(P, uc[e], wl[e], wr[e], st_, i_before, &underflow);
+                    S.rng[gp] = st_;
+                    S.idx[gp] = i_before + moved;
+                    S.yl[gp] = wl[e];
+                    S.yr[gp] = wr[e];
+                    if (rowoff + col + e >= A.own_lo && rowoff + col + e < A.own_hi) {
+                        hops += moved != 0;
+                        track_hop(A, gp, i_before, moved, dS, dA);
+                    }
+                }
+            }
+            const bool own = rowoff + col >= A.own_lo && rowoff + col < A.own_hi; // whole rows
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int lc = 2 * t + e;
+                double fi;
+                if (INT == INT_LAPLACE2D) { // detail.h:557-582 (same operand order)
+                    double lap = up[lc] + dn[lc] + mid[lc - 1] + mid[lc + 1] - 4 * uc[e];
+                    fi = UNIT ? lap : lap * P.k1;
+                }
+                else { // QuarticGradient2d, detail.h:700-711
+                    const double mk4_3 = P.k2 / 3.0;
+                    const double mk4_23 = 2.0 * mk4_3;
+                    const double u_pj = dn[lc], u_mj = up[lc], u_cp = mid[lc + 1], u_cm = mid[lc - 1];
+                    double l = u_pj + u_mj + u_cp + u_cm - 4 * uc[e];
+                    double dudx = 0.5 * (u_pj - u_mj);
+                    double dudy = 0.5 * (u_cp - u_cm);
+                    double d2udxdy = 0.25 * (dn[lc + 1] - dn[lc - 1] - up[lc + 1] + up[lc - 1]);
+                    double d2udx2 = u_pj - 2 * uc[e] + u_mj;
+                    double d2udy2 = u_cp - 2 * uc[e] + u_cm;
+                    fi = l * (P.k1 + mk4_3) + mk4_23 * (dudx * dudx * d2udx2 + dudy * dudy * d2udy2 +
+                                                        2.0 * dudx * dudy * d2udxdy);
+                }
+                double fp = f_potential<POT_CUSPY, UNIT>(P, uc[e], wl[e], wr[e]);
+                double ff = P.k_frame * (uf - uc[e]);
+                double F = ff + fp + fi;
+                double f = verlet_tail<UNIT>(P, F, vv[e], aa[e]);
+                acc[0] += own ? f * f : 0.0;
+                acc[1] += own ? ff * ff : 0.0;
+                nan |= uc[e] != uc[e];
+            }
+            *reinterpret_cast<double2*>(uo + rowoff + col) = un_c;
+            *reinterpret_cast<double2*>(vo + rowoff + col) = make_double2(vv[0], vv[1]);
+            *reinterpret_cast<double2*>(ao + rowoff + col) = make_double2(aa[0], aa[1]);
+        }
+        un_c = un_n;
+        hp2 = hp3;
+    }
+    if (nan) {
+        S.err[1] = 1;
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+    if (finalise) {
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+    }
+}
+
 } // namespace fqsb

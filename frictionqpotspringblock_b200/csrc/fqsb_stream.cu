@@ -142,6 +142,39 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
     if (use_tiled_2d(P)) {
         dim3 grid((unsigned)stream_step_tiles(P, 0), (unsigned)P.R);
         const bool unit = unit_parameters(P);
+        static const bool bulk = [] { // 0: register-staged look-ahead instead of the TMA engine
+            const char* e = std::getenv("FQSB_S2_BULK");
+            return e ? std::atoi(e) != 0 : true;
+        }();
+        if (bulk) {
+            constexpr int NS = 4;
+            const size_t smem = stream_2d_bulk_smem(NS);
+#define FQSB_2D_BULK(inter, unit_) \
+    { \
+        static const cudaError_t attr = cudaFuncSetAttribute( \
+            k_stream_2d_bulk<inter, unit_, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            (int)smem); \
+        if (attr != cudaSuccess) { \
+            return attr; \
+        } \
+        k_stream_2d_bulk<inter, unit_, NS><<<grid, FQSB_S2_THREADS, smem, stream>>>(P, S, A, flip, \
+                                                                                  finalise); \
+        return cudaGetLastError(); \
+    }
+            if (P.inter == INT_LAPLACE2D) {
+                if (unit)
+                    FQSB_2D_BULK(INT_LAPLACE2D, true)
+                else
+                    FQSB_2D_BULK(INT_LAPLACE2D, false)
+            }
+            else {
+                if (unit)
+                    FQSB_2D_BULK(INT_QUARTICGRADIENT2D, true)
+                else
+                    FQSB_2D_BULK(INT_QUARTICGRADIENT2D, false)
+            }
+#undef FQSB_2D_BULK
+        }
         if (P.inter == INT_LAPLACE2D) {
             if (unit)
                 k_stream_2d<INT_LAPLACE2D, true><<<grid, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, finalise);
