@@ -160,6 +160,96 @@ def workload_config(args, R, T, where):
     }
 
 
+def other_configs(F, device, peak):
+    """Short device-timed measurements of BASELINE configs #3, #4, #5 and of the thermal systems
+    (SURVEY section 8f row N4); times are CUDA-event times of the stepping-kernel launches."""
+    out = {}
+    phys = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, dt=0.1, distribution="random",
+                parameters=[2.0], offset=-50, seed=0, device=device)
+
+    def timed_steps(system, n, warm):
+        system.timeSteps(warm)
+        system.timeSteps(n)
+        return system.last_kernel_seconds / n
+
+    try:  # config #3: one Cuspy_Quartic line of 2^20 blocks, temporally blocked kernel (K2b)
+        N = 1 << 20
+        s = F.Line1d.System_Cuspy_Quartic(a1=1.0, a2=1.0, k_frame=1.0 / N, shape=[N], **phys)
+        s.u_frame = 0.5
+        sec = timed_steps(s, 2048, 256)
+        out["config3_line_2p20_quartic"] = {
+            "kernel": s.last_kernel, "us_per_step": 1e6 * sec, "block_updates_per_s": N / sec,
+            "algorithmic_GBps": 64.0 * N / sec / 1e9,
+            "note": "k steps per pass over memory: the algorithmic 64 B per block-update are not "
+                    "DRAM traffic (FP64-pipe bound)"}
+        del s
+    except Exception as e:  # pragma: no cover
+        out["config3_line_2p20_quartic"] = {"error": str(e)}
+    try:  # config #4: LongRange alpha = 1.5, N = 8192 x 1024 realisations (DMMA Toeplitz GEMM)
+        N, R = 8192, 1024
+        s = F.Line1d.Ensemble_Cuspy_LongRange(k_interactions=1.0, alpha=1.5, k_frame=1.0 / N,
+                                              shape=[N], nrealisations=R, **phys)
+        s.u_frame = np.full(R, 0.5)
+        sec = timed_steps(s, 4, 2)
+        out["config4_longrange_8192x1024"] = {
+            "kernel": s.last_kernel, "ms_per_step": 1e3 * sec,
+            "fp64_TFLOPs": 2.0 * N * N * R / sec / 1e12,
+            "block_updates_per_s": N * R / sec}
+        del s
+    except Exception as e:  # pragma: no cover
+        out["config4_longrange_8192x1024"] = {"error": str(e)}
+    try:  # config #5: 4096 x 4096 interface, Verlet step and no-passing sweeps
+        rows = cols = 4096
+        n = rows * cols
+        p2 = dict(phys)
+        s = F.Line2d.System_Cuspy_Laplace(k_interactions=1.0, k_frame=1.0 / n, shape=[rows, cols],
+                                          **p2)
+        s.u_frame = 1.0
+        sec = timed_steps(s, 40, 5)
+        out["config5_line2d_4096_verlet"] = {
+            "kernel": s.last_kernel, "us_per_step": 1e6 * sec, "block_updates_per_s": n / sec,
+            "algorithmic_GBps": 64.0 * n / sec / 1e9, "frac_of_hbm_peak": 64.0 * n / sec / 1e9 / peak}
+        del s
+        for key in ("m", "eta", "dt"):
+            p2.pop(key)
+        s = F.Line2d.System_Cuspy_Laplace_Nopassing(k_interactions=1.0, k_frame=1.0 / n,
+                                                    shape=[rows, cols], **p2)
+        s.u_frame = 1.0
+        steps0 = s.step_count
+        t0 = time.perf_counter()
+        ret = s.minimise(max_iter=2000, max_iter_is_error=False)
+        wall = time.perf_counter() - t0
+        sweeps = int(s.step_count - steps0)
+        # sweeps at the fixed point move no block between wells: the streaming rate of the kernel
+        s.minimise(tol=1e-300, max_iter=60, max_iter_is_error=False)
+        per = s.last_kernel_seconds / max(1, s.last_kernel_launches)
+        out["config5_line2d_4096_nopassing"] = {
+            "kernel": s.last_kernel, "minimise_ret": int(ret), "minimise_sweeps": sweeps,
+            "minimise_wall_ms": 1e3 * wall, "us_per_sweep_at_fixed_point": 1e6 * per,
+            "block_updates_per_s": n / per, "algorithmic_GBps": 32.0 * n / per / 1e9,
+            "frac_of_hbm_peak": 32.0 * n / per / 1e9 / peak}
+        del s
+    except Exception as e:  # pragma: no cover
+        out["config5_line2d_4096"] = {"error": str(e)}
+    try:  # thermal systems (External = RandomNormalForcing), flowSteps
+        for label, N, R, steps in (("thermal_example_N1000", 1000, 1, 2000),
+                                   ("thermal_ensemble_1024x4096", 4096, 1024, 200)):
+            rng = np.random.default_rng(0)
+            s = F.Line1d.Ensemble_Cuspy_Laplace_RandomForcing(
+                k_interactions=1.0, k_frame=1.0 / N, shape=[N], nrealisations=R, mean=0.0,
+                stddev=0.05, seed_forcing=0, dinc_init=rng.integers(0, 100, N),
+                dinc=100 * np.ones(N, dtype=np.int64), **phys)
+            s.flowSteps(steps, 5e-2)
+            s.flowSteps(steps, 5e-2)
+            sec = s.last_kernel_seconds / steps
+            out[label] = {"kernel": s.last_kernel, "us_per_step": 1e6 * sec,
+                          "block_updates_per_s": N * R / sec}
+            del s
+    except Exception as e:  # pragma: no cover
+        out["thermal"] = {"error": str(e)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +262,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-events", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-timed lines of BASELINE configs #3-#5 and the "
+                         "thermal systems")
     ap.add_argument("--pipeline", type=int, default=8, help="handles of the pipelined e2e arm")
     args = ap.parse_args()
 
@@ -422,7 +515,8 @@ def main():
     #      the next instability + kick + minimise, on every realisation of a fresh ensemble
     events = None
     if not args.no_events:
-        Re = min(R, 4096)
+        Re = R  # the whole ensemble of the named config (a longer work queue hides the tail of
+        #         the realisations with the longest avalanches)
         ens3 = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=Re, seed=rank * R * N,
                                                device=local_rank, **kw)
         ens3.set_stream(stream.cuda_stream)
@@ -443,6 +537,12 @@ def main():
                   "mean_minimise_steps": (ens3.step_count - steps0) / (Re * nev),
                   "block_updates_per_s": world * (ens3.step_count - steps0) * N / ev_sec}
         del ens3
+
+    # ---- the other BASELINE configs and the thermal systems (rank 0, device-timed kernel
+    #      launches, short): reported next to the headline, not part of `value`
+    other = None
+    if rank == 0 and not args.no_other_configs:
+        other = other_configs(F, local_rank, peak)
 
     # ---- CPU baseline (rank 0): the oracle port on all host cores, bounded sample
     cpu = None
@@ -484,6 +584,7 @@ def main():
                     "single_handle": {"value": e2e1_value, "ms_per_step": 1e3 * e2e1_sec / K}},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
             "quasistatic_events": events,
+            "other_configs": other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

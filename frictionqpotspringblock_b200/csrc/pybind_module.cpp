@@ -261,6 +261,49 @@ PYBIND11_MODULE(_FrictionQPotSpringBlock, m)
             mySystemNdDynamics(cls);
         }
     }
+    { // main.cpp:279-470
+        py::module sm = m.def_submodule("Particles", "Particles");
+        namespace SM = M::Particles;
+        using S1 = const std::array<size_t, 1>&;
+        using Str = const std::string&;
+        using Par = const std::vector<double>&;
+        using Inc = const std::vector<int64_t>&;
+        {
+            py::class_<SM::System_Cuspy, System> cls(sm, "System_Cuspy");
+            cls.def(py::init<double, double, double, double, double, S1, uint64_t, Str, Par,
+                             double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k_frame"),
+                    py::arg("dt"), FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+        }
+        {
+            using S = SM::System_Cuspy_RandomForcing;
+            py::class_<S, System> cls(sm, "System_Cuspy_RandomForcing");
+            cls.def(py::init<double, double, double, double, double, double, double, uint64_t,
+                             Inc, Inc, S1, uint64_t, Str, Par, double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k_frame"),
+                    py::arg("dt"), py::arg("mean"), py::arg("stddev"), py::arg("seed_forcing"),
+                    py::arg("dinc_init"), py::arg("dinc"), FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+            mySystemNdExternal<decltype(cls), S>(cls);
+        }
+        {
+            py::class_<SM::System_SemiSmooth, System> cls(sm, "System_SemiSmooth");
+            cls.def(py::init<double, double, double, double, double, double, S1, uint64_t, Str,
+                             Par, double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("kappa"),
+                    py::arg("k_frame"), py::arg("dt"), FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+        }
+        {
+            py::class_<SM::System_Smooth, System> cls(sm, "System_Smooth");
+            cls.def(py::init<double, double, double, double, double, S1, uint64_t, Str, Par,
+                             double, size_t>(),
+                    py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k_frame"),
+                    py::arg("dt"), FQSB_COMMON_ARGS);
+            mySystemNdDynamics(cls);
+        }
+    }
     {
         py::module sm = m.def_submodule("Line2d", "Line2d");
         namespace SM = M::Line2d;

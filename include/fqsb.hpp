@@ -488,6 +488,81 @@ public:
 
 } // namespace Line1d
 
+/** Particles.h:93-311: independent particles (no interactions) */
+namespace Particles {
+
+#define FQSB_SHAPE1 std::vector<size_t>{shape[0]}
+
+/** Particles.h:93-135 */
+class System_Cuspy : public detail::System {
+public:
+    System_Cuspy(double m, double eta, double mu, double k_frame, double dt,
+                 const std::array<size_t, 1>& shape, uint64_t seed,
+                 const std::string& distribution, const std::vector<double>& parameters,
+                 double offset = -100.0, size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_CUSPY, FQSB_INT_NONE, FQSB_MIN_DYNAMIC, FQSB_SHAPE1, m, eta, mu, 0.0,
+                   0.0, 0.0, k_frame, dt, seed, distribution, parameters, offset, nchunk);
+    }
+};
+
+/** Particles.h:161-230 */
+class System_Cuspy_RandomForcing : public detail::System {
+public:
+    System_Cuspy_RandomForcing(double m, double eta, double mu, double k_frame, double dt,
+                               double mean, double stddev, uint64_t seed_forcing,
+                               const std::vector<int64_t>& dinc_init,
+                               const std::vector<int64_t>& dinc,
+                               const std::array<size_t, 1>& shape, uint64_t seed,
+                               const std::string& distribution,
+                               const std::vector<double>& parameters, double offset = -100.0,
+                               size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_CUSPY, FQSB_INT_NONE, FQSB_MIN_NONE, FQSB_SHAPE1, m, eta, mu, 0.0, 0.0,
+                   0.0, k_frame, dt, seed, distribution, parameters, offset, nchunk);
+        initForcing(mean, stddev, seed_forcing, dinc_init, dinc);
+    }
+    const detail::RandomNormalForcing& external() const { return m_external; }
+    detail::RandomNormalForcing& external() { return m_external; }
+
+protected:
+    using detail::System::eventDrivenStep;
+    using detail::System::quasistaticActivityFirst;
+    using detail::System::quasistaticActivityLast;
+};
+
+/** Particles.h:233-270 (runs the SemiSmooth_Laplace kernels with k_interactions = 0: the
+ *  interaction term is an exact zero) */
+class System_SemiSmooth : public detail::System {
+public:
+    System_SemiSmooth(double m, double eta, double mu, double kappa, double k_frame, double dt,
+                      const std::array<size_t, 1>& shape, uint64_t seed,
+                      const std::string& distribution, const std::vector<double>& parameters,
+                      double offset = -100.0, size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_SEMISMOOTH, FQSB_INT_LAPLACE1D, FQSB_MIN_DYNAMIC, FQSB_SHAPE1, m, eta,
+                   mu, kappa, 0.0, 0.0, k_frame, dt, seed, distribution, parameters, offset,
+                   nchunk);
+    }
+};
+
+/** Particles.h:276-311 (Smooth_Laplace kernels with k_interactions = 0) */
+class System_Smooth : public detail::System {
+public:
+    System_Smooth(double m, double eta, double mu, double k_frame, double dt,
+                  const std::array<size_t, 1>& shape, uint64_t seed,
+                  const std::string& distribution, const std::vector<double>& parameters,
+                  double offset = -100.0, size_t nchunk = 5000)
+    {
+        initSystem(FQSB_POT_SMOOTH, FQSB_INT_LAPLACE1D, FQSB_MIN_DYNAMIC, FQSB_SHAPE1, m, eta, mu,
+                   0.0, 0.0, 0.0, k_frame, dt, seed, distribution, parameters, offset, nchunk);
+    }
+};
+
+#undef FQSB_SHAPE1
+
+} // namespace Particles
+
 namespace Line2d {
 
 #define FQSB_SHAPE2 std::vector<size_t>{shape[0], shape[1]}

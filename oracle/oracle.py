@@ -486,6 +486,8 @@ Line1d.System_Cuspy_Quartic_RandomForcing = _mk("Cuspy", "Quartic1d", "a1", "a2"
 # Particles.h:93-135 (no interactions)
 Particles.System_Cuspy = _mk("Cuspy", "None")
 Particles.System_Cuspy_RandomForcing = _mk("Cuspy", "None", minimisation=2, forcing=True)
+Particles.System_SemiSmooth = _mk("SemiSmooth", "None", kappa=True)  # Particles.h:233-270
+Particles.System_Smooth = _mk("Smooth", "None")  # Particles.h:276-311
 # Line2d.h:77-162 (+ the new 2-D no-passing system)
 Line2d.System_Cuspy_Laplace = _mk("Cuspy", "Laplace2d", "k_interactions")
 Line2d.System_Cuspy_QuarticGradient = _mk("Cuspy", "QuarticGradient2d", "k2", "k4")

@@ -60,6 +60,9 @@ def test_pybind_module_builds_and_refuses_without_gpu():
                  "System_Cuspy_Laplace_RandomForcing", "System_Cuspy_Quartic_RandomForcing"):
         assert hasattr(P.Line1d, name)
     assert hasattr(P.detail, "RandomNormalForcing_1")
+    for name in ("System_Cuspy", "System_Cuspy_RandomForcing", "System_SemiSmooth",
+                 "System_Smooth"):
+        assert hasattr(P.Particles, name)
     assert hasattr(P.Line2d, "System_Cuspy_Laplace")
     import frictionqpotspringblock_b200 as F
 
