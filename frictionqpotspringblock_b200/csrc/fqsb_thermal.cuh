@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(T + 32)
             const double fp = f_potential<POT_CUSPY, UNIT>(P, uc, yl[j], yr[j]);
             const double ff = P.k_frame * (uf - uc);
             const double F = ff + fp + fi;
-            verlet_tail_thermal<UNIT>(P, F, fth[pc], v[j], a[j]);
+            // (a clamped thread must not read block N-1's entry: its owner may be rewriting it)
+            const double ft = (FULL || p < N) ? fth[(FULL || p < N) ? p : 0] : 0.0;
+            verlet_tail_thermal<UNIT>(P, F, ft, v[j], a[j]);
         }
     };
     auto phase2 = [&](const int ocur) {

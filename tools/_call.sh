@@ -1,11 +1,7 @@
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_gpu_particles.py tests/test_cpp_host.py -x -q > gpurun_out/pytest_part.log 2>&1; echo rc=$? >> gpurun_out/pytest_part.log)
-tail -15 gpurun_out/pytest_part.log
-( time timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ) 2> gpurun_out/bench.time
-tail -3 gpurun_out/bench.err; cat gpurun_out/bench.time
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
-print(json.dumps(d.get('other_configs'), indent=1))
-print(d['value'], d['e2e']['value'], d['quasistatic_events']['value'], d['roofline_stream']['frac'])
-PY
+export PYTHONDONTWRITEBYTECODE=1
+(timeout 500 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_gpu_thermal.py -x -q -k "test_thermal_extreme_schedules or test_external_setters or test_reference_test_interactions" > gpurun_out/san_race_thermal.log 2>&1; echo rc=$? >> gpurun_out/san_race_thermal.log)
+tail -4 gpurun_out/san_race_thermal.log
+(timeout 600 compute-sanitizer --tool racecheck --print-limit 10 python -m pytest tests/test_gpu_parity.py -x -q -k "test_fixed_steps_line2d or test_minimise_and_event_driven_match_oracle or test_tiny_lines" > gpurun_out/san_race_parity.log 2>&1; echo rc=$? >> gpurun_out/san_race_parity.log)
+tail -4 gpurun_out/san_race_parity.log
+grep -c "Error: Race" gpurun_out/san_race_parity.log
