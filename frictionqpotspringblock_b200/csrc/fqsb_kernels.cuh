@@ -1866,11 +1866,21 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
             issue(rr);
         }
     }
-    // new position (detail.h:1549) of this thread's halo column in band row rr: plain loads
-    auto halo_position = [&](int rr) {
-        const i64 q = (i64)wrapped(rr) * C_ + hcol;
-        return ui[q] + P.dt * vi[q] + c2 * ai[q];
+    // raw state of this thread's halo column in band row rr (plain loads, threads 0 and 1); the
+    // new position (detail.h:1549) is formed one row later, so the loads are never waited for
+    // in the row that issues them (warp 0 would hold up the barrier of every row)
+    struct Halo {
+        double u, v, a;
     };
+    auto halo_load = [&](int rr) {
+        const i64 q = (i64)wrapped(rr) * C_ + hcol;
+        Halo h;
+        h.u = ui[q];
+        h.v = vi[q];
+        h.a = ai[q];
+        return h;
+    };
+    auto halo_position = [&](const Halo& h) { return h.u + P.dt * h.v + c2 * h.a; };
     // new positions of band row rr from its stage -> ring slot; returns the own pair
     auto positions = [&](int rr, double2& un) {
         const VerletStage& st = stage[(rr + 1) % NS];
@@ -1883,11 +1893,11 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
             *reinterpret_cast<double2*>(&sun[(row0 + rr) & 3][2 + 2 * t]) = un;
         }
     };
-    double hp0 = 0.0, hp1 = 0.0, hp2 = 0.0; // halo positions of rows i, i+1, i+2 (threads 0, 1)
+    Halo hm = {0.0, 0.0, 0.0}, h0 = hm, h1 = hm, h2 = hm; // rows -1, 0, then rows i+1, i+2
     if (t < 2) {
-        hp0 = halo_position(-1);
-        hp1 = halo_position(0);
-        hp2 = halo_position(1);
+        hm = halo_load(-1);
+        h0 = halo_load(0);
+        h1 = halo_load(1);
     }
     double2 un_c = make_double2(0.0, 0.0), un_n = un_c, un_dummy = un_c;
     mbar_wait(&full[0], 0u);
@@ -1895,8 +1905,8 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
     positions(-1, un_dummy);
     positions(0, un_c);
     if (t < 2) {
-        sun[(row0 + 3) & 3][hidx] = hp0;
-        sun[row0 & 3][hidx] = hp1;
+        sun[(row0 + 3) & 3][hidx] = halo_position(hm);
+        sun[row0 & 3][hidx] = halo_position(h0);
     }
 
     double acc[2] = {0.0, 0.0};
@@ -1904,15 +1914,14 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
     bool nan = false;
     for (int i = 0; i < nrow; ++i) {
         const int gi = row0 + i;
-        double hp3 = 0.0;
         if (t < 2 && i + 2 <= nrow) {
-            hp3 = halo_position(i + 2);
+            h2 = halo_load(i + 2);
         }
         // row i+1 landed? (fill number (i + 2) / NS of its stage)
         mbar_wait(&full[(i + 2) % NS], (unsigned)(((i + 2) / NS) & 1));
         positions(i + 1, un_n);
         if (t < 2) {
-            sun[(gi + 1) & 3][hidx] = hp2;
+            sun[(gi + 1) & 3][hidx] = halo_position(h1); // loaded one row ago
         }
         __syncthreads(); // positions of row i+1 visible; every thread is done with row i-1
         if (t == 0) {
@@ -1988,7 +1997,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
             *reinterpret_cast<double2*>(ao + rowoff + col) = make_double2(aa[0], aa[1]);
         }
         un_c = un_n;
-        hp2 = hp3;
+        h1 = h2;
     }
     if (nan) {
         S.err[1] = 1;
