@@ -1674,7 +1674,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
             stage[sp].u[hidx] = h2;
         }
         __syncthreads(); // halos of row i+1 visible; every thread is done with row i-1
-        if (t == 0 && i >= 1) {
+        if (t == FQSB_S2_THREADS - 32 && i >= 1) { // (not warp 0: it already feeds the halos)
             const int rr = i - 2 + NS; // refill the stage of row i-2 (last read by row i-1)
             if (rr <= nrow) {
                 issue(rr);
@@ -1924,7 +1924,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
             sun[(gi + 1) & 3][hidx] = halo_position(h1); // loaded one row ago
         }
         __syncthreads(); // positions of row i+1 visible; every thread is done with row i-1
-        if (t == 0) {
+        if (t == FQSB_S2_THREADS - 32) { // (not warp 0: it already feeds the halo columns)
             const int rr = i - 1 + NS; // refill the stage of row i-1 (row -1: read in the prologue)
             if (rr <= nrow) {
                 issue(rr);
