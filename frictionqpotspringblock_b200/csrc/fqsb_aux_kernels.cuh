@@ -74,7 +74,7 @@ __global__ void k_stream_settle_flags(const Par P, const State S)
 // ahead of a time step (m_inc++ comes first, detail.h:1541-1544), 0 for refresh()/set_inc();
 // `only_running`: skip realisations whose stepping call has already ended.
 // normal(mu, sigma) = mu + sigma*sqrt(2)*erf_inv(2r - 1), r = next_double() (prrng; the device
-// uses CUDA's erfinv, <= 5 ulp from boost's long-double evaluation).
+// uses erf_inv_dev, a few 1e-16 relative from boost's long-double evaluation).
 // =============================================================================================
 __global__ void __launch_bounds__(1024) k_thermal_draw(const Par P, const State S, const Thermal T,
                                                        int inc_add, int only_running)
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(1024) k_thermal_draw(const Par P, const State 
                 const u64 rank = carry + (u64)wexcl[warp] + (u64)__popc(bal & ((1u << lane) - 1u));
                 const u64 st = pcg_advance_inc(st0, rank, T.inc_rng);
                 const double z = pcg_double(st);
-                val = T.mean + T.sigma_sqrt2 * erfinv(2.0 * z - 1.0);
+                val = T.mean + T.sigma_sqrt2 * erf_inv_dev(2.0 * z - 1.0);
                 T.f_ext[base + p] = val;
                 T.next[base + p] += T.dinc[base + p];
             }

@@ -223,6 +223,80 @@ __host__ __device__ inline u64 pcg_seed_seq(u64 initstate, u64 initseq, u64* inc
     return s;
 }
 
+// ---- erf_inv for prrng::pcg32::normal (thermal systems) ------------------------------------------
+// normal(mu, sigma) = mu + sigma*sqrt(2)*erf_inv(2r - 1). With w = -log(1 - z^2):
+//   erf_inv(z) = z * p(w - 3.125)          w < 6.25   (|z| < 0.99903)
+//              = z * q(sqrt(w) - 3.25)     w < 16
+//              = z * s(sqrt(w) - 4.35)     w <= 22    (prrng's doubles: |z| <= 1 - 2^-31, w < 20.8)
+// (the decomposition of M. Giles, "Approximating the erfinv function", GPU Computing Gems 2011).
+// The polynomials are Chebyshev interpolants of degree 24 / 20 / 12 fitted here against a
+// 50-digit erfinv (tools/erfinv_fit.py): max relative error 2.8e-16 / 2.7e-16 / 4.6e-16 when
+// evaluated in double. Even and odd parts are two independent FMA chains: the producer warp of the
+// thermal kernel waits on the latency of this function once per step, not on its throughput.
+// centre 3.125
+__device__ const double kErfInvCentral[25] = {
+    1.6536545626831027, 0.24015818242558834, -0.006033670871426851,
+    -0.0007407025341546431, 0.00018673420801981186, -1.3882523393957483e-05,
+    -1.3654691758785656e-06, 4.23478816822246e-07, -2.907039127564132e-08,
+    -4.1126604371632185e-09, 1.051223377050429e-09, -5.414303283919504e-11,
+    -1.2978805369932565e-11, 2.6305268312595183e-12, -8.07192593899004e-14,
+    -4.0020031087558496e-14, 6.521333511502239e-15, -3.94018812230432e-17,
+    -1.2215637192404172e-16, 1.5510787009902526e-17, 6.075050702072414e-19,
+    -3.4734793888538036e-19, 1.999259988861535e-20, 3.194015548136271e-21,
+    -3.5932028927020693e-22};
+
+// centre 3.25
+__device__ const double kErfInvMid[21] = {
+    3.0838856104922208, 1.0052589676941655, 0.005370914553555033,
+    -0.0037512085082247342, 0.00249144209795696, -0.0016882755354488555,
+    0.0009532893415794137, -0.0003550378137852452, 2.4031512865758357e-05,
+    6.828711739251955e-05, -4.732068066544697e-05, 1.2465028224217455e-05,
+    2.93257845538535e-06, -3.985705945648173e-06, 1.4815977874022539e-06,
+    -2.761716223816241e-08, -2.4549818963339823e-07, 1.3158663683192966e-07,
+    -2.091453334773126e-08, -1.5305397964152548e-08, 7.680200479077053e-09};
+
+// centre 4.35
+__device__ const double kErfInvFar[13] = {
+    4.193227791584444, 1.0101034080837366, 0.0005424991500763608,
+    -0.000529058407104589, 0.00018294384014653055, -5.308491165471322e-05,
+    1.62270677686947e-05, -6.545270788708373e-06, 3.507615965115579e-06,
+    -1.9824451116752552e-06, 9.905280208516674e-07, -3.934390741898877e-07,
+    9.900018726096847e-08};
+
+template <int N>
+__device__ __forceinline__ double poly_even_odd(const double (&c)[N], double t)
+{
+    const double t2 = t * t;
+    constexpr int TOP_E = (N - 1) & ~1;            // highest even index
+    constexpr int TOP_O = ((N - 1) & 1) ? N - 1 : N - 2; // highest odd index
+    double e = c[TOP_E], o = c[TOP_O];
+#pragma unroll
+    for (int k = TOP_E - 2; k >= 0; k -= 2) {
+        e = fma(e, t2, c[k]);
+    }
+#pragma unroll
+    for (int k = TOP_O - 2; k >= 1; k -= 2) {
+        o = fma(o, t2, c[k]);
+    }
+    return fma(o, t, e);
+}
+
+__device__ __forceinline__ double erf_inv_dev(double z)
+{
+    const double w = -log((1.0 - z) * (1.0 + z));
+    double p;
+    if (w < 6.25) {
+        p = poly_even_odd(kErfInvCentral, w - 3.125);
+    }
+    else if (w < 16.0) {
+        p = poly_even_odd(kErfInvMid, sqrt(w) - 3.25);
+    }
+    else {
+        p = poly_even_odd(kErfInvFar, sqrt(w) - 4.35);
+    }
+    return p * z;
+}
+
 // ---- distributions -> yield spacing ------------------------------------
 enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DIST_GAMMA = 4,
        DIST_PARETO = 5, DIST_WEIBULL = 6, DIST_NORMAL = 7 };

@@ -15,10 +15,10 @@
 //       publish one ballot word per (slice j, warp) -- block order is (j, warp, lane);
 //   producer warp, after that barrier: scans the popcounts of the <= 128 words, writes the due
 //       blocks in rank order into a list, then walks the list 32 draws at a time: LCG jump by
-//       the rank (tabulated coefficients), uniform -> normal (erfinv), value into fnew[parity];
+//       the rank (tabulated coefficients), uniform -> normal (erf_inv_dev), value into fnew[parity];
 //   integrator warps, after the barrier of step s+1: copy fnew into fth for the blocks they
 //       know to be due, and integrate.
-// The ~150-instruction erfinv chain thus runs beside the integration instead of in it, once per
+// The erf_inv chain thus runs beside the integration instead of in it, once per
 // 32 draws instead of once per warp that owns a due block, and the step keeps its one barrier.
 #pragma once
 
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(T + 32)
                 const u64 st = k < FQSB_TH_JUMPS ? jm[k] * st0 + jp[k]
                                                  : pcg_advance_inc(st0, (u64)k, TH.inc_rng);
                 fnew[(size_t)par * N + p] =
-                    TH.mean + TH.sigma_sqrt2 * erfinv(2.0 * pcg_double(st) - 1.0);
+                    TH.mean + TH.sigma_sqrt2 * erf_inv_dev(2.0 * pcg_double(st) - 1.0);
             }
             st0 = total < FQSB_TH_JUMPS ? jm[total] * st0 + jp[total]
                                         : pcg_advance_inc(st0, (u64)total, TH.inc_rng);

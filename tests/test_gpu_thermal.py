@@ -3,7 +3,7 @@ N4; /root/reference/include/FrictionQPotSpringBlock/detail.h:881-1000, Line1d.h:
 
 The schedule (`next`), the generator state and the well indices are integers: bit-exact against
 the oracle. The random forces go through erf_inv -- the oracle restates boost's long-double
-evaluation, the device uses CUDA's double-precision erfinv (<= 5 ulp) -- so forces and the
+evaluation, the device uses its own double-precision erf_inv_dev (a few 1e-16) -- so forces and the
 trajectory are compared at 1e-12 of their scale (BASELINE.json north_star), the reference's own
 golden with the reference's own np.allclose.
 """
@@ -120,7 +120,7 @@ def test_thermal_extreme_schedules(kernel):
 
 
 def test_thermal_resident_equals_streaming_bitwise():
-    """both device paths draw through the same erfinv: identical bits, sparse schedule
+    """both device paths draw through the same erf_inv_dev: identical bits, sparse schedule
     (dinc = 100 as in the reference's example) over several launches"""
     F = product()
     N = 1000
@@ -170,6 +170,25 @@ def test_external_setters_and_set_inc():
     with pytest.raises(AttributeError):
         F.Line1d.System_Cuspy_Laplace(shape=[N], k_frame=1.0 / N, k_interactions=1.0,
                                       **PHYS).external
+
+
+def test_device_normal_draws_accuracy():
+    """2.6e5 draws of the device's erf_inv (Chebyshev fits, tools/erfinv_fit.py) against the
+    oracle's long-double solve: a few 1e-16 relative, tails included"""
+    F = product()
+    N, R = 4096, 64
+    kw = dict(shape=[N], k_frame=1.0 / N, k_interactions=1.0, **PHYS)
+    ens = F.Line1d.Ensemble_Cuspy_Laplace_RandomForcing(
+        nrealisations=R, mean=0.0, stddev=1.0, seed_forcing=123, dinc_init=np.ones(N, dtype=int),
+        dinc=np.ones(N, dtype=int), **kw)
+    ens.timeStep()
+    got = ens.external.f_thermal
+    worst = 0.0
+    for r in range(R):
+        ref = orc.pcg32_normal(123 + r, N, 0.0, 1.0)
+        worst = max(worst, np.max(np.abs(got[r] - ref) / np.abs(ref)))
+    assert worst < 2e-15, worst
+    assert np.abs(got).max() > 4.0  # the sample reaches the tails
 
 
 def test_thermal_ensemble_equals_independent_systems():
