@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_thermal.py -x -q > gpurun_out/pytest_thermal.log 2>&1; echo rc=$? >> gpurun_out/pytest_thermal.log)
-tail -12 gpurun_out/pytest_thermal.log
-timeout 200 python tools/thermal_bench.py 2>&1 | tail -2
+(timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo rc=$? >> gpurun_out/pytest.log)
+tail -4 gpurun_out/pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -2 gpurun_out/bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['e2e']['value'], d['quasistatic_events']['value'], d['roofline_stream']['frac'], d['gpu_launches'])
+PY
