@@ -93,9 +93,14 @@ int plan_band_rows(const Par& P, int resident, double halo, int max_tiles)
         return 0;
     }
     const int strips = (P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX;
-    int best = FQSB_S2_TY;
+    // fewest rows per band that keep strips x bands within max_tiles (very large interfaces)
+    const int max_bands = max_tiles / strips > 0 ? max_tiles / strips : 1;
+    const int ty_min = (P.rows + max_bands - 1) / max_bands;
+    const int ty_lo = ty_min > 8 ? ty_min : 8;
+    const int ty_hi = 2 * ty_lo > 128 ? 2 * ty_lo : 128;
+    int best = ty_lo;
     double best_cost = 1e300;
-    for (int ty = 8; ty <= 128; ++ty) {
+    for (int ty = ty_lo; ty <= ty_hi; ++ty) {
         const int bands = (P.rows + ty - 1) / ty;
         if (strips * bands > max_tiles) {
             continue;
