@@ -452,6 +452,14 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
         TRY(dev_alloc(s, &S.ctl, (size_t)s->R));
         TRY(dev_alloc(s, &S.err, 2));
         S.tiles = (int)grid_for(s->N);
+        {
+            // the tiled 1-D step uses one CTA per FQSB_ST_TILE blocks: the partial-sum buffer
+            // must cover it for lines beyond 148 * 16 tiles (N > 4.8e6 with the streaming kernel)
+            const i64 tiled = (s->N + FQSB_ST_TILE - 1) / FQSB_ST_TILE;
+            if (P.rank == 1 && tiled > S.tiles) {
+                S.tiles = (int)tiled;
+            }
+        }
         if (P.rank == 2) {
             // k_stream_2d: 2 CTAs per SM (126 registers), 2 halo rows of u,v,a = 0.75 rows of
             // traffic per band; k_stream_np_2d: FQSB_S2_NP_CTAS CTAs per SM, 2 halo rows of u = 0.5 rows
