@@ -31,6 +31,15 @@ def make_sharded(cls, total_realisations: int, rank: int, world: int, *, seed: i
     """Construct this rank's shard of an ``Ensemble_*`` class."""
     first, count = shard_realisations(total_realisations, rank, world)
     size = int(np.prod(kw["shape"]))
+    if "seed_forcing" in kw:
+        # thermal ensembles: realisation r draws its random forces from
+        # pcg32(seed_forcing + r * seed_forcing_stride); per-realisation schedules are sliced
+        stride = int(kw.get("seed_forcing_stride", 1) or 1)
+        kw["seed_forcing"] = int(kw["seed_forcing"]) + first * stride
+        for key in ("dinc_init", "dinc"):
+            arr = np.asarray(kw[key])
+            if arr.ndim == len(kw["shape"]) + 1:
+                kw[key] = arr[first:first + count]
     return cls(nrealisations=count, seed=shard_seed(seed, first, size), **kw), first, count
 
 

@@ -85,3 +85,27 @@ def test_world_size_2_gloo_gather_matches_unsharded(tmp_path):
         uf[r] = s.u_frame
     assert np.array_equal(got["S"], S)
     assert np.array_equal(got["uf"], uf)
+
+
+def test_make_sharded_passes_disjoint_seeds_and_forcing():
+    """make_sharded hands every rank its realisations' disorder seeds and, for thermal ensembles,
+    their forcing seeds and schedule slices (host logic only: a recording stand-in for the class)"""
+    from frictionqpotspringblock_b200.distributed import make_sharded
+
+    class Recorder:
+        def __init__(self, **kw):
+            self.kw = kw
+
+    N, total = 8, 5
+    dinc_init = np.arange(total * N).reshape(total, N)
+    seen = []
+    for rank in range(2):
+        obj, first, count = make_sharded(Recorder, total, rank, 2, seed=7, shape=[N],
+                                         seed_forcing=100, dinc_init=dinc_init,
+                                         dinc=np.ones(N, dtype=int))
+        assert obj.kw["nrealisations"] == count and obj.kw["seed"] == 7 + first * N
+        assert obj.kw["seed_forcing"] == 100 + first
+        assert np.array_equal(obj.kw["dinc_init"], dinc_init[first:first + count])
+        assert obj.kw["dinc"].shape == (N,)  # a shared schedule is passed through
+        seen += list(range(first, first + count))
+    assert seen == list(range(total))
