@@ -115,7 +115,10 @@ SIGNATURES = {
     "fqsb_chunk_data": (C.c_int, [_P, _P, C.c_int64, _P]),
     "fqsb_chunk_state_at": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fqsb_chunk_restore": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
-    "fqsb_avalanche": (C.c_int, [_P, _P, _P, _P]),
+    "fqsb_avalanche": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    "fqsb_mark_indices": (C.c_int, [_P]),
+    "fqsb_avalanche_since_mark": (C.c_int, [_P, _P, _P]),
+    "fqsb_event_record": (C.c_int, [_P, _P, _P, _P, _P]),
     "fqsb_set_owned_range": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "fqsb_logged_steps": (C.c_int, [_P, C.c_int64, _P]),
     "fqsb_snapshot": (C.c_int, [_P]),
@@ -123,7 +126,19 @@ SIGNATURES = {
     "fqsb_export_cells": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int]),
     "fqsb_import_cells": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int]),
     "fqsb_advance_uniformly": (C.c_int, [_P, _P, _P]),
-    "fqsb_reduce_sums": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "fqsb_reduce_sums": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "fqsb_slab_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.c_int]),
+    "fqsb_slab_ipc_handle": (C.c_int, [_P, _P]),
+    "fqsb_slab_connect": (C.c_int, [_P, _P, _P]),
+    "fqsb_slab_info": (C.c_int, [_P, _P]),
+    "fqsb_slab_exchange": (C.c_int, [_P, C.c_int]),
+    "fqsb_slab_time_steps": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_double]),
+    "fqsb_slab_minimise": (C.c_int, [_P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_int64,
+                                     C.c_int, _P, _P]),
+    "fqsb_slab_sums": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "fqsb_slab_mark_indices": (C.c_int, [_P, C.c_int]),
+    "fqsb_slab_event_driven_step": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_int, _P]),
+    "fqsb_slab_first_stop": (C.c_int64, [_P, C.c_int64, C.c_double, C.c_int64, _P, _P]),
     "fqsb_enable_random_forcing": (C.c_int, [_P, C.c_double, C.c_double, C.c_uint64, C.c_int64,
                                              _P, _P, C.c_int64]),
     "fqsb_external_get_f_thermal": (C.c_int, [_P, _P, C.c_int64]),

@@ -34,6 +34,8 @@ def _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
     p.seed = int(seed)
     p.distribution = _capi.DIST[distribution]
     parameters = [float(i) for i in parameters]
+    if len(parameters) > 4:
+        raise RuntimeError("at most 4 distribution parameters")
     p.nparameters = len(parameters)
     for k, val in enumerate(parameters[:4]):
         p.parameters[k] = val
@@ -367,10 +369,33 @@ class Ensemble:
         """(S, A) per realisation since ``i_n``: S = sum(i - i_n), A = #(i != i_n), reduced on
         the device (what examples/Line1d_Cuspy_Laplace.py:61 computes on the host)."""
         i_n = np.ascontiguousarray(i_n, dtype=np.int64)
+        if i_n.shape != self._user_shape:
+            raise RuntimeError("assertion failed (xt::has_shape(i_n, m_u.shape()))")
         S = np.empty(self._R, dtype=np.int64)
         A = np.empty(self._R, dtype=np.int64)
-        check(lib.fqsb_avalanche(self._h, i_n.ctypes.data, S.ctypes.data, A.ctypes.data))
+        check(lib.fqsb_avalanche(self._h, i_n.ctypes.data, i_n.size, S.ctypes.data,
+                                 A.ctypes.data))
         return self._scalar(S), self._scalar(A)
+
+    def mark_indices(self):
+        """Keep ``i_n = system.chunk.index_at_align`` on the device:
+        the start of an event, against which :meth:`avalanche_since_mark` reduces S and A."""
+        check(lib.fqsb_mark_indices(self._h))
+
+    def avalanche_since_mark(self):
+        """(S, A) per realisation since :meth:`mark_indices`, reduced on the device: nothing of
+        size R*N crosses PCIe (examples/Line1d_Cuspy_Laplace.py:59-61 without the host arrays)."""
+        S = np.empty(self._R, dtype=np.int64)
+        A = np.empty(self._R, dtype=np.int64)
+        check(lib.fqsb_avalanche_since_mark(self._h, S.ctypes.data, A.ctypes.data))
+        return self._scalar(S), self._scalar(A)
+
+    def event_record(self):
+        """(sum |i - i_n|, #(i != i_n), quasistaticActivityFirst, quasistaticActivityLast) of the
+        last ``minimise(time_activity=True)`` / ``minimise_truncate`` (detail.h:1768-1778)."""
+        out = [np.empty(self._R, dtype=np.int64) for _ in range(4)]
+        check(lib.fqsb_event_record(self._h, *[o.ctypes.data for o in out]))
+        return tuple(self._scalar(o) for o in out)
 
     # ---- dynamics (main.cpp:205-226)
     def _no_dynamics(self):

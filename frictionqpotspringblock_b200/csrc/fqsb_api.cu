@@ -46,6 +46,9 @@ static int cuda_fail(cudaError_t e, const char* what)
 // the reference's assertion text (config.h:19-24)
 #define ASSERT_MSG(expr) (std::string("fqsb: assertion failed (") + expr + ") \n\t")
 
+struct fqsb_slab_state;
+static void slab_free(struct fqsb_system* s);
+
 struct fqsb_system {
     fqsb_params par;
     Par P;
@@ -88,6 +91,9 @@ struct fqsb_system {
     // External = RandomNormalForcing (detail.h:881-1000): enabled by fqsb_enable_random_forcing
     bool thermal;
     Thermal th;
+    // member of a slab-decomposed system (fqsb_slab.inl)
+    fqsb_slab_state* slab;
+    i64* d_mark;     // [R*N] indices kept by fqsb_mark_indices (nullptr until then)
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -363,6 +369,8 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->last_kernel = "";
     s->ev0 = s->ev1 = nullptr;
     s->lr_gemm = false;
+    s->slab = nullptr;
+    s->d_mark = nullptr;
     s->own_lo = 0;
     s->own_hi = 0;
     for (int k = 0; k < 5; ++k) {
@@ -556,6 +564,7 @@ void fqsb_destroy(fqsb_system* s)
     if (s->stream) {
         cudaStreamSynchronize(s->stream);
     }
+    slab_free(s);
     for (void* p : s->allocs) {
         cudaFree(p);
     }
@@ -1620,21 +1629,77 @@ int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* valu
     return check_flags(s);
 }
 
-int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A)
+static int avalanche_out(fqsb_system* s, const i64* i_n_dev, int64_t* out_S, int64_t* out_A)
 {
-    TRY(enter(s));
-    if (!s->d_in) {
-        TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
-    }
-    CU(cudaMemcpyAsync(s->d_in, i_n, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
-                       s->stream));
-    TRY(reduce_to_host(s, 4, 1, s->d_in));
+    TRY(reduce_to_host(s, 4, 1, i_n_dev));
     for (i64 r = 0; r < s->R; ++r) {
         if (out_S) {
             out_S[r] = (int64_t)s->h_out[4 * r];
         }
         if (out_A) {
             out_A[r] = (int64_t)s->h_out[4 * r + 1];
+        }
+    }
+    return FQSB_OK;
+}
+
+int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t n, int64_t* out_S, int64_t* out_A)
+{
+    TRY(enter(s));
+    if (n != s->n || !i_n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(i_n, m_u.shape())"));
+    }
+    if (!s->d_in) {
+        TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
+    }
+    CU(cudaMemcpyAsync(s->d_in, i_n, (size_t)s->n * sizeof(i64), cudaMemcpyHostToDevice,
+                       s->stream));
+    return avalanche_out(s, s->d_in, out_S, out_A);
+}
+
+static int mark_index(fqsb_system* s)
+{
+    if (!s->d_mark) {
+        TRY(dev_alloc(s, &s->d_mark, (size_t)s->n));
+    }
+    CU(cudaMemcpyAsync(s->d_mark, s->S.idx, (size_t)s->n * sizeof(i64), cudaMemcpyDeviceToDevice,
+                       s->stream));
+    return FQSB_OK;
+}
+
+// N1: the examples' `i_n = system.chunk.index_at_align` kept on the device
+int fqsb_mark_indices(fqsb_system* s)
+{
+    TRY(enter(s));
+    return mark_index(s);
+}
+
+int fqsb_avalanche_since_mark(fqsb_system* s, int64_t* out_S, int64_t* out_A)
+{
+    TRY(enter(s));
+    if (!s->d_mark) {
+        return fail(FQSB_EASSERT, "no marked indices (call fqsb_mark_indices first)");
+    }
+    return avalanche_out(s, s->d_mark, out_S, out_A);
+}
+
+int fqsb_event_record(fqsb_system* s, int64_t* S_abs, int64_t* A, int64_t* first, int64_t* last)
+{
+    TRY(enter(s));
+    TRY(pull_ctl(s));
+    for (i64 r = 0; r < s->R; ++r) {
+        const Ctl& c = s->h_ctl[r];
+        if (S_abs) {
+            S_abs[r] = c.S;
+        }
+        if (A) {
+            A[r] = c.A;
+        }
+        if (first) {
+            first[r] = c.qs_first;
+        }
+        if (last) {
+            last[r] = c.qs_last;
         }
     }
     return FQSB_OK;
@@ -1790,7 +1855,8 @@ int fqsb_advance_uniformly(fqsb_system* s, const double* du, const double* du_fr
 // raw per-realisation sums over the owned range: out [R][4]
 //   what 1: {sum f^2, sum f_frame^2}   2: {sum v^2, sum f_frame}
 //   what 3: {-, off-branch count, -, min displacement}   4: {sum (i-i_n), #(i != i_n), sum |i-i_n|}
-int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, double* out)
+int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, int64_t n,
+                     double* out)
 {
     TRY(enter(s));
     if (what < 1 || what > 4) {
@@ -1798,6 +1864,9 @@ int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n
     }
     const i64* d_in = nullptr;
     if (what == 4) {
+        if (n != s->n || !i_n) {
+            return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(i_n, m_u.shape())"));
+        }
         if (!s->d_in) {
             TRY(dev_alloc(s, &s->d_in, (size_t)s->n));
         }
@@ -1939,3 +2008,5 @@ int fqsb_external_set_state(fqsb_system* s, const uint64_t* state) // [R] detail
 }
 
 } // extern "C"
+
+#include "fqsb_slab.inl"

@@ -1,0 +1,1044 @@
+// fqsb_slab.inl -- slab domain decomposition of ONE very large line / interface over several
+// GPUs, inside the library (included by fqsb_api.cu; SURVEY.md section 8e, BASELINE configs #3, #5).
+//
+// Every member (= one fqsb_system on one GPU) integrates its rows extended by `halo` rows per side
+// that mirror the neighbours' rows; a batch of k <= halo steps needs no communication (the local
+// array is treated as periodic by the unchanged kernels; the error entering through the outermost
+// halo row travels one row per step). After a batch:
+//   k_slab_push    writes the member's outermost owned rows (u, v, a, y_l, y_r, index, pcg32
+//                  state) STRAIGHT INTO THE NEIGHBOURS' MEMORY over NVLink (peer-mapped stores
+//                  into a double-buffered mailbox) and its k x 5 log of per-step sums into every
+//                  member's gather mailbox, then publishes an epoch number with st.release.sys;
+//   k_slab_import  spins (ld.acquire.sys) on the epochs the neighbours publish, copies the mailbox
+//                  into its halo rows, adds the logs of all members in rank order (-> identical
+//                  sums, hence identical stop decisions, on every member) into host-mapped memory.
+// No NCCL, no host staging, no Python in the exchange: the only host work per batch is the
+// StopList replay (detail.h:1764-1784) on the k global sums. The members of a slab live either
+// in one process (peer access enabled between the devices) or in one process per GPU (the
+// mailboxes are shared through CUDA IPC handles; the caller moves the 64-byte handles).
+//
+// Per-step decision of the reference (detail.h:1754-1785) batched: the criterion fired at step
+// s* < k of a batch -> every member rolls back to its snapshot and redoes exactly s* steps.
+
+#define FQSB_SLAB_MAXW 16
+#define FQSB_SLAB_FLAGS 32 // 8-byte words reserved for the epoch flags at the head of a mailbox
+
+namespace fqsb {
+
+struct SlabDev {
+    int rank, world;
+    i64 hc; // cells of `halo` rows (one side)
+    i64 n;  // local cells (owned + 2 * hc)
+    int gcap; // doubles per member in the gather mailbox
+    u64* peer[FQSB_SLAB_MAXW]; // mailboxes of all members (peer[rank] = own)
+    u64* epoch;           // device [2]: halo / gather epochs completed by this member
+    unsigned int* ticket; // device [2]
+    double* h_res;        // host-mapped [world * gcap]
+    volatile int* h_status; // host-mapped: [0] peer timeout
+    unsigned long long timeout_ns;
+};
+
+// mailbox layout (8-byte words): flags | halo mail [2 parity][2 side][7 planes][hc] |
+// gather [2 parity][world][gcap]
+__host__ __device__ __forceinline__ u64* slab_mail(u64* base, int parity, int side, i64 hc)
+{
+    return base + FQSB_SLAB_FLAGS + (i64)((parity * 2 + side) * 7) * hc;
+}
+
+__host__ __device__ __forceinline__ double* slab_gather(u64* base, int parity, int member, i64 hc,
+                                                        int world, int gcap)
+{
+    return reinterpret_cast<double*>(base + FQSB_SLAB_FLAGS + 28 * hc) +
+           (i64)(parity * world + member) * gcap;
+}
+
+inline size_t slab_mailbox_words(i64 hc, int world, int gcap)
+{
+    return (size_t)FQSB_SLAB_FLAGS + 28 * (size_t)hc + 2 * (size_t)world * (size_t)gcap;
+}
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p)
+{
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// spin until *flag >= epoch (published by a peer with st.release.sys); gives up after timeout_ns
+__device__ __forceinline__ bool slab_wait(const u64* flag, u64 epoch, const SlabDev& D)
+{
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(flag) < epoch) {
+        if (global_ns() - t0 > D.timeout_ns) {
+            D.h_status[0] = 1;
+            __threadfence_system();
+            return false;
+        }
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// ---- after a batch: outermost owned rows -> the neighbours' mailboxes, log -> all mailboxes ------
+__global__ void __launch_bounds__(256)
+    k_slab_push(const State S, const SlabDev D, const double* log, int nlog, int halos)
+{
+    __shared__ int s_last;
+    const u64 e = D.epoch[0] + 1;
+    const int par = (int)(e & 1ULL);
+    const int prev = (D.rank + D.world - 1) % D.world, next = (D.rank + 1) % D.world;
+    // my top rows become the previous member's bottom halo (its side 1 = "from next"), my bottom
+    // rows the next member's top halo (side 0 = "from prev")
+    u64* to_prev = slab_mail(D.peer[prev], par, 1, D.hc);
+    u64* to_next = slab_mail(D.peer[next], par, 0, D.hc);
+    const u64* plane[7] = {reinterpret_cast<const u64*>(S.u),  reinterpret_cast<const u64*>(S.v),
+                           reinterpret_cast<const u64*>(S.a),  reinterpret_cast<const u64*>(S.yl),
+                           reinterpret_cast<const u64*>(S.yr), reinterpret_cast<const u64*>(S.idx),
+                           S.rng};
+    const i64 top = D.hc, bot = D.n - 2 * D.hc;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (!halos) {
+        // gather only
+    }
+    else if (((D.hc | D.n) & 1) == 0) { // 16-byte stores: every offset is then 16-byte aligned
+        const i64 h2 = D.hc >> 1;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const ulonglong2* st = reinterpret_cast<const ulonglong2*>(plane[q] + top);
+            const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(plane[q] + bot);
+            ulonglong2* dp = reinterpret_cast<ulonglong2*>(to_prev + (i64)q * D.hc);
+            ulonglong2* dn = reinterpret_cast<ulonglong2*>(to_next + (i64)q * D.hc);
+            for (i64 c = t0; c < h2; c += stride) {
+                dp[c] = st[c];
+                dn[c] = sb[c];
+            }
+        }
+    }
+    else {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            for (i64 c = t0; c < D.hc; c += stride) {
+                to_prev[(i64)q * D.hc + c] = plane[q][top + c];
+                to_next[(i64)q * D.hc + c] = plane[q][bot + c];
+            }
+        }
+    }
+    const u64 ge = D.epoch[1] + 1;
+    if (nlog > 0 && blockIdx.x == 0) {
+        const int gpar = (int)(ge & 1ULL);
+        for (int j = 0; j < D.world; ++j) {
+            double* dst = slab_gather(D.peer[j], gpar, D.rank, D.hc, D.world, D.gcap);
+            for (int i = threadIdx.x; i < nlog; i += blockDim.x) {
+                dst[i] = log[i];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(&D.ticket[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    // the last CTA publishes the epochs: everything above is visible system-wide before them
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        D.ticket[0] = 0u;
+        if (halos) {
+            st_release_sys(D.peer[prev] + 1, e); // prev's flag "from next"
+            st_release_sys(D.peer[next] + 0, e); // next's flag "from prev"
+        }
+    }
+    if (nlog > 0 && threadIdx.x < D.world) {
+        st_release_sys(D.peer[threadIdx.x] + 2 + D.rank, ge);
+    }
+}
+
+// ---- before the next batch: mailbox -> halo rows; logs of all members -> host-mapped result ------
+// raw == 0: h_res[i] = sum over members (rank order) of their entry i; raw != 0: h_res[j*nlog + i]
+__global__ void __launch_bounds__(256)
+    k_slab_import(const State S, const SlabDev D, int nlog, int raw, int halos)
+{
+    __shared__ int s_ok, s_last;
+    const u64 e = D.epoch[0] + 1;
+    const u64 ge = D.epoch[1] + 1;
+    u64* self = D.peer[D.rank];
+    if (halos) {
+        const int par = (int)(e & 1ULL);
+        if (threadIdx.x == 0) {
+            s_ok = slab_wait(self + 0, e, D) && slab_wait(self + 1, e, D);
+        }
+        __syncthreads();
+        if (s_ok) {
+            const u64* from_prev = slab_mail(self, par, 0, D.hc);
+            const u64* from_next = slab_mail(self, par, 1, D.hc);
+            u64* plane[7] = {reinterpret_cast<u64*>(S.u),  reinterpret_cast<u64*>(S.v),
+                             reinterpret_cast<u64*>(S.a),  reinterpret_cast<u64*>(S.yl),
+                             reinterpret_cast<u64*>(S.yr), reinterpret_cast<u64*>(S.idx), S.rng};
+            const i64 stride = (i64)gridDim.x * blockDim.x;
+            const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+            const i64 bot = D.n - D.hc;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                for (i64 c = t0; c < D.hc; c += stride) {
+                    plane[q][c] = __ldcg(from_prev + (i64)q * D.hc + c);
+                    plane[q][bot + c] = __ldcg(from_next + (i64)q * D.hc + c);
+                }
+            }
+        }
+    }
+    if (nlog > 0 && blockIdx.x == 0) {
+        const int gpar = (int)(ge & 1ULL);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_ok = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x < D.world) {
+            if (!slab_wait(self + 2 + threadIdx.x, ge, D)) {
+                s_ok = 0;
+            }
+        }
+        __syncthreads();
+        if (s_ok) {
+            for (int i = threadIdx.x; i < nlog; i += blockDim.x) {
+                if (raw) {
+                    for (int j = 0; j < D.world; ++j) {
+                        D.h_res[j * nlog + i] =
+                            __ldcg(slab_gather(self, gpar, j, D.hc, D.world, D.gcap) + i);
+                    }
+                }
+                else {
+                    double acc = 0.0;
+                    for (int j = 0; j < D.world; ++j) {
+                        acc += __ldcg(slab_gather(self, gpar, j, D.hc, D.world, D.gcap) + i);
+                    }
+                    D.h_res[i] = acc;
+                }
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(&D.ticket[1], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        D.ticket[1] = 0u;
+        if (halos) {
+            D.epoch[0] = e;
+        }
+        if (nlog > 0) {
+            D.epoch[1] = ge;
+        }
+    }
+}
+
+// snapshot / rollback of the whole local state in one launch (dir 0: state -> snapshot)
+struct SnapArgs {
+    u64* a[7];
+    u64* b[7];
+    double *uf_a, *uf_b;
+    Ctl *ctl_a, *ctl_b;
+    i64 n;
+};
+
+__global__ void __launch_bounds__(256) k_slab_copy_state(const SnapArgs X)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((X.n & 1) == 0) {
+        const i64 n2 = X.n >> 1;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(X.a[q]);
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(X.b[q]);
+            for (i64 c = t0; c < n2; c += stride) {
+                dst[c] = src[c];
+            }
+        }
+    }
+    else {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            for (i64 c = t0; c < X.n; c += stride) {
+                X.b[q][c] = X.a[q][c];
+            }
+        }
+    }
+    if (t0 == 0) {
+        *X.uf_b = *X.uf_a;
+        *X.ctl_b = *X.ctl_a;
+    }
+}
+
+// u_frame += duf; du[0] = dup (the uniform shift k_align applies)
+__global__ void k_slab_shift(const State S, double* du, double dup, double duf)
+{
+    du[0] = dup;
+    S.u_frame[0] += duf;
+}
+
+} // namespace fqsb
+
+struct fqsb_slab_state {
+    int rank, world;
+    i64 halo_cells;
+    int kmax, gcap;
+    u64* mailbox;
+    size_t mailbox_bytes;
+    u64* peer[FQSB_SLAB_MAXW];
+    bool peer_ipc[FQSB_SLAB_MAXW];
+    bool connected;
+    u64* d_epoch;
+    unsigned int* d_ticket;
+    double* h_res;
+    int* h_status;
+    SlabDev dev;
+    bool overdamped;
+    // CUDA graph of one full batch (snapshot + k logged steps + push + import), replayed while k
+    // and the mode stay the same
+    cudaGraphExec_t graph;
+    i64 graph_k, seen_k;
+    int graph_mode, seen_mode;
+    i64 batches, redone;
+};
+
+static int slab_require(fqsb_system* s, bool connected = true)
+{
+    TRY(enter(s));
+    if (!s->slab) {
+        return fail(FQSB_EASSERT, "not a slab member (call fqsb_slab_init first)");
+    }
+    if (connected && !s->slab->connected) {
+        return fail(FQSB_EASSERT, "slab members are not connected (fqsb_slab_connect)");
+    }
+    return FQSB_OK;
+}
+
+static void slab_free(fqsb_system* s)
+{
+    fqsb_slab_state* L = s->slab;
+    if (!L) {
+        return;
+    }
+    for (int j = 0; j < L->world; ++j) {
+        if (L->peer_ipc[j] && L->peer[j]) {
+            cudaIpcCloseMemHandle(L->peer[j]);
+        }
+    }
+    if (L->graph) {
+        cudaGraphExecDestroy(L->graph);
+    }
+    if (L->mailbox) {
+        cudaFree(L->mailbox);
+    }
+    if (L->d_epoch) {
+        cudaFree(L->d_epoch);
+    }
+    if (L->d_ticket) {
+        cudaFree(L->d_ticket);
+    }
+    if (L->h_res) {
+        cudaFreeHost(L->h_res);
+    }
+    if (L->h_status) {
+        cudaFreeHost(L->h_status);
+    }
+    delete L;
+    s->slab = nullptr;
+}
+
+// all launches of `k` steps (Verlet, or no-passing sweeps) on the streaming kernels, without any
+// host synchronisation. MODE_LOG: per-step sums over the owned range -> s->d_log; MODE_FIXED:
+// plain steps.
+static int slab_enqueue_steps(fqsb_system* s, i64 k, int mode, int flow, double v_frame)
+{
+    const bool overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
+    RunArgs A = make_args(mode, k);
+    A.flow = flow;
+    A.v_frame = v_frame;
+    A.own_lo = (int)s->own_lo;
+    A.own_hi = (int)s->own_hi;
+    A.log = s->d_log;
+    const unsigned rg = (unsigned)((s->R + 127) / 128);
+    k_ctl_begin<<<rg, 128, 0, s->stream>>>(s->P, s->S, 0, overdamped ? 1 : 0, s->d_out);
+    const int finalise = (mode != MODE_FIXED || flow) ? 1 : 0;
+    const i64 nl = overdamped ? k + 1 : k;
+    for (i64 b = 0; b < nl; ++b) {
+        cudaError_t e = overdamped
+                            ? launch_stream_sweep(s->P, s->S, A, s->stream, (int)(b & 1), b == 0, b < k)
+                            : launch_stream_step(s->P, s->S, A, s->stream, (int)(b & 1), finalise);
+        if (e != cudaSuccess) {
+            return cuda_fail(e, "stream kernel launch");
+        }
+    }
+    if (!finalise && !overdamped) {
+        k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, k, 0);
+    }
+    dim3 grid((unsigned)s->S.tiles, (unsigned)s->R);
+    k_stream_settle<<<grid, 256, 0, s->stream>>>(s->P, s->S, overdamped ? 0 : 1);
+    k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
+    CU(cudaGetLastError());
+    s->launches += nl + 3 + ((!finalise && !overdamped) ? 1 : 0);
+    s->steps += k;
+    invalidate_forces(s);
+    return FQSB_OK;
+}
+
+static int slab_ensure_snapshot(fqsb_system* s)
+{
+    const size_t n = (size_t)s->n;
+    if (!s->snap_idx) {
+        for (int k = 0; k < 5; ++k) {
+            TRY(dev_alloc(s, &s->snap_d[k], n));
+        }
+        TRY(dev_alloc(s, &s->snap_idx, n));
+        TRY(dev_alloc(s, &s->snap_rng, n));
+        TRY(dev_alloc(s, &s->snap_uf, (size_t)s->R));
+        TRY(dev_alloc(s, &s->snap_ctl, (size_t)s->R));
+    }
+    return FQSB_OK;
+}
+
+static int slab_copy_state(fqsb_system* s, bool restore)
+{
+    SnapArgs X;
+    u64* live[7] = {(u64*)s->S.u, (u64*)s->S.v, (u64*)s->S.a, (u64*)s->S.yl, (u64*)s->S.yr,
+                    (u64*)s->S.idx, s->S.rng};
+    u64* snap[7] = {(u64*)s->snap_d[0], (u64*)s->snap_d[1], (u64*)s->snap_d[2], (u64*)s->snap_d[3],
+                    (u64*)s->snap_d[4], (u64*)s->snap_idx, s->snap_rng};
+    for (int q = 0; q < 7; ++q) {
+        X.a[q] = restore ? snap[q] : live[q];
+        X.b[q] = restore ? live[q] : snap[q];
+    }
+    X.uf_a = restore ? s->snap_uf : s->S.u_frame;
+    X.uf_b = restore ? s->S.u_frame : s->snap_uf;
+    X.ctl_a = restore ? s->snap_ctl : s->S.ctl;
+    X.ctl_b = restore ? s->S.ctl : s->snap_ctl;
+    X.n = s->n;
+    k_slab_copy_state<<<148 * 4, 256, 0, s->stream>>>(X);
+    CU(cudaGetLastError());
+    s->launches++;
+    if (restore) {
+        invalidate_forces(s);
+    }
+    else {
+        s->snap_valid = true;
+    }
+    return FQSB_OK;
+}
+
+static int slab_enqueue_push(fqsb_system* s, int nlog, const double* src, int halos)
+{
+    fqsb_slab_state* L = s->slab;
+    // enough CTAs to keep the NVLink stores in flight, few enough to coexist with other streams
+    const i64 words = 14 * L->halo_cells;
+    unsigned grid = halos ? (unsigned)((words / 2 + 2047) / 2048) : 1u;
+    grid = grid < 1u ? 1u : (grid > 64u ? 64u : grid);
+    k_slab_push<<<grid, 256, 0, s->stream>>>(s->S, L->dev, src, nlog, halos);
+    CU(cudaGetLastError());
+    s->launches++;
+    return FQSB_OK;
+}
+
+static int slab_enqueue_import(fqsb_system* s, int nlog, int raw, int halos)
+{
+    fqsb_slab_state* L = s->slab;
+    const i64 words = 14 * L->halo_cells;
+    unsigned grid = halos ? (unsigned)((words + 4095) / 4096) : 1u;
+    grid = grid < 1u ? 1u : (grid > 32u ? 32u : grid);
+    k_slab_import<<<grid, 256, 0, s->stream>>>(s->S, L->dev, nlog, raw, halos);
+    CU(cudaGetLastError());
+    s->launches++;
+    if (halos) {
+        invalidate_forces(s);
+    }
+    return FQSB_OK;
+}
+
+static int slab_sync(fqsb_system* s)
+{
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->slab->h_status[0]) {
+        s->slab->h_status[0] = 0;
+        return fail(FQSB_ECUDA, "slab: timed out waiting for a neighbouring member");
+    }
+    return FQSB_OK;
+}
+
+// one batch on one member: [snapshot] + k steps + push, as direct launches or as a graph replay
+static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, bool snapshot, int flow,
+                              double v_frame)
+{
+    CU(cudaSetDevice(s->device));
+    fqsb_slab_state* L = s->slab;
+    const int nlog = mode == MODE_LOG ? (int)(k * FQSB_NLOG) : 0;
+    const int gmode = mode * 4 + (snapshot ? 2 : 0) + (flow ? 1 : 0);
+    static const bool use_graph = [] {
+        const char* e = std::getenv("FQSB_SLAB_GRAPH");
+        return e ? std::atoi(e) != 0 : true;
+    }();
+    auto body = [&]() -> int {
+        if (snapshot) {
+            TRY(slab_copy_state(s, false));
+        }
+        TRY(slab_enqueue_steps(s, k, mode, flow, v_frame));
+        TRY(slab_enqueue_push(s, nlog, s->d_log, 1));
+        return FQSB_OK;
+    };
+    if (!use_graph || flow) { // (flowSteps: v_frame is a kernel argument, not worth a graph)
+        return body();
+    }
+    auto replay = [&]() -> int {
+        CU(cudaGraphLaunch(L->graph, s->stream));
+        s->launches += k + 6;
+        s->steps += k;
+        invalidate_forces(s);
+        if (snapshot) {
+            s->snap_valid = true;
+        }
+        return FQSB_OK;
+    };
+    if (L->graph && L->graph_k == k && L->graph_mode == gmode) {
+        return replay();
+    }
+    if (L->seen_k == k && L->seen_mode == gmode) {
+        // second batch of this shape (everything is allocated and warm): capture it
+        if (L->graph) {
+            cudaGraphExecDestroy(L->graph);
+            L->graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const i64 launches0 = s->launches, steps0 = s->steps;
+        int rc = body();
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        s->launches = launches0;
+        s->steps = steps0;
+        if (rc != FQSB_OK || ce != cudaSuccess || !g) {
+            if (g) {
+                cudaGraphDestroy(g);
+            }
+            cudaGetLastError();
+            L->seen_k = 0;
+            return rc != FQSB_OK ? rc : cuda_fail(ce, "slab graph capture");
+        }
+        ce = cudaGraphInstantiate(&L->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) {
+            L->graph = nullptr;
+            L->seen_k = 0;
+            return cuda_fail(ce, "cudaGraphInstantiate");
+        }
+        L->graph_k = k;
+        L->graph_mode = gmode;
+        return replay();
+    }
+    // first batch of this shape: direct launches (allocations, function attributes)
+    L->seen_k = k;
+    L->seen_mode = gmode;
+    return body();
+}
+
+// ---- host-side StopList (GooseFEM::Iterate::StopList) in the (num, den) form
+//      of the device (fqsb_device.cuh: ring_stop), any niter_tol
+struct HostRing {
+    std::vector<double> num, den;
+    explicit HostRing(size_t n) : num(n, std::numeric_limits<double>::infinity()), den(n, 1.0) {}
+    void roll_insert(double sf, double sff)
+    {
+        for (size_t k = 0; k + 1 < num.size(); ++k) {
+            num[k] = num[k + 1];
+            den[k] = den[k + 1];
+        }
+        num.back() = sf;
+        den.back() = sff != 0.0 ? sff : 1.0; // detail.h:1516-1519
+    }
+    bool stop(double tol) const
+    {
+        const double tol2 = tol * tol, tol4 = tol2 * tol2;
+        bool descending = true, less1 = true, less2 = true;
+        for (size_t k = 0; k < num.size(); ++k) {
+            if (k + 1 < num.size() && num[k + 1] * den[k] > num[k] * den[k + 1]) {
+                descending = false;
+            }
+            less1 = less1 && (num[k] < tol2 * den[k]);
+            less2 = less2 && (num[k] < tol4 * den[k]);
+        }
+        return (descending && less1) || less2;
+    }
+};
+
+// replay of the per-step decisions over a batch log [k][FQSB_NLOG]; returns the 1-based step at
+// which the criterion fires, 0 if it does not, -1 on NaN (detail.h:1567-1569)
+static i64 slab_first_stop(const double* log, i64 k, HostRing& ring, double tol)
+{
+    for (i64 j = 0; j < k; ++j) {
+        const double sf = log[j * FQSB_NLOG], sff = log[j * FQSB_NLOG + 1];
+        if (sf != sf) {
+            return -1;
+        }
+        ring.roll_insert(sf, sff);
+        if (ring.stop(tol)) {
+            return j + 1;
+        }
+    }
+    return 0;
+}
+
+static int slab_check_group(fqsb_system** m, int nm)
+{
+    if (!m || nm < 1) {
+        return fail(FQSB_EASSERT, "null slab group");
+    }
+    for (int g = 0; g < nm; ++g) {
+        TRY(slab_require(m[g]));
+    }
+    return FQSB_OK;
+}
+
+static int slab_flags_all(fqsb_system** m, int nm)
+{
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(check_flags(m[g]));
+    }
+    return FQSB_OK;
+}
+
+// local reduction (k_reduce) on every member + raw gather: out[world][4] on every member's host
+static int slab_reduce_gather(fqsb_system** m, int nm, int what, int direction, bool use_mark)
+{
+    for (int g = 0; g < nm; ++g) {
+        fqsb_system* s = m[g];
+        CU(cudaSetDevice(s->device));
+        if (what == 3) {
+            TRY(align(s, nullptr));
+        }
+        if (use_mark && !s->d_mark) {
+            return fail(FQSB_EASSERT, "no marked indices (fqsb_slab_mark_indices)");
+        }
+        TRY(reduce(s, what, direction, use_mark ? s->d_mark : nullptr));
+        TRY(slab_enqueue_push(s, 4, s->d_out, 0));
+    }
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(slab_enqueue_import(m[g], 4, 1, 0));
+    }
+    for (int g = 0; g < nm; ++g) {
+        TRY(slab_sync(m[g]));
+    }
+    return FQSB_OK;
+}
+
+extern "C" {
+
+int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int kmax)
+{
+    TRY(enter(s));
+    if (s->slab) {
+        return fail(FQSB_EASSERT, "already a slab member");
+    }
+    if (world < 1 || world > FQSB_SLAB_MAXW || rank < 0 || rank >= world) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("0 <= rank < world <= 16"));
+    }
+    if (s->R != 1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("nrealisations == 1 (a slab is part of ONE system)"));
+    }
+    if (halo_cells < 1 || 3 * halo_cells > s->N) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("1 <= halo, owned rows >= halo rows"));
+    }
+    // nearest-neighbour stencils with per-block disorder only: LongRange couples all blocks and
+    // the thermal classes consume one ordered pcg32 stream per realisation
+    if (s->P.inter == INT_LONGRANGE1D || s->thermal || s->par.minimisation == FQSB_MIN_NONE) {
+        return fail(FQSB_EUNSUPPORTED,
+                    "slab decomposition needs a nearest-neighbour, athermal system");
+    }
+    if ((s->par.kernel & 15) != 2) {
+        return fail(FQSB_EASSERT, "slab members run the streaming kernels (params.kernel = 2)");
+    }
+    if (kmax < 1) {
+        kmax = 64;
+    }
+    fqsb_slab_state* L = new fqsb_slab_state();
+    memset(L, 0, sizeof *L);
+    s->slab = L;
+    L->rank = rank;
+    L->world = world;
+    L->halo_cells = halo_cells;
+    L->kmax = kmax;
+    L->gcap = kmax * FQSB_NLOG > 8 ? kmax * FQSB_NLOG : 8;
+    L->overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
+    L->mailbox_bytes = slab_mailbox_words(halo_cells, world, L->gcap) * 8;
+    auto build = [&]() -> int {
+        CU(cudaMalloc((void**)&L->mailbox, L->mailbox_bytes));
+        CU(cudaMemset(L->mailbox, 0, L->mailbox_bytes));
+        CU(cudaMalloc((void**)&L->d_epoch, 2 * sizeof(u64)));
+        CU(cudaMemset(L->d_epoch, 0, 2 * sizeof(u64)));
+        CU(cudaMalloc((void**)&L->d_ticket, 2 * sizeof(unsigned int)));
+        CU(cudaMemset(L->d_ticket, 0, 2 * sizeof(unsigned int)));
+        const size_t res = (size_t)world * (size_t)L->gcap;
+        CU(cudaHostAlloc((void**)&L->h_res, res * sizeof(double), cudaHostAllocMapped));
+        CU(cudaHostAlloc((void**)&L->h_status, 4 * sizeof(int), cudaHostAllocMapped));
+        memset(L->h_status, 0, 4 * sizeof(int));
+        const size_t need = (size_t)kmax * FQSB_NLOG;
+        if (need > s->log_cap) {
+            TRY(dev_alloc(s, &s->d_log, need));
+            s->log_cap = need;
+        }
+        TRY(ensure_stream_buffers(s));
+        TRY(slab_ensure_snapshot(s));
+        CU(cudaDeviceSynchronize());
+        return FQSB_OK;
+    };
+    int rc = build();
+    if (rc != FQSB_OK) {
+        std::string keep = g_err;
+        slab_free(s);
+        g_err = keep;
+        return rc;
+    }
+    L->peer[rank] = L->mailbox;
+    s->own_lo = halo_cells;
+    s->own_hi = s->N - halo_cells;
+    SlabDev& D = L->dev;
+    D.rank = rank;
+    D.world = world;
+    D.hc = halo_cells;
+    D.n = s->N;
+    D.gcap = L->gcap;
+    D.epoch = L->d_epoch;
+    D.ticket = L->d_ticket;
+    D.h_res = L->h_res;
+    D.h_status = L->h_status;
+    D.timeout_ns = 20ULL * 1000000000ULL;
+    if (const char* e = std::getenv("FQSB_SLAB_TIMEOUT_MS")) {
+        D.timeout_ns = (unsigned long long)std::atoll(e) * 1000000ULL;
+    }
+    return FQSB_OK;
+}
+
+int fqsb_slab_ipc_handle(fqsb_system* s, void* out64)
+{
+    TRY(slab_require(s, false));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->slab->mailbox));
+    memcpy(out64, &h, 64);
+    return FQSB_OK;
+}
+
+// locals[j] != NULL: member j lives in this process (its mailbox is used directly, peer access is
+// enabled between the two devices); otherwise ipc_handles + 64 * j is member j's IPC handle
+int fqsb_slab_connect(fqsb_system* s, fqsb_system* const* locals, const void* ipc_handles)
+{
+    TRY(slab_require(s, false));
+    fqsb_slab_state* L = s->slab;
+    for (int j = 0; j < L->world; ++j) {
+        if (j == L->rank) {
+            continue;
+        }
+        if (locals && locals[j]) {
+            fqsb_system* o = locals[j];
+            if (!o->slab || o->slab->world != L->world || o->slab->rank != j ||
+                o->slab->halo_cells != L->halo_cells || o->slab->gcap != L->gcap) {
+                return fail(FQSB_EASSERT, "slab members do not match");
+            }
+            if (o->device != s->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, s->device, o->device));
+                if (!can) {
+                    return fail(FQSB_ECUDA, "no peer access between the devices of the slab");
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+                }
+                cudaGetLastError();
+            }
+            L->peer[j] = o->slab->mailbox;
+            L->peer_ipc[j] = false;
+        }
+        else if (ipc_handles) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char*)ipc_handles + 64 * (size_t)j, 64);
+            void* p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            L->peer[j] = (u64*)p;
+            L->peer_ipc[j] = true;
+        }
+        else {
+            return fail(FQSB_EASSERT, "slab member without a local handle or an IPC handle");
+        }
+    }
+    for (int j = 0; j < L->world; ++j) {
+        L->dev.peer[j] = L->peer[j];
+    }
+    L->connected = true;
+    return FQSB_OK;
+}
+
+int fqsb_slab_info(fqsb_system* s, int64_t* out /* [8] */)
+{
+    TRY(slab_require(s, false));
+    fqsb_slab_state* L = s->slab;
+    out[0] = L->rank;
+    out[1] = L->world;
+    out[2] = L->halo_cells;
+    out[3] = s->own_lo;
+    out[4] = s->own_hi;
+    out[5] = L->batches;
+    out[6] = L->redone;
+    out[7] = L->graph ? 1 : 0;
+    return FQSB_OK;
+}
+
+// refresh the halo rows of every member from its neighbours' owned rows
+int fqsb_slab_exchange(fqsb_system** m, int nm)
+{
+    TRY(slab_check_group(m, nm));
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(slab_enqueue_push(m[g], 0, nullptr, 1));
+    }
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(slab_enqueue_import(m[g], 0, 0, 1));
+    }
+    for (int g = 0; g < nm; ++g) {
+        TRY(slab_sync(m[g]));
+    }
+    return FQSB_OK;
+}
+
+// timeSteps(n) / flowSteps(n, v_frame) of the decomposed system (detail.h:1577-1583, 1637-1645):
+// batches of `batch` <= halo rows steps, one peer-memory halo exchange per batch, no host
+// synchronisation until the end
+int fqsb_slab_time_steps(fqsb_system** m, int nm, int64_t n, int64_t batch, int flow, double v_frame)
+{
+    TRY(slab_check_group(m, nm));
+    for (int g = 0; g < nm; ++g) {
+        TRY(require_dynamic(m[g]));
+    }
+    if (n < 0 || batch < 1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("n >= 0 && batch >= 1"));
+    }
+    i64 left = n;
+    while (left > 0) {
+        const i64 k = left < batch ? left : batch;
+        for (int g = 0; g < nm; ++g) {
+            TRY(slab_enqueue_batch(m[g], k, MODE_FIXED, false, flow, v_frame));
+        }
+        for (int g = 0; g < nm; ++g) {
+            CU(cudaSetDevice(m[g]->device));
+            TRY(slab_enqueue_import(m[g], 0, 0, 1));
+        }
+        left -= k;
+    }
+    for (int g = 0; g < nm; ++g) {
+        TRY(slab_sync(m[g]));
+    }
+    return slab_flags_all(m, nm);
+}
+
+// minimise() of the decomposed system (detail.h:1676-1792, dynamic or overdamped): the reference
+// decides after every step; here every batch logs its per-step global sums and the criterion is
+// replayed on them. *ret: 0 converged, steps + 1 otherwise (quirk Q4). *steps_out: steps taken.
+int fqsb_slab_minimise(fqsb_system** m, int nm, double tol, int64_t niter_tol, int64_t max_iter,
+                       int64_t batch, int max_iter_is_error, int64_t* ret, int64_t* steps_out)
+{
+    TRY(slab_check_group(m, nm));
+    if (!(tol < 1.0)) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("tol < 1.0")); // detail.h:1684
+    }
+    if (niter_tol < 1 || batch < 1 || batch > m[0]->slab->kmax) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("niter_tol >= 1 && 1 <= batch <= kmax"));
+    }
+    HostRing ring((size_t)niter_tol);
+    i64 done = 0;
+    auto run_batch = [&](i64 k, bool snapshot) -> int {
+        for (int g = 0; g < nm; ++g) {
+            TRY(slab_enqueue_batch(m[g], k, MODE_LOG, snapshot, 0, 0.0));
+        }
+        for (int g = 0; g < nm; ++g) {
+            CU(cudaSetDevice(m[g]->device));
+            TRY(slab_enqueue_import(m[g], (int)(k * FQSB_NLOG), 0, 1));
+        }
+        for (int g = 0; g < nm; ++g) {
+            TRY(slab_sync(m[g]));
+            m[g]->slab->batches++;
+        }
+        return FQSB_OK;
+    };
+    while (done < max_iter) {
+        const i64 k = batch < max_iter - done ? batch : max_iter - done;
+        TRY(run_batch(k, true));
+        const HostRing saved = ring;
+        const i64 stop = slab_first_stop(m[0]->slab->h_res, k, ring, tol);
+        if (stop < 0) {
+            return fail(FQSB_ENAN, "NaN entries found"); // detail.h:1568
+        }
+        if (stop > 0) {
+            if (stop < k) { // the criterion fired inside the batch: redo exactly `stop` steps
+                for (int g = 0; g < nm; ++g) {
+                    CU(cudaSetDevice(m[g]->device));
+                    TRY(slab_copy_state(m[g], true));
+                    m[g]->slab->redone++;
+                }
+                ring = saved;
+                TRY(run_batch(stop, false));
+                if (slab_first_stop(m[0]->slab->h_res, stop, ring, tol) != stop) {
+                    return fail(FQSB_EASSERT, "slab: the redone batch did not reproduce its log");
+                }
+            }
+            for (int g = 0; g < nm; ++g) { // quench(), detail.h:1781
+                CU(cudaSetDevice(m[g]->device));
+                k_zero_va<<<grid_for(m[g]->n), 256, 0, m[g]->stream>>>(m[g]->P, m[g]->S);
+                CU(cudaGetLastError());
+                m[g]->launches++;
+            }
+            TRY(slab_flags_all(m, nm));
+            if (ret) {
+                *ret = 0;
+            }
+            if (steps_out) {
+                *steps_out = done + stop;
+            }
+            return FQSB_OK;
+        }
+        done += k;
+    }
+    TRY(slab_flags_all(m, nm));
+    if (ret) {
+        *ret = done + 1; // detail.h:1791 (quirk Q4)
+    }
+    if (steps_out) {
+        *steps_out = done;
+    }
+    if (max_iter_is_error) {
+        return fail(FQSB_ENOCONV, "No convergence found"); // detail.h:1788
+    }
+    return FQSB_OK;
+}
+
+// sums over the whole decomposed system, members added in rank order. out[4]:
+//   what 1: {sum f^2, sum f_frame^2}   2: {sum v^2, sum f_frame}
+//   what 3: {-, off-branch count, -, min displacement}
+//   what 4: {sum (i - i_mark), #(i != i_mark), sum |i - i_mark|} against fqsb_slab_mark_indices
+int fqsb_slab_sums(fqsb_system** m, int nm, int what, int direction, double* out)
+{
+    TRY(slab_check_group(m, nm));
+    if (what < 1 || what > 4) {
+        return fail(FQSB_EASSERT, "unknown reduction");
+    }
+    TRY(slab_reduce_gather(m, nm, what, direction, what == 4));
+    const fqsb_slab_state* L = m[0]->slab;
+    double acc[3] = {0.0, 0.0, 0.0}, mn = 1.7976931348623157e308;
+    for (int j = 0; j < L->world; ++j) {
+        for (int c = 0; c < 3; ++c) {
+            acc[c] += L->h_res[4 * j + c];
+        }
+        mn = std::fmin(mn, L->h_res[4 * j + 3]);
+    }
+    out[0] = acc[0];
+    out[1] = acc[1];
+    out[2] = acc[2];
+    out[3] = mn;
+    return what == 3 ? slab_flags_all(m, nm) : FQSB_OK;
+}
+
+// device-side copy of the current well indices: the i_n of the examples' S = sum(i - i_n)
+int fqsb_slab_mark_indices(fqsb_system** m, int nm)
+{
+    TRY(slab_check_group(m, nm));
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(mark_index(m[g]));
+    }
+    return FQSB_OK;
+}
+
+// eventDrivenStep(eps, kick, direction) of the decomposed system (detail.h:1933-1960): the uniform
+// displacement is agreed over all members (one gather of 4 doubles), applied locally -- halo rows
+// move with their originals, no exchange needed
+int fqsb_slab_event_driven_step(fqsb_system** m, int nm, double eps, int kick, int direction,
+                                double* du_frame)
+{
+    TRY(slab_check_group(m, nm));
+    if (direction != 1 && direction != -1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("direction == 1 || direction == -1"));
+    }
+    const Par& P = m[0]->P;
+    double dup;
+    if (!kick) {
+        if (P.pot == POT_SMOOTH) {
+            return fail(FQSB_EUNSUPPORTED, "Operation not possible."); // detail.h:420
+        }
+        double sums[4];
+        TRY(fqsb_slab_sums(m, nm, 3, direction, sums));
+        const double d = sums[1] > 0.0 ? 0.0 : sums[3];
+        if (d < 0.5 * eps) {
+            if (du_frame) {
+                *du_frame = 0.0;
+            }
+            return FQSB_OK;
+        }
+        dup = direction > 0 ? d - 0.5 * eps : 0.5 * eps - d;
+    }
+    else {
+        dup = direction > 0 ? eps : -eps;
+    }
+    const double duf = dup * (P.k_frame + P.mu) / P.k_frame;
+    for (int g = 0; g < nm; ++g) {
+        fqsb_system* s = m[g];
+        CU(cudaSetDevice(s->device));
+        k_slab_shift<<<1, 1, 0, s->stream>>>(s->S, s->d_du, dup, duf);
+        TRY(advance(s));
+    }
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(check_flags(m[g]));
+    }
+    if (du_frame) {
+        *du_frame = duf;
+    }
+    return FQSB_OK;
+}
+
+// the StopList replay as a plain host function (unit-tested without a GPU): ring_num / ring_den
+// [niter_tol] carry the state between calls (start: +inf / 1)
+int64_t fqsb_slab_first_stop(const double* log, int64_t k, double tol, int64_t niter_tol,
+                             double* ring_num, double* ring_den)
+{
+    HostRing ring((size_t)niter_tol);
+    for (int64_t i = 0; i < niter_tol; ++i) {
+        ring.num[(size_t)i] = ring_num[i];
+        ring.den[(size_t)i] = ring_den[i];
+    }
+    const i64 stop = slab_first_stop(log, k, ring, tol);
+    for (int64_t i = 0; i < niter_tol; ++i) {
+        ring_num[i] = ring.num[(size_t)i];
+        ring_den[i] = ring.den[(size_t)i];
+    }
+    return stop;
+}
+
+} // extern "C"

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FQSB_ABI_VERSION 3
+#define FQSB_ABI_VERSION 4
 
 typedef enum {
     FQSB_OK = 0,
@@ -198,8 +198,20 @@ int fqsb_chunk_state_at(fqsb_system* s, const int64_t* index, uint64_t* state, i
 int fqsb_chunk_restore(fqsb_system* s, const uint64_t* state, const double* value,
                        const int64_t* index, int64_t n);
 /* signed well-index change since `i_n` summed per realisation (the examples' S) and the number
- * of blocks that changed (A): out_S [R], out_A [R] (either may be NULL) */
-int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t* out_S, int64_t* out_A);
+ * of blocks that changed (A): i_n [R*size] (n = R*size is checked), out_S [R], out_A [R] (either
+ * may be NULL). ref: examples/Line1d_Cuspy_Laplace.py:59-61 */
+int fqsb_avalanche(fqsb_system* s, const int64_t* i_n, int64_t n, int64_t* out_S, int64_t* out_A);
+/* the same without moving R*size indices over PCIe twice per event:
+ * fqsb_mark_indices keeps a device-side copy of the current well indices (the `i_n =
+ * system.chunk.index_at_align` of the examples); fqsb_avalanche_since_mark reduces S = sum(i - i_n)
+ * and A = #(i != i_n) per realisation on the device and returns R x 16 bytes. */
+int fqsb_mark_indices(fqsb_system* s);
+int fqsb_avalanche_since_mark(fqsb_system* s, int64_t* out_S, int64_t* out_A);
+/* per-realisation event record of the last minimise(time_activity = 1) / minimise_truncate call,
+ * kept by the stepping kernel itself: S_abs = sum |i - i_n|, A = #(i != i_n) (ref:
+ * detail.h:1768-1778, 1863-1864), first / last = quasistaticActivityFirst / Last (ref: 1802-1818).
+ * Any pointer may be NULL. R x 32 bytes. */
+int fqsb_event_record(fqsb_system* s, int64_t* S_abs, int64_t* A, int64_t* first, int64_t* last);
 
 /* thermal systems: External = RandomNormalForcing (ref: detail.h:881-1000; classes
  * Line1d.h:261-330 System_Cuspy_Laplace_RandomForcing, Line1d.h:486-556
@@ -236,8 +248,50 @@ int fqsb_export_cells(fqsb_system* s, int64_t first, int64_t count, void* buf, i
 int fqsb_import_cells(fqsb_system* s, int64_t first, int64_t count, const void* buf, int on_device);
 /* u += du[r], u_frame += du_frame[r], re-align (advanceUniformly, ref: detail.h:2027-2050) */
 int fqsb_advance_uniformly(fqsb_system* s, const double* du, const double* du_frame);
-/* raw sums over the owned range, out [R][4] (see fqsb_api.cu) */
-int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, double* out);
+/* raw sums over the owned range, out [R][4] (see fqsb_api.cu); i_n [n] is read for what == 4 */
+int fqsb_reduce_sums(fqsb_system* s, int what, int direction, const int64_t* i_n, int64_t n,
+                     double* out);
+
+/* slab decomposition inside the library (BASELINE configs #3, #5) --------
+ * ONE very large line / interface over G GPUs: member g (a handle with nrealisations == 1,
+ * params.kernel = 2, params.seed_first / seed_period set) owns a contiguous range of rows and
+ * integrates them extended by `halo` rows per side. Batches of k <= halo steps run without
+ * communication; after a batch every member stores its outermost owned rows straight into its
+ * neighbours' memory (NVLink peer stores + st.release.sys epoch flags, no NCCL, no host staging)
+ * and its k x 5 log of per-step sums into every member's mailbox; the per-step stop decision of
+ * the reference (ref: detail.h:1754-1785) is replayed on the rank-ordered global sums, identically
+ * on every member. Members live in ONE process (`members` = all G handles, peer access between
+ * the devices) or in one process per GPU (`members` = the local handle, nmembers = 1; mailboxes
+ * shared through 64-byte CUDA IPC handles that the caller moves between the processes). */
+int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int kmax);
+int fqsb_slab_ipc_handle(fqsb_system* s, void* out64);
+/* locals [world] (entries may be NULL) : members living in this process; ipc_handles [world][64]
+ * (may be NULL): fqsb_slab_ipc_handle of the others */
+int fqsb_slab_connect(fqsb_system* s, fqsb_system* const* locals, const void* ipc_handles);
+/* out [8]: rank, world, halo_cells, own_lo, own_hi, batches, batches redone, graph in use */
+int fqsb_slab_info(fqsb_system* s, int64_t* out);
+int fqsb_slab_exchange(fqsb_system** members, int nmembers);
+/* timeSteps (flow == 0) / flowSteps (ref: detail.h:1577-1583, 1637-1645), `batch` steps per exchange */
+int fqsb_slab_time_steps(fqsb_system** members, int nmembers, int64_t n, int64_t batch, int flow,
+                         double v_frame);
+/* minimise, dynamic or overdamped (ref: detail.h:1676-1792); any niter_tol >= 1.
+ * *ret: 0 converged, steps + 1 otherwise; *steps: steps taken */
+int fqsb_slab_minimise(fqsb_system** members, int nmembers, double tol, int64_t niter_tol,
+                       int64_t max_iter, int64_t batch, int max_iter_is_error, int64_t* ret,
+                       int64_t* steps);
+/* sums over the whole system (members added in rank order), out [4]:
+ * what 1 {sum f^2, sum f_frame^2}, 2 {sum v^2, sum f_frame}, 3 {-, off-branch count, -, min
+ * displacement}, 4 {sum (i - i_mark), #(i != i_mark), sum |i - i_mark|} */
+int fqsb_slab_sums(fqsb_system** members, int nmembers, int what, int direction, double* out);
+int fqsb_slab_mark_indices(fqsb_system** members, int nmembers);
+/* ref: detail.h:1933-1960 */
+int fqsb_slab_event_driven_step(fqsb_system** members, int nmembers, double eps, int kick,
+                                int direction, double* du_frame);
+/* host-only: replay of the StopList criterion (GooseFEM::Iterate::StopList + detail.h:1780) over
+ * a batch log [k][5]; ring_num / ring_den [niter_tol] carry the ring between calls (start: +inf,
+ * 1). Returns the 1-based stopping step, 0 if none, -1 on NaN. */
+int64_t fqsb_slab_first_stop(const double* log, int64_t k, double tol, int64_t niter_tol,
+                             double* ring_num, double* ring_den);
 
 /* host staging helpers (pinned memory for the e2e path) ---------------------------------- */
 void* fqsb_host_alloc(size_t bytes);

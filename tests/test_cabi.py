@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     assert missing == []
     # and the Python binding declares a signature for each of them
     assert sorted(_capi.SIGNATURES) == declared_symbols()
-    assert lib.fqsb_abi_version() == 3
+    assert lib.fqsb_abi_version() == 4
 
 
 def test_params_struct_layout_matches_header():

@@ -109,3 +109,27 @@ def test_make_sharded_passes_disjoint_seeds_and_forcing():
         assert obj.kw["dinc"].shape == (N,)  # a shared schedule is passed through
         seen += list(range(first, first + count))
     assert seen == list(range(total))
+
+
+def test_make_sharded_follows_a_non_default_seed_stride():
+    """Realisation r of an Ensemble uses initstates seed + r*seed_stride + p (include/fqsb.h): a
+    shard must start at seed + first*seed_stride whatever the stride, or ranks would reuse
+    initstates of other ranks. A rank without realisations is an error (nrealisations = 0 would be
+    read as 1 by fqsb_create)."""
+    from frictionqpotspringblock_b200.distributed import make_sharded
+
+    class Recorder:
+        def __init__(self, **kw):
+            self.kw = kw
+
+    N, total, stride, seed = 8, 7, 1000, 11
+    unsharded = [seed + r * stride for r in range(total)]
+    got = []
+    for rank in range(3):
+        obj, first, count = make_sharded(Recorder, total, rank, 3, seed=seed, shape=[N],
+                                         seed_stride=stride)
+        assert obj.kw["seed_stride"] == stride
+        got += [obj.kw["seed"] + k * stride for k in range(count)]
+    assert got == unsharded
+    with pytest.raises(ValueError):
+        make_sharded(Recorder, 2, 2, 3, seed=0, shape=[N])
