@@ -107,6 +107,7 @@ cudaError_t launch_resident_thermal(const ResidentCfg& cfg, const Par& P, const 
 cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
                                cudaStream_t stream, int flip, int finalise);
 int stream_step_tiles(const Par& P, int generic_tiles);
+int stream_launch_tiles(const Par& P, int generic_tiles, bool sweep);
 int plan_band_rows(const Par& P, int resident, double halo, int max_tiles);
 const char* stream_step_name(const Par& P);
 // no-passing: launch l decides sweep l-1 and performs sweep l (`first`: nothing to decide yet)

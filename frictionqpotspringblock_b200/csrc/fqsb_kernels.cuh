@@ -689,7 +689,7 @@ __device__ __forceinline__ void block_sum(double (&x)[NV], double* scratch /* [3
 __device__ __forceinline__ void stream_finalise(const Par& P, const State& S, const RunArgs& A,
                                                 int r, int flip, double uf, double (&acc)[2],
                                                 int hops, int dS, int dA, double* scratch,
-                                                int* iscratch, int* s_last)
+                                                int* iscratch, int* s_last, const int fin = 1)
 {
     Ctl& ctl = S.ctl[r];
     block_sum<2>(acc, scratch);
@@ -707,6 +707,19 @@ __device__ __forceinline__ void stream_finalise(const Par& P, const State& S, co
         hops = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4] : 0);
         dS = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4 + 1] : 0);
         dA = __reduce_add_sync(0xffffffffu, lane < nw ? iscratch[lane * 4 + 2] : 0);
+    }
+    if ((fin & 3) == 2) {
+        // slab batches (fqsb_slab.inl): the per-CTA partials of step (fin >> 2) go to their own
+        // slot and are added up once per batch -- no ticket, no last-CTA tail between two steps
+        if (threadIdx.x == 0) {
+            double* slot = A.log + ((size_t)(fin >> 2) * gridDim.x + blockIdx.x) * FQSB_NPART;
+            slot[0] = acc[0];
+            slot[1] = acc[1];
+            slot[2] = (double)hops;
+            slot[3] = (double)dS;
+            slot[4] = (double)dA;
+        }
+        return;
     }
     double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
     if (threadIdx.x == 0) {
@@ -892,7 +905,7 @@ __global__ void __launch_bounds__(FQSB_ST_THREADS, 2)
         S.err[0] = 1;
     }
     if (finalise) {
-        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last, finalise);
     }
 }
 
@@ -1099,7 +1112,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
         S.err[0] = 1;
     }
     if (finalise) {
-        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last, finalise);
     }
 }
 
@@ -1179,7 +1192,7 @@ __global__ void __launch_bounds__(256)
         S.err[0] = 1;
     }
     if (finalise) {
-        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last, finalise);
     }
 }
 
@@ -1236,8 +1249,10 @@ template <int INT>
 __global__ void __launch_bounds__(256)
     k_stream_np(const __grid_constant__ Par P, const __grid_constant__ State S,
                 const __grid_constant__ RunArgs A, const int flip, const int first,
-                const int do_sweep)
+                const int sweep_arg)
 {
+    // sweep_arg: bit 0 = perform the sweep; bits 1.. = 1 + log slot of a slab batch (0: none)
+    const int do_sweep = sweep_arg & 1, slot = sweep_arg >> 1;
     __shared__ double scratch[32 * 2];
     __shared__ int s_last;
     const int r = blockIdx.y;
@@ -1329,6 +1344,19 @@ __global__ void __launch_bounds__(256)
         S.err[1] = 1;
     }
     block_sum<2>(acc, scratch);
+    if (slot) {
+        // slab batches (fqsb_slab.inl): this launch's residual partials belong to sweep slot - 1;
+        // they are added up once per batch -- no ticket, no last-CTA tail between two sweeps
+        if (threadIdx.x == 0 && !first) {
+            double* e = A.log + ((size_t)(slot - 1) * gridDim.x + blockIdx.x) * FQSB_NPART;
+            e[0] = acc[0];
+            e[1] = acc[1];
+            e[2] = 0.0;
+            e[3] = 0.0;
+            e[4] = 0.0;
+        }
+        return;
+    }
     double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
     if (threadIdx.x == 0) {
         part[0] = acc[0];
@@ -1351,8 +1379,10 @@ template <int CTAS> // resident CTAs per SM the register budget is sized for
 __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
     k_stream_np_2d(const __grid_constant__ Par P, const __grid_constant__ State S,
                    const __grid_constant__ RunArgs A, const int flip, const int first,
-                   const int do_sweep)
+                   const int sweep_arg)
 {
+    // sweep_arg: bit 0 = perform the sweep; bits 1.. = 1 + log slot of a slab batch (0: none)
+    const int do_sweep = sweep_arg & 1, slot = sweep_arg >> 1;
     constexpr int TX = FQSB_S2_TX;
     const int TY = P.s2_ty_np > 0 ? P.s2_ty_np : FQSB_S2_TY;
     __shared__ __align__(16) double su[4][TX + 4]; // [1] left halo, [2..2+TX) data, then right
@@ -1535,6 +1565,19 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
         S.err[1] = 1;
     }
     block_sum<2>(acc, scratch);
+    if (slot) {
+        // slab batches (fqsb_slab.inl): this launch's residual partials belong to sweep slot - 1;
+        // they are added up once per batch -- no ticket, no last-CTA tail between two sweeps
+        if (threadIdx.x == 0 && !first) {
+            double* e = A.log + ((size_t)(slot - 1) * gridDim.x + blockIdx.x) * FQSB_NPART;
+            e[0] = acc[0];
+            e[1] = acc[1];
+            e[2] = 0.0;
+            e[3] = 0.0;
+            e[4] = 0.0;
+        }
+        return;
+    }
     double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
     if (threadIdx.x == 0) {
         part[0] = acc[0];
@@ -1579,8 +1622,10 @@ template <int NS, int CTAS> // stages of the ring, resident CTAs per SM
 __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
     k_stream_np_2d_bulk(const __grid_constant__ Par P, const __grid_constant__ State S,
                         const __grid_constant__ RunArgs A, const int flip, const int first,
-                        const int do_sweep)
+                        const int sweep_arg)
 {
+    // sweep_arg: bit 0 = perform the sweep; bits 1.. = 1 + log slot of a slab batch (0: none)
+    const int do_sweep = sweep_arg & 1, slot = sweep_arg >> 1;
     constexpr int TX = FQSB_S2_TX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     BulkStage* stage = reinterpret_cast<BulkStage*>(smem_raw);
@@ -1758,6 +1803,19 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, CTAS)
         S.err[1] = 1;
     }
     block_sum<2>(acc, scratch);
+    if (slot) {
+        // slab batches (fqsb_slab.inl): this launch's residual partials belong to sweep slot - 1;
+        // they are added up once per batch -- no ticket, no last-CTA tail between two sweeps
+        if (threadIdx.x == 0 && !first) {
+            double* e = A.log + ((size_t)(slot - 1) * gridDim.x + blockIdx.x) * FQSB_NPART;
+            e[0] = acc[0];
+            e[1] = acc[1];
+            e[2] = 0.0;
+            e[3] = 0.0;
+            e[4] = 0.0;
+        }
+        return;
+    }
     double* part = S.part + ((size_t)r * gridDim.x + blockIdx.x) * FQSB_NPART;
     if (threadIdx.x == 0) {
         part[0] = acc[0];
@@ -2006,7 +2064,7 @@ __global__ void __launch_bounds__(FQSB_S2_THREADS, 2)
         S.err[0] = 1;
     }
     if (finalise) {
-        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last);
+        stream_finalise(P, S, A, r, flip, uf, acc, hops, dS, dA, scratch, iscratch, &s_last, finalise);
     }
 }
 

@@ -33,7 +33,7 @@ struct SlabDev {
     u64* peer[FQSB_SLAB_MAXW]; // mailboxes of all members (peer[rank] = own)
     u64* epoch;           // device [2]: halo / gather epochs completed by this member
     unsigned int* ticket; // device [2]
-    double* h_res;        // host-mapped [world * gcap]
+    double* h_res;        // host-mapped [2 gather parity][world * gcap]
     volatile int* h_status; // host-mapped: [0] peer timeout
     unsigned long long timeout_ns;
 };
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256)
     }
     if (nlog > 0 && blockIdx.x == 0) {
         const int gpar = (int)(ge & 1ULL);
+        double* res = D.h_res + (size_t)gpar * D.world * D.gcap;
         __syncthreads();
         if (threadIdx.x == 0) {
             s_ok = 1;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256)
             for (int i = threadIdx.x; i < nlog; i += blockDim.x) {
                 if (raw) {
                     for (int j = 0; j < D.world; ++j) {
-                        D.h_res[j * nlog + i] =
+                        res[j * nlog + i] =
                             __ldcg(slab_gather(self, gpar, j, D.hc, D.world, D.gcap) + i);
                     }
                 }
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(256)
                     for (int j = 0; j < D.world; ++j) {
                         acc += __ldcg(slab_gather(self, gpar, j, D.hc, D.world, D.gcap) + i);
                     }
-                    D.h_res[i] = acc;
+                    res[i] = acc;
                 }
             }
         }
@@ -246,6 +247,42 @@ __global__ void __launch_bounds__(256)
         }
         if (nlog > 0) {
             D.epoch[1] = ge;
+        }
+    }
+}
+
+// a logged batch leaves per-CTA partials [k][tiles][FQSB_NPART] (stream_finalise / the sweep
+// kernels in slot mode): add them up per step (CTAs in a fixed order) -> log [k][FQSB_NLOG], and
+// settle the bookkeeping the per-step finalise would have kept
+__global__ void __launch_bounds__(256)
+    k_slab_reduce_log(const State S, const double* part, int tiles, double* log, int k,
+                      int overdamped)
+{
+    __shared__ double scratch[32 * FQSB_NLOG];
+    const int j = blockIdx.x;
+    double tot[FQSB_NLOG] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* e = part + (size_t)j * tiles * FQSB_NPART;
+    for (int c = threadIdx.x; c < tiles; c += blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < FQSB_NLOG; ++q) {
+            tot[q] += e[(size_t)c * FQSB_NPART + q];
+        }
+    }
+    block_sum<FQSB_NLOG>(tot, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < FQSB_NLOG; ++q) {
+            log[j * FQSB_NLOG + q] = tot[q];
+        }
+        if (j == 0) {
+            Ctl& c = S.ctl[0];
+            if (!overdamped) {
+                c.inc += k; // detail.h:1541
+            }
+            c.steps = k;
+            c.flip = k & 1;
+            c.count = 0u;
+            c.status = ST_EXHAUSTED;
         }
     }
 }
@@ -297,6 +334,20 @@ __global__ void k_slab_shift(const State S, double* du, double dup, double duf)
 
 } // namespace fqsb
 
+struct SlabSnap {
+    u64* p[7];
+    double* uf;
+    Ctl* ctl;
+};
+
+struct SlabGraph { // CUDA graph of one batch shape (snapshot + k steps + reduce + push)
+    i64 k;
+    int gmode;
+    bool seen;
+    cudaGraphExec_t exec;
+};
+#define FQSB_SLAB_GRAPHS 6
+
 struct fqsb_slab_state {
     int rank, world;
     i64 halo_cells;
@@ -312,12 +363,13 @@ struct fqsb_slab_state {
     int* h_status;
     SlabDev dev;
     bool overdamped;
-    // CUDA graph of one full batch (snapshot + k logged steps + push + import), replayed while k
-    // and the mode stay the same
-    cudaGraphExec_t graph;
-    i64 graph_k, seen_k;
-    int graph_mode, seen_mode;
-    i64 batches, redone;
+    SlabSnap snap[2];   // two snapshots: a speculative batch keeps its predecessor's intact
+    double* d_part;     // [kmax][tiles][FQSB_NPART] per-CTA partials of a logged batch
+    int part_tiles;
+    cudaEvent_t ev[2];  // recorded after the import of a batch
+    u64 gathers;        // gather epochs enqueued so far (host mirror of d_epoch[1])
+    SlabGraph graphs[FQSB_SLAB_GRAPHS];
+    i64 batches, redone, wasted;
 };
 
 static int slab_require(fqsb_system* s, bool connected = true)
@@ -343,8 +395,15 @@ static void slab_free(fqsb_system* s)
             cudaIpcCloseMemHandle(L->peer[j]);
         }
     }
-    if (L->graph) {
-        cudaGraphExecDestroy(L->graph);
+    for (int k = 0; k < FQSB_SLAB_GRAPHS; ++k) {
+        if (L->graphs[k].exec) {
+            cudaGraphExecDestroy(L->graphs[k].exec);
+        }
+    }
+    for (int k = 0; k < 2; ++k) {
+        if (L->ev[k]) {
+            cudaEventDestroy(L->ev[k]);
+        }
     }
     if (L->mailbox) {
         cudaFree(L->mailbox);
@@ -366,81 +425,75 @@ static void slab_free(fqsb_system* s)
 }
 
 // all launches of `k` steps (Verlet, or no-passing sweeps) on the streaming kernels, without any
-// host synchronisation. MODE_LOG: per-step sums over the owned range -> s->d_log; MODE_FIXED:
-// plain steps.
+// host synchronisation. MODE_LOG: every launch leaves its per-CTA partial sums over the owned range
+// in its own slot, k_slab_reduce_log adds them up -> s->d_log [k][FQSB_NLOG]; MODE_FIXED: plain steps.
 static int slab_enqueue_steps(fqsb_system* s, i64 k, int mode, int flow, double v_frame)
 {
+    fqsb_slab_state* L = s->slab;
     const bool overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
     RunArgs A = make_args(mode, k);
     A.flow = flow;
     A.v_frame = v_frame;
     A.own_lo = (int)s->own_lo;
     A.own_hi = (int)s->own_hi;
-    A.log = s->d_log;
+    A.log = mode == MODE_LOG ? L->d_part : nullptr;
+    const bool slots = mode == MODE_LOG;
     const unsigned rg = (unsigned)((s->R + 127) / 128);
     k_ctl_begin<<<rg, 128, 0, s->stream>>>(s->P, s->S, 0, overdamped ? 1 : 0, s->d_out);
-    const int finalise = (mode != MODE_FIXED || flow) ? 1 : 0;
+    const int finalise = flow ? 1 : 0;
     const i64 nl = overdamped ? k + 1 : k;
     for (i64 b = 0; b < nl; ++b) {
-        cudaError_t e = overdamped
-                            ? launch_stream_sweep(s->P, s->S, A, s->stream, (int)(b & 1), b == 0, b < k)
-                            : launch_stream_step(s->P, s->S, A, s->stream, (int)(b & 1), finalise);
+        cudaError_t e;
+        if (overdamped) {
+            const int sweep = (b < k ? 1 : 0) | (slots ? (int)((b > 0 ? b : 1) << 1) : 0);
+            e = launch_stream_sweep(s->P, s->S, A, s->stream, (int)(b & 1), b == 0, sweep);
+        }
+        else {
+            e = launch_stream_step(s->P, s->S, A, s->stream, (int)(b & 1),
+                                   slots ? (2 | (int)(b << 2)) : finalise);
+        }
         if (e != cudaSuccess) {
             return cuda_fail(e, "stream kernel launch");
         }
     }
-    if (!finalise && !overdamped) {
+    if (slots) {
+        k_slab_reduce_log<<<(unsigned)k, 256, 0, s->stream>>>(s->S, L->d_part, L->part_tiles,
+                                                              s->d_log, (int)k, overdamped ? 1 : 0);
+    }
+    else if (!finalise && !overdamped) {
         k_stream_fixed_done<<<rg, 128, 0, s->stream>>>(s->P, s->S, k, 0);
     }
     dim3 grid((unsigned)s->S.tiles, (unsigned)s->R);
     k_stream_settle<<<grid, 256, 0, s->stream>>>(s->P, s->S, overdamped ? 0 : 1);
     k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
     CU(cudaGetLastError());
-    s->launches += nl + 3 + ((!finalise && !overdamped) ? 1 : 0);
+    s->launches += nl + 4;
     s->steps += k;
     invalidate_forces(s);
     return FQSB_OK;
 }
 
-static int slab_ensure_snapshot(fqsb_system* s)
+// slot: which of the two snapshots; restore = snapshot -> live state
+static int slab_copy_state(fqsb_system* s, int slot, bool restore)
 {
-    const size_t n = (size_t)s->n;
-    if (!s->snap_idx) {
-        for (int k = 0; k < 5; ++k) {
-            TRY(dev_alloc(s, &s->snap_d[k], n));
-        }
-        TRY(dev_alloc(s, &s->snap_idx, n));
-        TRY(dev_alloc(s, &s->snap_rng, n));
-        TRY(dev_alloc(s, &s->snap_uf, (size_t)s->R));
-        TRY(dev_alloc(s, &s->snap_ctl, (size_t)s->R));
-    }
-    return FQSB_OK;
-}
-
-static int slab_copy_state(fqsb_system* s, bool restore)
-{
+    const SlabSnap& Z = s->slab->snap[slot];
     SnapArgs X;
     u64* live[7] = {(u64*)s->S.u, (u64*)s->S.v, (u64*)s->S.a, (u64*)s->S.yl, (u64*)s->S.yr,
                     (u64*)s->S.idx, s->S.rng};
-    u64* snap[7] = {(u64*)s->snap_d[0], (u64*)s->snap_d[1], (u64*)s->snap_d[2], (u64*)s->snap_d[3],
-                    (u64*)s->snap_d[4], (u64*)s->snap_idx, s->snap_rng};
     for (int q = 0; q < 7; ++q) {
-        X.a[q] = restore ? snap[q] : live[q];
-        X.b[q] = restore ? live[q] : snap[q];
+        X.a[q] = restore ? Z.p[q] : live[q];
+        X.b[q] = restore ? live[q] : Z.p[q];
     }
-    X.uf_a = restore ? s->snap_uf : s->S.u_frame;
-    X.uf_b = restore ? s->S.u_frame : s->snap_uf;
-    X.ctl_a = restore ? s->snap_ctl : s->S.ctl;
-    X.ctl_b = restore ? s->S.ctl : s->snap_ctl;
+    X.uf_a = restore ? Z.uf : s->S.u_frame;
+    X.uf_b = restore ? s->S.u_frame : Z.uf;
+    X.ctl_a = restore ? Z.ctl : s->S.ctl;
+    X.ctl_b = restore ? s->S.ctl : Z.ctl;
     X.n = s->n;
     k_slab_copy_state<<<148 * 4, 256, 0, s->stream>>>(X);
     CU(cudaGetLastError());
     s->launches++;
     if (restore) {
         invalidate_forces(s);
-    }
-    else {
-        s->snap_valid = true;
     }
     return FQSB_OK;
 }
@@ -458,7 +511,9 @@ static int slab_enqueue_push(fqsb_system* s, int nlog, const double* src, int ha
     return FQSB_OK;
 }
 
-static int slab_enqueue_import(fqsb_system* s, int nlog, int raw, int halos)
+// returns (through *res) where the gathered values of this import will appear on the host
+static int slab_enqueue_import(fqsb_system* s, int nlog, int raw, int halos,
+                               const double** res = nullptr, int ev = -1)
 {
     fqsb_slab_state* L = s->slab;
     const i64 words = 14 * L->halo_cells;
@@ -467,8 +522,26 @@ static int slab_enqueue_import(fqsb_system* s, int nlog, int raw, int halos)
     k_slab_import<<<grid, 256, 0, s->stream>>>(s->S, L->dev, nlog, raw, halos);
     CU(cudaGetLastError());
     s->launches++;
+    if (nlog > 0) {
+        L->gathers++;
+        if (res) {
+            *res = L->h_res + (size_t)(L->gathers & 1ULL) * L->world * L->gcap;
+        }
+    }
+    if (ev >= 0) {
+        CU(cudaEventRecord(L->ev[ev], s->stream));
+    }
     if (halos) {
         invalidate_forces(s);
+    }
+    return FQSB_OK;
+}
+
+static int slab_status(fqsb_system* s)
+{
+    if (s->slab->h_status[0]) {
+        s->slab->h_status[0] = 0;
+        return fail(FQSB_ECUDA, "slab: timed out waiting for a neighbouring member");
     }
     return FQSB_OK;
 }
@@ -477,28 +550,32 @@ static int slab_sync(fqsb_system* s)
 {
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
-    if (s->slab->h_status[0]) {
-        s->slab->h_status[0] = 0;
-        return fail(FQSB_ECUDA, "slab: timed out waiting for a neighbouring member");
-    }
-    return FQSB_OK;
+    return slab_status(s);
 }
 
-// one batch on one member: [snapshot] + k steps + push, as direct launches or as a graph replay
-static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, bool snapshot, int flow,
+static int slab_wait_event(fqsb_system* s, int ev)
+{
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->slab->ev[ev]));
+    return slab_status(s);
+}
+
+// one batch on one member: [snapshot into `snap_slot`] + k steps + push, as direct launches or as
+// the replay of a CUDA graph captured on the second batch of the same shape
+static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, int snap_slot, int flow,
                               double v_frame)
 {
     CU(cudaSetDevice(s->device));
     fqsb_slab_state* L = s->slab;
     const int nlog = mode == MODE_LOG ? (int)(k * FQSB_NLOG) : 0;
-    const int gmode = mode * 4 + (snapshot ? 2 : 0) + (flow ? 1 : 0);
+    const int gmode = mode * 8 + (snap_slot + 1) * 2 + (flow ? 1 : 0);
     static const bool use_graph = [] {
         const char* e = std::getenv("FQSB_SLAB_GRAPH");
         return e ? std::atoi(e) != 0 : true;
     }();
     auto body = [&]() -> int {
-        if (snapshot) {
-            TRY(slab_copy_state(s, false));
+        if (snap_slot >= 0) {
+            TRY(slab_copy_state(s, snap_slot, false));
         }
         TRY(slab_enqueue_steps(s, k, mode, flow, v_frame));
         TRY(slab_enqueue_push(s, nlog, s->d_log, 1));
@@ -507,25 +584,36 @@ static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, bool snapshot, in
     if (!use_graph || flow) { // (flowSteps: v_frame is a kernel argument, not worth a graph)
         return body();
     }
-    auto replay = [&]() -> int {
-        CU(cudaGraphLaunch(L->graph, s->stream));
-        s->launches += k + 6;
-        s->steps += k;
-        invalidate_forces(s);
-        if (snapshot) {
-            s->snap_valid = true;
+    SlabGraph* G = nullptr;
+    for (int i = 0; i < FQSB_SLAB_GRAPHS; ++i) {
+        if (L->graphs[i].seen && L->graphs[i].k == k && L->graphs[i].gmode == gmode) {
+            G = &L->graphs[i];
         }
-        return FQSB_OK;
-    };
-    if (L->graph && L->graph_k == k && L->graph_mode == gmode) {
-        return replay();
     }
-    if (L->seen_k == k && L->seen_mode == gmode) {
-        // second batch of this shape (everything is allocated and warm): capture it
-        if (L->graph) {
-            cudaGraphExecDestroy(L->graph);
-            L->graph = nullptr;
+    if (!G) {
+        // first batch of this shape: direct launches (allocations, function attributes); shapes
+        // seen once only (e.g. the redone tail of a minimisation) are recycled first
+        for (int i = 0; i < FQSB_SLAB_GRAPHS && !G; ++i) {
+            if (!L->graphs[i].seen) {
+                G = &L->graphs[i];
+            }
         }
+        for (int i = 0; i < FQSB_SLAB_GRAPHS && !G; ++i) {
+            if (!L->graphs[i].exec) {
+                G = &L->graphs[i];
+            }
+        }
+        if (!G) {
+            G = &L->graphs[0];
+            cudaGraphExecDestroy(G->exec);
+        }
+        G->exec = nullptr;
+        G->seen = true;
+        G->k = k;
+        G->gmode = gmode;
+        return body();
+    }
+    if (!G->exec) { // second batch of this shape: capture it
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         const i64 launches0 = s->launches, steps0 = s->steps;
@@ -538,24 +626,22 @@ static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, bool snapshot, in
                 cudaGraphDestroy(g);
             }
             cudaGetLastError();
-            L->seen_k = 0;
+            G->seen = false;
             return rc != FQSB_OK ? rc : cuda_fail(ce, "slab graph capture");
         }
-        ce = cudaGraphInstantiate(&L->graph, g, 0);
+        ce = cudaGraphInstantiate(&G->exec, g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) {
-            L->graph = nullptr;
-            L->seen_k = 0;
+            G->exec = nullptr;
+            G->seen = false;
             return cuda_fail(ce, "cudaGraphInstantiate");
         }
-        L->graph_k = k;
-        L->graph_mode = gmode;
-        return replay();
     }
-    // first batch of this shape: direct launches (allocations, function attributes)
-    L->seen_k = k;
-    L->seen_mode = gmode;
-    return body();
+    CU(cudaGraphLaunch(G->exec, s->stream));
+    s->launches += k + 7;
+    s->steps += k;
+    invalidate_forces(s);
+    return FQSB_OK;
 }
 
 // ---- host-side StopList (GooseFEM::Iterate::StopList) in the (num, den) form
@@ -624,8 +710,9 @@ static int slab_flags_all(fqsb_system** m, int nm)
     return FQSB_OK;
 }
 
-// local reduction (k_reduce) on every member + raw gather: out[world][4] on every member's host
-static int slab_reduce_gather(fqsb_system** m, int nm, int what, int direction, bool use_mark)
+// local reduction (k_reduce) on every member + raw gather: (*res)[world][4] on the host
+static int slab_reduce_gather(fqsb_system** m, int nm, int what, int direction, bool use_mark,
+                              const double** res)
 {
     for (int g = 0; g < nm; ++g) {
         fqsb_system* s = m[g];
@@ -641,7 +728,7 @@ static int slab_reduce_gather(fqsb_system** m, int nm, int what, int direction, 
     }
     for (int g = 0; g < nm; ++g) {
         CU(cudaSetDevice(m[g]->device));
-        TRY(slab_enqueue_import(m[g], 4, 1, 0));
+        TRY(slab_enqueue_import(m[g], 4, 1, 0, g == 0 ? res : nullptr));
     }
     for (int g = 0; g < nm; ++g) {
         TRY(slab_sync(m[g]));
@@ -695,7 +782,7 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
         CU(cudaMemset(L->d_epoch, 0, 2 * sizeof(u64)));
         CU(cudaMalloc((void**)&L->d_ticket, 2 * sizeof(unsigned int)));
         CU(cudaMemset(L->d_ticket, 0, 2 * sizeof(unsigned int)));
-        const size_t res = (size_t)world * (size_t)L->gcap;
+        const size_t res = 2 * (size_t)world * (size_t)L->gcap;
         CU(cudaHostAlloc((void**)&L->h_res, res * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostAlloc((void**)&L->h_status, 4 * sizeof(int), cudaHostAllocMapped));
         memset(L->h_status, 0, 4 * sizeof(int));
@@ -705,7 +792,20 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
             s->log_cap = need;
         }
         TRY(ensure_stream_buffers(s));
-        TRY(slab_ensure_snapshot(s));
+        for (int z = 0; z < 2; ++z) {
+            for (int q = 0; q < 7; ++q) {
+                TRY(dev_alloc(s, &L->snap[z].p[q], (size_t)s->n));
+            }
+            TRY(dev_alloc(s, &L->snap[z].uf, 1));
+            TRY(dev_alloc(s, &L->snap[z].ctl, 1));
+            CU(cudaEventCreateWithFlags(&L->ev[z], cudaEventDisableTiming));
+        }
+        {
+            const int sweep_tiles = stream_launch_tiles(s->P, s->S.tiles, true);
+            const int step_tiles = stream_launch_tiles(s->P, s->S.tiles, false);
+            L->part_tiles = L->overdamped ? sweep_tiles : step_tiles;
+            TRY(dev_alloc(s, &L->d_part, (size_t)kmax * (size_t)L->part_tiles * FQSB_NPART));
+        }
         CU(cudaDeviceSynchronize());
         return FQSB_OK;
     };
@@ -806,8 +906,11 @@ int fqsb_slab_info(fqsb_system* s, int64_t* out /* [8] */)
     out[3] = s->own_lo;
     out[4] = s->own_hi;
     out[5] = L->batches;
-    out[6] = L->redone;
-    out[7] = L->graph ? 1 : 0;
+    out[6] = L->redone + (L->wasted << 32);
+    out[7] = 0;
+    for (int i = 0; i < FQSB_SLAB_GRAPHS; ++i) {
+        out[7] += L->graphs[i].exec ? 1 : 0;
+    }
     return FQSB_OK;
 }
 
@@ -845,7 +948,7 @@ int fqsb_slab_time_steps(fqsb_system** m, int nm, int64_t n, int64_t batch, int 
     while (left > 0) {
         const i64 k = left < batch ? left : batch;
         for (int g = 0; g < nm; ++g) {
-            TRY(slab_enqueue_batch(m[g], k, MODE_FIXED, false, flow, v_frame));
+            TRY(slab_enqueue_batch(m[g], k, MODE_FIXED, -1, flow, v_frame));
         }
         for (int g = 0; g < nm; ++g) {
             CU(cudaSetDevice(m[g]->device));
@@ -861,7 +964,10 @@ int fqsb_slab_time_steps(fqsb_system** m, int nm, int64_t n, int64_t batch, int 
 
 // minimise() of the decomposed system (detail.h:1676-1792, dynamic or overdamped): the reference
 // decides after every step; here every batch logs its per-step global sums and the criterion is
-// replayed on them. *ret: 0 converged, steps + 1 otherwise (quirk Q4). *steps_out: steps taken.
+// replayed on them. The host never sits between two batches: batch e+1 is enqueued (with its own
+// snapshot) before the sums of batch e are looked at; when batch e turns out to hold the stopping
+// step, the speculative batch is discarded by restoring a snapshot.
+// *ret: 0 converged, steps + 1 otherwise (quirk Q4). *steps_out: steps taken.
 int fqsb_slab_minimise(fqsb_system** m, int nm, double tol, int64_t niter_tol, int64_t max_iter,
                        int64_t batch, int max_iter_is_error, int64_t* ret, int64_t* steps_out)
 {
@@ -872,41 +978,94 @@ int fqsb_slab_minimise(fqsb_system** m, int nm, double tol, int64_t niter_tol, i
     if (niter_tol < 1 || batch < 1 || batch > m[0]->slab->kmax) {
         return fail(FQSB_EASSERT, ASSERT_MSG("niter_tol >= 1 && 1 <= batch <= kmax"));
     }
+    static const bool speculate = [] {
+        const char* e = std::getenv("FQSB_SLAB_SPECULATE");
+        return e ? std::atoi(e) != 0 : true;
+    }();
     HostRing ring((size_t)niter_tol);
-    i64 done = 0;
-    auto run_batch = [&](i64 k, bool snapshot) -> int {
+    // enqueue one batch on every member: snapshot into `slot`, k logged steps, push, import
+    auto enqueue = [&](i64 k, int slot, const double** res) -> int {
         for (int g = 0; g < nm; ++g) {
-            TRY(slab_enqueue_batch(m[g], k, MODE_LOG, snapshot, 0, 0.0));
+            TRY(slab_enqueue_batch(m[g], k, MODE_LOG, slot, 0, 0.0));
         }
         for (int g = 0; g < nm; ++g) {
             CU(cudaSetDevice(m[g]->device));
-            TRY(slab_enqueue_import(m[g], (int)(k * FQSB_NLOG), 0, 1));
-        }
-        for (int g = 0; g < nm; ++g) {
-            TRY(slab_sync(m[g]));
+            TRY(slab_enqueue_import(m[g], (int)(k * FQSB_NLOG), 0, 1, g == 0 ? res : nullptr,
+                                    slot >= 0 ? slot : 0));
             m[g]->slab->batches++;
         }
         return FQSB_OK;
     };
-    while (done < max_iter) {
-        const i64 k = batch < max_iter - done ? batch : max_iter - done;
-        TRY(run_batch(k, true));
+    auto wait = [&](int slot) -> int {
+        for (int g = 0; g < nm; ++g) {
+            TRY(slab_wait_event(m[g], slot));
+        }
+        return FQSB_OK;
+    };
+    auto restore = [&](int slot) -> int {
+        for (int g = 0; g < nm; ++g) {
+            CU(cudaSetDevice(m[g]->device));
+            TRY(slab_copy_state(m[g], slot, true));
+        }
+        return FQSB_OK;
+    };
+    auto finish = [&](i64 code, i64 steps) -> int {
+        TRY(slab_flags_all(m, nm));
+        if (ret) {
+            *ret = code;
+        }
+        if (steps_out) {
+            *steps_out = steps;
+        }
+        return FQSB_OK;
+    };
+    if (max_iter <= 0) {
+        TRY(finish(1, 0));
+        return max_iter_is_error ? fail(FQSB_ENOCONV, "No convergence found") : FQSB_OK;
+    }
+    i64 done = 0;
+    int slot = 0;
+    i64 k = batch < max_iter ? batch : max_iter;
+    const double* res = nullptr;
+    TRY(enqueue(k, slot, &res));
+    for (;;) {
+        // the next batch, before this one's sums are known
+        const i64 left = max_iter - done - k;
+        const i64 k_next = left < batch ? left : batch;
+        const double* res_next = nullptr;
+        const bool spec = speculate && k_next > 0;
+        if (spec) {
+            TRY(enqueue(k_next, slot ^ 1, &res_next));
+        }
+        TRY(wait(slot));
         const HostRing saved = ring;
-        const i64 stop = slab_first_stop(m[0]->slab->h_res, k, ring, tol);
+        const i64 stop = slab_first_stop(res, k, ring, tol);
         if (stop < 0) {
+            for (int g = 0; g < nm; ++g) {
+                slab_sync(m[g]);
+            }
             return fail(FQSB_ENAN, "NaN entries found"); // detail.h:1568
         }
         if (stop > 0) {
             if (stop < k) { // the criterion fired inside the batch: redo exactly `stop` steps
+                TRY(restore(slot));
+                ring = saved;
+                const double* res_redo = nullptr;
+                TRY(enqueue(stop, -1, &res_redo));
+                TRY(wait(0));
                 for (int g = 0; g < nm; ++g) {
-                    CU(cudaSetDevice(m[g]->device));
-                    TRY(slab_copy_state(m[g], true));
                     m[g]->slab->redone++;
                 }
-                ring = saved;
-                TRY(run_batch(stop, false));
-                if (slab_first_stop(m[0]->slab->h_res, stop, ring, tol) != stop) {
+                if (slab_first_stop(res_redo, stop, ring, tol) != stop) {
                     return fail(FQSB_EASSERT, "slab: the redone batch did not reproduce its log");
+                }
+            }
+            else if (spec) { // the speculative batch started from exactly the state to keep
+                TRY(restore(slot ^ 1));
+            }
+            if (spec) {
+                for (int g = 0; g < nm; ++g) {
+                    m[g]->slab->wasted++;
                 }
             }
             for (int g = 0; g < nm; ++g) { // quench(), detail.h:1781
@@ -915,24 +1074,20 @@ int fqsb_slab_minimise(fqsb_system** m, int nm, double tol, int64_t niter_tol, i
                 CU(cudaGetLastError());
                 m[g]->launches++;
             }
-            TRY(slab_flags_all(m, nm));
-            if (ret) {
-                *ret = 0;
-            }
-            if (steps_out) {
-                *steps_out = done + stop;
-            }
-            return FQSB_OK;
+            return finish(0, done + stop);
         }
         done += k;
+        if (k_next <= 0) {
+            break;
+        }
+        if (!spec) {
+            TRY(enqueue(k_next, slot ^ 1, &res_next));
+        }
+        k = k_next;
+        slot ^= 1;
+        res = res_next;
     }
-    TRY(slab_flags_all(m, nm));
-    if (ret) {
-        *ret = done + 1; // detail.h:1791 (quirk Q4)
-    }
-    if (steps_out) {
-        *steps_out = done;
-    }
+    TRY(finish(done + 1, done)); // detail.h:1791 (quirk Q4)
     if (max_iter_is_error) {
         return fail(FQSB_ENOCONV, "No convergence found"); // detail.h:1788
     }
@@ -949,14 +1104,15 @@ int fqsb_slab_sums(fqsb_system** m, int nm, int what, int direction, double* out
     if (what < 1 || what > 4) {
         return fail(FQSB_EASSERT, "unknown reduction");
     }
-    TRY(slab_reduce_gather(m, nm, what, direction, what == 4));
+    const double* res = nullptr;
+    TRY(slab_reduce_gather(m, nm, what, direction, what == 4, &res));
     const fqsb_slab_state* L = m[0]->slab;
     double acc[3] = {0.0, 0.0, 0.0}, mn = 1.7976931348623157e308;
     for (int j = 0; j < L->world; ++j) {
         for (int c = 0; c < 3; ++c) {
-            acc[c] += L->h_res[4 * j + c];
+            acc[c] += res[4 * j + c];
         }
-        mn = std::fmin(mn, L->h_res[4 * j + 3]);
+        mn = std::fmin(mn, res[4 * j + 3]);
     }
     out[0] = acc[0];
     out[1] = acc[1];

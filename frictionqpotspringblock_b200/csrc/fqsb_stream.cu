@@ -38,6 +38,26 @@ static int combo_of(int pot, int inter)
 
 bool combination_supported(int pot, int inter) { return combo_of(pot, inter) >= 0; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once on every
+// device a kernel is launched on (a process may drive several GPUs, e.g. the members of a slab)
+template <class K>
+static cudaError_t ensure_dynamic_smem(K kernel, size_t smem, bool (&done)[64])
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    if (dev >= 0 && dev < 64 && done[dev]) {
+        return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) {
+        done[dev] = true;
+    }
+    return e;
+}
+
 cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
                             const RunArgs& A, cudaStream_t stream)
 {
@@ -81,6 +101,15 @@ static int stream_sweep_tiles(const Par& P)
 {
     const int ty = P.s2_ty_np > 0 ? P.s2_ty_np : FQSB_S2_TY;
     return ((P.cols + FQSB_S2_TX - 1) / FQSB_S2_TX) * ((P.rows + ty - 1) / ty);
+}
+
+// CTAs per launch (x dimension) of the kernel launch_stream_step / launch_stream_sweep pick
+int stream_launch_tiles(const Par& P, int generic_tiles, bool sweep)
+{
+    if (sweep) {
+        return use_tiled_2d(P) ? stream_sweep_tiles(P) : generic_tiles;
+    }
+    return stream_step_tiles(P, generic_tiles);
 }
 
 // Rows per CTA of the row-marching 2-D kernels: the grid (strips x bands x realisations) should
@@ -156,9 +185,8 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
             const size_t smem = stream_2d_bulk_smem(NS);
 #define FQSB_2D_BULK(inter, unit_) \
     { \
-        static const cudaError_t attr = cudaFuncSetAttribute( \
-            k_stream_2d_bulk<inter, unit_, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-            (int)smem); \
+        static bool done[64] = {}; \
+        const cudaError_t attr = ensure_dynamic_smem(k_stream_2d_bulk<inter, unit_, NS>, smem, done); \
         if (attr != cudaSuccess) { \
             return attr; \
         } \
@@ -239,9 +267,9 @@ cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
         }();
         if (bulk) {
             constexpr int NS = FQSB_S2_BULK_STAGES;
-            static const cudaError_t attr = cudaFuncSetAttribute(
-                k_stream_np_2d_bulk<NS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                (int)stream_np_2d_bulk_smem(NS));
+            static bool done[64] = {};
+            const cudaError_t attr = ensure_dynamic_smem(k_stream_np_2d_bulk<NS, 2>,
+                                                         stream_np_2d_bulk_smem(NS), done);
             if (attr != cudaSuccess) {
                 return attr;
             }
