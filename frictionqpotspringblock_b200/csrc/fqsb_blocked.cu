@@ -134,11 +134,12 @@ BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
     }
     int sms = 148;
     {
-        int dev = 0;
-        cudaDeviceProp prop;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
-            prop.multiProcessorCount > 0) {
-            sms = prop.multiProcessorCount;
+        // (cudaDeviceGetAttribute, not cudaGetDeviceProperties: the latter costs milliseconds per
+        // call and the planner runs once per dynamics call)
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+            sms = n;
         }
     }
     if (own_hint > 0) {

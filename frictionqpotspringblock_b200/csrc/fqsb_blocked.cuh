@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(FQSB_BK_T)
     double uf = (flip ? K.uf2 : S.u_frame)[r];
 
     double v[B], a[B], yl[B], yr[B];
-    unsigned ownmask = 0u;
+    // ownmask: blocks this tile writes back; summask: those of them that enter the sums (a member
+    // of a slab-decomposed line leaves out the halo copies of its neighbours' blocks)
+    unsigned ownmask = 0u, summask = 0u;
 #pragma unroll
     for (int j = 0; j < B; ++j) {
         const int q = t + j * T;
@@ -105,6 +107,9 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         }
         if (q >= H && q < H + cnt) {
             ownmask |= 1u << j;
+            if (gp >= A.own_lo && gp < A.own_hi) {
+                summask |= 1u << j;
+            }
         }
     }
     // the cells just outside the tile stay frozen at their input value: the error this makes
@@ -172,6 +177,8 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                     sdidx[q] += moved;
                     if ((ownmask >> j) & 1u) { // halo copies are accounted for by their owner
                         underflow |= uflag;
+                    }
+                    if ((summask >> j) & 1u) {
                         hops += moved != 0;
                         track_hop(A, base + gp, i0, moved, dS, dA);
                     }
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(FQSB_BK_T)
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
             if (decltype(accumulate)::value) {
-                const bool own = (ownmask >> j) & 1u;
+                const bool own = (summask >> j) & 1u;
                 sf += own ? f * f : 0.0;
                 sff += own ? ff * ff : 0.0;
             }
@@ -333,6 +340,18 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         }
     }
     __syncthreads();
+    if (A.mode == MODE_LOG) {
+        // member of a slab-decomposed line (fqsb_slab.inl): hand the member's per-step sums over;
+        // the decision is taken on the sums of ALL members (k_slab_import), which then commits
+        // the batch or asks for a shorter one
+        for (int i = t; i < nsteps * FQSB_NLOG; i += T) {
+            A.log[i] = tot[i];
+        }
+        if (t == 0) {
+            ctl.count = 0u;
+        }
+        return;
+    }
     if (warp != 0) {
         return;
     }

@@ -251,6 +251,184 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// =============================================================================================
+// 1-D lines: every member runs the temporally blocked kernel (fqsb_blocked.cuh) on its local line,
+// ONE launch per batch of k steps. That kernel writes the complete new state into the other buffer
+// set, so a batch is revocable without a snapshot, and the commit / redo protocol of the single-GPU
+// kernel carries over: the stop decision moves from k_blocked's last tile into k_slab_import_blocked
+// -- after the members' per-step sums have been gathered -- where every member replays
+// timeStepsUntilEvent / minimise (detail.h:1605-1619, 1764-1784) on identical global sums and
+// either commits the batch (flips the buffer set) or asks for a batch of exactly s* steps. The host
+// only enqueues batches and polls the status.
+// =============================================================================================
+struct SlabPlanes {
+    u64* p[2][7]; // the two buffer sets: u, v, a, y_l, y_r, idx, rng
+};
+
+// set_arg 0 / 1: that buffer set; 2: the set the logged batch just wrote (Ctl::flip ^ 1)
+__global__ void __launch_bounds__(256)
+    k_slab_push_blocked(const State S, const SlabDev D, const SlabPlanes PL, const int set_arg,
+                        const double* log, const int logged)
+{
+    __shared__ int s_last;
+    const int set = set_arg < 2 ? set_arg : (S.ctl[0].flip ^ 1);
+    const int nlog = logged ? S.ctl[0].batch * FQSB_NLOG : 0;
+    const u64 e = D.epoch[0] + 1;
+    const int par = (int)(e & 1ULL);
+    const int prev = (D.rank + D.world - 1) % D.world, next = (D.rank + 1) % D.world;
+    u64* to_prev = slab_mail(D.peer[prev], par, 1, D.hc);
+    u64* to_next = slab_mail(D.peer[next], par, 0, D.hc);
+    const i64 top = D.hc, bot = D.n - 2 * D.hc;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        const u64* src = PL.p[set][q];
+        for (i64 c = t0; c < D.hc; c += stride) {
+            to_prev[(i64)q * D.hc + c] = src[top + c];
+            to_next[(i64)q * D.hc + c] = src[bot + c];
+        }
+    }
+    const u64 ge = D.epoch[1] + 1;
+    if (nlog > 0 && blockIdx.x == 0) {
+        const int gpar = (int)(ge & 1ULL);
+        for (int j = 0; j < D.world; ++j) {
+            double* dst = slab_gather(D.peer[j], gpar, D.rank, D.hc, D.world, D.gcap);
+            for (int i = threadIdx.x; i < nlog; i += blockDim.x) {
+                dst[i] = log[i];
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(&D.ticket[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    __threadfence_system();
+    if (threadIdx.x == 0) {
+        D.ticket[0] = 0u;
+        st_release_sys(D.peer[prev] + 1, e);
+        st_release_sys(D.peer[next] + 0, e);
+    }
+    if (logged && threadIdx.x < D.world) { // (published even when nlog == 0: the epochs stay in step)
+        st_release_sys(D.peer[threadIdx.x] + 2 + D.rank, ge);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_slab_import_blocked(const State S, const SlabDev D, const SlabPlanes PL, const int set_arg,
+                          const int logged, const RunArgs A, const int ksteps)
+{
+    __shared__ int s_ok, s_last;
+    __shared__ double tot[FQSB_BK_MAXSTEPS * FQSB_NLOG];
+    Ctl& ctl = S.ctl[0];
+    const int flip = ctl.flip;
+    const int set = set_arg < 2 ? set_arg : (flip ^ 1);
+    const int nsteps = logged ? ctl.batch : 0;
+    const bool running = ctl.status == ST_RUNNING;
+    const u64 e = D.epoch[0] + 1;
+    const u64 ge = D.epoch[1] + 1;
+    u64* self = D.peer[D.rank];
+    const int par = (int)(e & 1ULL);
+    if (threadIdx.x == 0) {
+        s_ok = slab_wait(self + 0, e, D) && slab_wait(self + 1, e, D);
+    }
+    __syncthreads();
+    if (s_ok) {
+        const u64* from_prev = slab_mail(self, par, 0, D.hc);
+        const u64* from_next = slab_mail(self, par, 1, D.hc);
+        const i64 stride = (i64)gridDim.x * blockDim.x;
+        const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+        const i64 bot = D.n - D.hc;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            u64* dst = PL.p[set][q];
+            for (i64 c = t0; c < D.hc; c += stride) {
+                dst[c] = __ldcg(from_prev + (i64)q * D.hc + c);
+                dst[bot + c] = __ldcg(from_next + (i64)q * D.hc + c);
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_last = atomicAdd(&D.ticket[1], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    // ---- the last CTA: every halo row of this member is in place. Gather the members' sums
+    //      (rank order), replay the per-step decisions, commit or ask for a redo
+    __threadfence();
+    if (logged) {
+        const int gpar = (int)(ge & 1ULL);
+        if (threadIdx.x == 0) {
+            s_ok = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x < D.world) {
+            if (!slab_wait(self + 2 + threadIdx.x, ge, D)) {
+                s_ok = 0;
+            }
+        }
+        __syncthreads();
+        const int nlog = nsteps * FQSB_NLOG;
+        for (int i = threadIdx.x; i < nlog; i += blockDim.x) {
+            double acc = 0.0;
+            for (int j = 0; j < D.world; ++j) {
+                acc += __ldcg(slab_gather(self, gpar, j, D.hc, D.world, D.gcap) + i);
+            }
+            tot[i] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && running && s_ok && nsteps > 0) {
+            const int lane = threadIdx.x;
+            Prog g;
+            prog_load(g, ctl);
+            RingEntry ring = ring_load(ctl, A, lane);
+            int status = ST_RUNNING;
+            double sf = 0.0, sff = 0.0;
+            int s = 0;
+            for (; s < nsteps; ++s) {
+                sf = tot[s * FQSB_NLOG];
+                sff = tot[s * FQSB_NLOG + 1];
+                g.inc++; // detail.h:1541
+                status = step_decide(A, g, ring, lane, sf, sff, (int)tot[s * FQSB_NLOG + 2],
+                                     (int)tot[s * FQSB_NLOG + 3], (int)tot[s * FQSB_NLOG + 4]);
+                if (status != ST_RUNNING) {
+                    break;
+                }
+            }
+            if (status == ST_RUNNING || s == nsteps - 1) { // commit
+                ring_store(ctl, A, lane, ring);
+                if (lane == 0) {
+                    prog_store(g, ctl);
+                    ctl.residual = residual_from_sums(sf, sff);
+                    ctl.flip = flip ^ 1;
+                    const i64 left = A.max_steps - g.steps;
+                    ctl.batch = (int)(left < ksteps ? left : ksteps);
+                    ctl.status = status;
+                }
+            }
+            else if (lane == 0) { // the criterion fired inside the batch: redo exactly s + 1 steps
+                ctl.batch = s + 1;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        D.ticket[1] = 0u;
+        D.epoch[0] = e;
+        if (logged) {
+            D.epoch[1] = ge;
+        }
+    }
+}
+
 // a logged batch leaves per-CTA partials [k][tiles][FQSB_NPART] (stream_finalise / the sweep
 // kernels in slot mode): add them up per step (CTAs in a fixed order) -> log [k][FQSB_NLOG], and
 // settle the bookkeeping the per-step finalise would have kept
@@ -363,6 +541,7 @@ struct fqsb_slab_state {
     int* h_status;
     SlabDev dev;
     bool overdamped;
+    bool blocked;       // 1-D line: members run the temporally blocked kernel
     SlabSnap snap[2];   // two snapshots: a speculative batch keeps its predecessor's intact
     double* d_part;     // [kmax][tiles][FQSB_NPART] per-CTA partials of a logged batch
     int part_tiles;
@@ -371,6 +550,8 @@ struct fqsb_slab_state {
     SlabGraph graphs[FQSB_SLAB_GRAPHS];
     i64 batches, redone, wasted;
 };
+
+static int slab_flags_all_fwd(fqsb_system** m, int nm);
 
 static int slab_require(fqsb_system* s, bool connected = true)
 {
@@ -644,6 +825,173 @@ static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, int snap_slot, in
     return FQSB_OK;
 }
 
+// ---- 1-D lines on the temporally blocked kernel ------------------------------------------------
+static SlabPlanes slab_planes(const fqsb_system* s)
+{
+    SlabPlanes PL;
+    u64* a[7] = {(u64*)s->S.u, (u64*)s->S.v, (u64*)s->S.a, (u64*)s->S.yl, (u64*)s->S.yr,
+                 (u64*)s->S.idx, s->S.rng};
+    u64* b[7] = {(u64*)s->S.u2, (u64*)s->S.v2, (u64*)s->S.a2, (u64*)s->bk.yl2, (u64*)s->bk.yr2,
+                 (u64*)s->bk.idx2, s->bk.rng2};
+    for (int q = 0; q < 7; ++q) {
+        PL.p[0][q] = a[q];
+        PL.p[1][q] = b[q];
+    }
+    return PL;
+}
+
+static unsigned slab_copy_grid(const fqsb_slab_state* L, unsigned cap)
+{
+    const i64 words = 14 * L->halo_cells;
+    unsigned grid = (unsigned)((words + 4095) / 4096);
+    return grid < 1u ? 1u : (grid > cap ? cap : grid);
+}
+
+// One dynamics call of a slab of blocked members. A.mode == MODE_FIXED: n = A.max_steps steps in
+// batches of `batch`; stop modes: batches until every member's (identical) status leaves
+// ST_RUNNING. On return the current state sits in the primary buffer set and h_ctl is up to date.
+static int slab_blocked_run(fqsb_system** m, int nm, RunArgs A, i64 batch)
+{
+    if (batch > FQSB_BK_MAXSTEPS) {
+        batch = FQSB_BK_MAXSTEPS;
+    }
+    std::vector<BlockedPlan> plan((size_t)nm);
+    for (int g = 0; g < nm; ++g) {
+        fqsb_system* s = m[g];
+        CU(cudaSetDevice(s->device));
+        plan[(size_t)g] = blocked_plan(s->P, (int)batch, (s->par.kernel >> 16) & 0xffff);
+        const BlockedPlan& pl = plan[(size_t)g];
+        if (pl.B < 2 || pl.B > 8 || blocked_smem(pl.B) > 227 * 1024 || pl.ksteps < batch) {
+            return fail(FQSB_EUNSUPPORTED, "no tile geometry for the blocked kernel");
+        }
+        TRY(ensure_blocked_buffers(s, pl));
+        const unsigned rg = (unsigned)((s->R + 127) / 128);
+        k_ctl_begin<<<rg, 128, 0, s->stream>>>(s->P, s->S, 0, 0, s->d_out);
+        CU(cudaGetLastError());
+        s->launches++;
+        s->last_kernel = "slab_blocked_1d";
+        invalidate_forces(s);
+    }
+    A.own_lo = (int)m[0]->own_lo;
+    A.own_hi = (int)m[0]->own_hi;
+    if (A.mode == MODE_FIXED) {
+        int parity = 0;
+        i64 left = A.max_steps;
+        while (left > 0) {
+            const i64 k = left < batch ? left : batch;
+            for (int g = 0; g < nm; ++g) {
+                fqsb_system* s = m[g];
+                CU(cudaSetDevice(s->device));
+                RunArgs Ag = A;
+                Ag.own_lo = (int)s->own_lo;
+                Ag.own_hi = (int)s->own_hi;
+                BlockedArgs K = s->bk;
+                K.nsteps = (int)k;
+                K.flip = parity;
+                cudaError_t e = launch_blocked(plan[(size_t)g], s->P, s->S, Ag, K, s->stream);
+                if (e != cudaSuccess) {
+                    return cuda_fail(e, "blocked kernel launch");
+                }
+                k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
+                    s->S, s->slab->dev, slab_planes(s), parity ^ 1, nullptr, 0);
+                CU(cudaGetLastError());
+                s->launches += 2;
+                s->steps += k;
+            }
+            for (int g = 0; g < nm; ++g) {
+                fqsb_system* s = m[g];
+                CU(cudaSetDevice(s->device));
+                k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
+                    s->S, s->slab->dev, slab_planes(s), parity ^ 1, 0, A, (int)batch);
+                CU(cudaGetLastError());
+                s->launches++;
+            }
+            parity ^= 1;
+            left -= k;
+        }
+        for (int g = 0; g < nm; ++g) {
+            fqsb_system* s = m[g];
+            CU(cudaSetDevice(s->device));
+            CU(launch_blocked_fixed_done(s->P, s->S, A.max_steps, parity, s->stream));
+            s->launches++;
+        }
+    }
+    else {
+        RunArgs Alog = A;
+        Alog.mode = MODE_LOG;
+        Alog.track = 0;
+        for (int g = 0; g < nm; ++g) {
+            fqsb_system* s = m[g];
+            CU(cudaSetDevice(s->device));
+            CU(launch_blocked_begin(s->P, s->S, (int)batch, A.max_steps, s->stream));
+            s->launches++;
+        }
+        i64 nb = 4;
+        for (;;) {
+            for (i64 b = 0; b < nb; ++b) {
+                for (int g = 0; g < nm; ++g) {
+                    fqsb_system* s = m[g];
+                    CU(cudaSetDevice(s->device));
+                    RunArgs Ag = Alog;
+                    Ag.own_lo = (int)s->own_lo;
+                    Ag.own_hi = (int)s->own_hi;
+                    Ag.log = s->d_log;
+                    cudaError_t e =
+                        launch_blocked(plan[(size_t)g], s->P, s->S, Ag, s->bk, s->stream);
+                    if (e != cudaSuccess) {
+                        return cuda_fail(e, "blocked kernel launch");
+                    }
+                    k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
+                        s->S, s->slab->dev, slab_planes(s), 2, s->d_log, 1);
+                    CU(cudaGetLastError());
+                    s->launches += 2;
+                }
+                for (int g = 0; g < nm; ++g) {
+                    fqsb_system* s = m[g];
+                    CU(cudaSetDevice(s->device));
+                    k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
+                        s->S, s->slab->dev, slab_planes(s), 2, 1, A, (int)batch);
+                    CU(cudaGetLastError());
+                    s->launches++;
+                    s->slab->batches++;
+                    s->slab->gathers++;
+                }
+            }
+            bool running = false;
+            for (int g = 0; g < nm; ++g) {
+                CU(cudaSetDevice(m[g]->device));
+                TRY(pull_ctl(m[g]));
+                TRY(slab_status(m[g]));
+                running |= m[g]->h_ctl[0].status == ST_RUNNING;
+            }
+            if (!running) {
+                break;
+            }
+            if (nb < 64) {
+                nb *= 2;
+            }
+        }
+    }
+    for (int g = 0; g < nm; ++g) {
+        fqsb_system* s = m[g];
+        CU(cudaSetDevice(s->device));
+        CU(launch_blocked_settle(s->P, s->S, s->bk, s->stream));
+        const unsigned rg = (unsigned)((s->R + 127) / 128);
+        k_stream_settle_flags<<<rg, 128, 0, s->stream>>>(s->P, s->S);
+        CU(cudaGetLastError());
+        s->launches += 2;
+    }
+    for (int g = 0; g < nm; ++g) {
+        CU(cudaSetDevice(m[g]->device));
+        TRY(pull_ctl(m[g]));
+        TRY(slab_status(m[g]));
+        if (A.mode != MODE_FIXED) {
+            m[g]->steps += m[g]->h_ctl[0].steps;
+        }
+    }
+    return slab_flags_all_fwd(m, nm);
+}
+
 // ---- host-side StopList (GooseFEM::Iterate::StopList) in the (num, den) form
 //      of the device (fqsb_device.cuh: ring_stop), any niter_tol
 struct HostRing {
@@ -710,6 +1058,8 @@ static int slab_flags_all(fqsb_system** m, int nm)
     return FQSB_OK;
 }
 
+static int slab_flags_all_fwd(fqsb_system** m, int nm) { return slab_flags_all(m, nm); }
+
 // local reduction (k_reduce) on every member + raw gather: (*res)[world][4] on the host
 static int slab_reduce_gather(fqsb_system** m, int nm, int what, int direction, bool use_mark,
                               const double** res)
@@ -759,8 +1109,16 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
         return fail(FQSB_EUNSUPPORTED,
                     "slab decomposition needs a nearest-neighbour, athermal system");
     }
-    if ((s->par.kernel & 15) != 2) {
-        return fail(FQSB_EASSERT, "slab members run the streaming kernels (params.kernel = 2)");
+    const int ksel = s->par.kernel & 15;
+    if (ksel == 1) {
+        return fail(FQSB_EASSERT, "a slab member cannot be forced onto the resident kernel");
+    }
+    // 1-D nearest-neighbour lines: the temporally blocked kernel (one launch per batch) unless the
+    // streaming kernels are forced; everything else streams
+    const bool blocked = ksel != 2 && s->P.rank == 1 && blocked_supported(s->P) &&
+                         s->par.minimisation == FQSB_MIN_DYNAMIC;
+    if (ksel == 3 && !blocked) {
+        return fail(FQSB_EUNSUPPORTED, "no blocked kernel for this system");
     }
     if (kmax < 1) {
         kmax = 64;
@@ -774,6 +1132,7 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
     L->kmax = kmax;
     L->gcap = kmax * FQSB_NLOG > 8 ? kmax * FQSB_NLOG : 8;
     L->overdamped = s->par.minimisation == FQSB_MIN_OVERDAMPED;
+    L->blocked = blocked;
     L->mailbox_bytes = slab_mailbox_words(halo_cells, world, L->gcap) * 8;
     auto build = [&]() -> int {
         CU(cudaMalloc((void**)&L->mailbox, L->mailbox_bytes));
@@ -793,11 +1152,13 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
         }
         TRY(ensure_stream_buffers(s));
         for (int z = 0; z < 2; ++z) {
-            for (int q = 0; q < 7; ++q) {
-                TRY(dev_alloc(s, &L->snap[z].p[q], (size_t)s->n));
+            if (!blocked) { // (a blocked batch is revocable by itself: no snapshots)
+                for (int q = 0; q < 7; ++q) {
+                    TRY(dev_alloc(s, &L->snap[z].p[q], (size_t)s->n));
+                }
+                TRY(dev_alloc(s, &L->snap[z].uf, 1));
+                TRY(dev_alloc(s, &L->snap[z].ctl, 1));
             }
-            TRY(dev_alloc(s, &L->snap[z].uf, 1));
-            TRY(dev_alloc(s, &L->snap[z].ctl, 1));
             CU(cudaEventCreateWithFlags(&L->ev[z], cudaEventDisableTiming));
         }
         {
@@ -944,6 +1305,12 @@ int fqsb_slab_time_steps(fqsb_system** m, int nm, int64_t n, int64_t batch, int 
     if (n < 0 || batch < 1) {
         return fail(FQSB_EASSERT, ASSERT_MSG("n >= 0 && batch >= 1"));
     }
+    if (m[0]->slab->blocked) {
+        RunArgs A = make_args(MODE_FIXED, n);
+        A.flow = flow;
+        A.v_frame = v_frame;
+        return n > 0 ? slab_blocked_run(m, nm, A, batch) : FQSB_OK;
+    }
     i64 left = n;
     while (left > 0) {
         const i64 k = left < batch ? left : batch;
@@ -977,6 +1344,28 @@ int fqsb_slab_minimise(fqsb_system** m, int nm, double tol, int64_t niter_tol, i
     }
     if (niter_tol < 1 || batch < 1 || batch > m[0]->slab->kmax) {
         return fail(FQSB_EASSERT, ASSERT_MSG("niter_tol >= 1 && 1 <= batch <= kmax"));
+    }
+    if (m[0]->slab->blocked && niter_tol <= FQSB_RING && max_iter > 0) {
+        // (longer StopLists than the device's warp-held ring take the host replay below)
+        RunArgs A = make_args(MODE_MINIMISE, max_iter);
+        A.tol = tol;
+        A.tol2 = tol * tol;
+        A.niter_tol = (int)niter_tol;
+        TRY(slab_blocked_run(m, nm, A, batch));
+        const Ctl& c = m[0]->h_ctl[0];
+        if (c.status == ST_NAN) {
+            return fail(FQSB_ENAN, "NaN entries found");
+        }
+        if (ret) {
+            *ret = c.status == ST_CONVERGED ? 0 : c.steps + 1;
+        }
+        if (steps_out) {
+            *steps_out = c.steps;
+        }
+        if (c.status != ST_CONVERGED && max_iter_is_error) {
+            return fail(FQSB_ENOCONV, "No convergence found");
+        }
+        return FQSB_OK;
     }
     static const bool speculate = [] {
         const char* e = std::getenv("FQSB_SLAB_SPECULATE");

@@ -96,7 +96,7 @@ class SlabSystem:
     ``residual``, S) are identical on every member / rank."""
 
     def __init__(self, module: str, cls: str, *, halo: int = 32, devices=None, rank: int = 0,
-                 world: int = 1, device: int = -1, allgather=None, batch=None, **kw):
+                 world: int = 1, device: int = -1, allgather=None, batch=None, kernel=None, **kw):
         if cls not in SUPPORTED.get(module, ()):
             raise RuntimeError(f"slab decomposition is not available for {module}.{cls}: it needs a "
                                "nearest-neighbour, athermal system")
@@ -110,6 +110,14 @@ class SlabSystem:
         # their forces are exact for k = halo. Jacobi sweeps: the residual of state k reads the
         # neighbouring halo row AT state k, which is exact only for k <= halo - 1.
         kmax = self.halo - 1 if self._overdamped else self.halo
+        # kernel of the members: 1-D dynamic lines take the temporally blocked kernel (one launch =
+        # one batch of <= 64 steps, stop decision on the device), everything else streams (one
+        # launch per step, CUDA-graph batches). `kernel=2` forces the streaming kernels.
+        if kernel is None:
+            kernel = 0 if (module == "Line1d" and not self._overdamped) else 2
+        self.kernel = int(kernel)
+        if (self.kernel & 15) != 2:
+            kmax = min(kmax, 64)  # FQSB_BK_MAXSTEPS
         self.batch = kmax if batch is None else int(batch)
         if not 1 <= self.batch <= kmax:
             raise ValueError("batch must be in [1, halo] (halo - 1 for the no-passing sweeps)")
@@ -126,7 +134,7 @@ class SlabSystem:
         self.plans = [slab_plan(shape, r, self.world, self.halo) for r in ranks]
         self.members = []
         for r, d, plan in zip(ranks, devs, self.plans):
-            m = getattr(ns, cls)(shape=plan["local_shape"], kernel=2, device=d,
+            m = getattr(ns, cls)(shape=plan["local_shape"], kernel=self.kernel, device=d,
                                  seed_first=plan["seed_first"], seed_period=plan["seed_period"],
                                  **kw)
             check(lib.fqsb_slab_init(m._h, r, self.world, plan["halo_cells"], self.halo))
