@@ -420,11 +420,13 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         D.ticket[1] = 0u;
         D.epoch[0] = e;
         if (logged) {
             D.epoch[1] = ge;
+            D.h_status[1] = ctl.status; // the host stops enqueueing batches once this leaves RUNNING
         }
     }
 }
@@ -546,6 +548,7 @@ struct fqsb_slab_state {
     double* d_part;     // [kmax][tiles][FQSB_NPART] per-CTA partials of a logged batch
     int part_tiles;
     cudaEvent_t ev[2];  // recorded after the import of a batch
+    cudaEvent_t evb[4]; // blocked path: ring of events bounding the host's run-ahead
     u64 gathers;        // gather epochs enqueued so far (host mirror of d_epoch[1])
     SlabGraph graphs[FQSB_SLAB_GRAPHS];
     i64 batches, redone, wasted;
@@ -584,6 +587,11 @@ static void slab_free(fqsb_system* s)
     for (int k = 0; k < 2; ++k) {
         if (L->ev[k]) {
             cudaEventDestroy(L->ev[k]);
+        }
+    }
+    for (int k = 0; k < 4; ++k) {
+        if (L->evb[k]) {
+            cudaEventDestroy(L->evb[k]);
         }
     }
     if (L->mailbox) {
@@ -734,10 +742,10 @@ static int slab_sync(fqsb_system* s)
     return slab_status(s);
 }
 
-static int slab_wait_event(fqsb_system* s, int ev)
+static int slab_wait_event(fqsb_system* s, int ev, bool blocked_ring = false)
 {
     CU(cudaSetDevice(s->device));
-    CU(cudaEventSynchronize(s->slab->ev[ev]));
+    CU(cudaEventSynchronize(blocked_ring ? s->slab->evb[ev] : s->slab->ev[ev]));
     return slab_status(s);
 }
 
@@ -792,9 +800,27 @@ static int slab_enqueue_batch(fqsb_system* s, i64 k, int mode, int snap_slot, in
         G->seen = true;
         G->k = k;
         G->gmode = gmode;
-        return body();
+        TRY(body());
+        // ... and captured right away (the GPU is busy with the batch just enqueued), so that the
+        // next batch of this shape is a single graph launch
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const i64 launches0 = s->launches, steps0 = s->steps;
+        int rc = body();
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        s->launches = launches0;
+        s->steps = steps0;
+        if (rc == FQSB_OK && ce == cudaSuccess && g &&
+            cudaGraphInstantiate(&G->exec, g, 0) != cudaSuccess) {
+            G->exec = nullptr;
+        }
+        if (g) {
+            cudaGraphDestroy(g);
+        }
+        cudaGetLastError();
+        return FQSB_OK;
     }
-    if (!G->exec) { // second batch of this shape: capture it
+    if (!G->exec) { // (the capture after the first batch failed: try once more)
         cudaGraph_t g = nullptr;
         CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         const i64 launches0 = s->launches, steps0 = s->steps;
@@ -926,49 +952,49 @@ static int slab_blocked_run(fqsb_system** m, int nm, RunArgs A, i64 batch)
             CU(launch_blocked_begin(s->P, s->S, (int)batch, A.max_steps, s->stream));
             s->launches++;
         }
-        i64 nb = 4;
-        for (;;) {
-            for (i64 b = 0; b < nb; ++b) {
+        // The host runs at most 3 batches ahead of the device: batch b is enqueued once batch b - 3
+        // has finished, and only while the status the import kernel mirrors into host-mapped
+        // memory says "running". No synchronisation of the whole stream inside the loop.
+        for (int g = 0; g < nm; ++g) {
+            m[g]->slab->h_status[1] = ST_RUNNING;
+        }
+        for (i64 b = 0;; ++b) {
+            if (b >= 3) {
+                bool running = true;
                 for (int g = 0; g < nm; ++g) {
-                    fqsb_system* s = m[g];
-                    CU(cudaSetDevice(s->device));
-                    RunArgs Ag = Alog;
-                    Ag.own_lo = (int)s->own_lo;
-                    Ag.own_hi = (int)s->own_hi;
-                    Ag.log = s->d_log;
-                    cudaError_t e =
-                        launch_blocked(plan[(size_t)g], s->P, s->S, Ag, s->bk, s->stream);
-                    if (e != cudaSuccess) {
-                        return cuda_fail(e, "blocked kernel launch");
-                    }
-                    k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
-                        s->S, s->slab->dev, slab_planes(s), 2, s->d_log, 1);
-                    CU(cudaGetLastError());
-                    s->launches += 2;
+                    TRY(slab_wait_event(m[g], (int)((b - 3) & 3), true));
+                    running = running && m[g]->slab->h_status[1] == ST_RUNNING;
                 }
-                for (int g = 0; g < nm; ++g) {
-                    fqsb_system* s = m[g];
-                    CU(cudaSetDevice(s->device));
-                    k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
-                        s->S, s->slab->dev, slab_planes(s), 2, 1, A, (int)batch);
-                    CU(cudaGetLastError());
-                    s->launches++;
-                    s->slab->batches++;
-                    s->slab->gathers++;
+                if (!running) {
+                    break;
                 }
             }
-            bool running = false;
             for (int g = 0; g < nm; ++g) {
-                CU(cudaSetDevice(m[g]->device));
-                TRY(pull_ctl(m[g]));
-                TRY(slab_status(m[g]));
-                running |= m[g]->h_ctl[0].status == ST_RUNNING;
+                fqsb_system* s = m[g];
+                CU(cudaSetDevice(s->device));
+                RunArgs Ag = Alog;
+                Ag.own_lo = (int)s->own_lo;
+                Ag.own_hi = (int)s->own_hi;
+                Ag.log = s->d_log;
+                cudaError_t e = launch_blocked(plan[(size_t)g], s->P, s->S, Ag, s->bk, s->stream);
+                if (e != cudaSuccess) {
+                    return cuda_fail(e, "blocked kernel launch");
+                }
+                k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
+                    s->S, s->slab->dev, slab_planes(s), 2, s->d_log, 1);
+                CU(cudaGetLastError());
+                s->launches += 2;
             }
-            if (!running) {
-                break;
-            }
-            if (nb < 64) {
-                nb *= 2;
+            for (int g = 0; g < nm; ++g) {
+                fqsb_system* s = m[g];
+                CU(cudaSetDevice(s->device));
+                k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
+                    s->S, s->slab->dev, slab_planes(s), 2, 1, A, (int)batch);
+                CU(cudaGetLastError());
+                CU(cudaEventRecord(s->slab->evb[b & 3], s->stream));
+                s->launches++;
+                s->slab->batches++;
+                s->slab->gathers++;
             }
         }
     }
@@ -1160,6 +1186,9 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
                 TRY(dev_alloc(s, &L->snap[z].ctl, 1));
             }
             CU(cudaEventCreateWithFlags(&L->ev[z], cudaEventDisableTiming));
+        }
+        for (int z = 0; z < 4; ++z) {
+            CU(cudaEventCreateWithFlags(&L->evb[z], cudaEventDisableTiming));
         }
         {
             const int sweep_tiles = stream_launch_tiles(s->P, s->S.tiles, true);
