@@ -101,6 +101,7 @@ SIGNATURES = {
     "fqsb_qs_activity": (C.c_int, [_P, _P, _P]),
     "fqsb_time_steps": (C.c_int, [_P, C.c_int64]),
     "fqsb_flow_steps": (C.c_int, [_P, C.c_int64, C.c_double]),
+    "fqsb_run_from_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P]),
     "fqsb_time_steps_until_event": (C.c_int, [_P, C.c_double, C.c_int64, C.c_int64, _P]),
     "fqsb_minimise": (C.c_int, [_P, C.c_double, C.c_int64, C.c_int64, C.c_int, C.c_int, _P]),
     "fqsb_minimise_truncate": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, C.c_int64,

@@ -410,6 +410,30 @@ class Ensemble:
         self._no_dynamics()
         check(lib.fqsb_time_steps(self._h, int(n)))
 
+    def run_from_host(self, n, u=None, v=None, a=None, out_u=None, out_v=None, out_a=None,
+                      mean_f_frame=None):
+        """``self.u = u; self.v = v; self.a = a; self.timeSteps(n)`` and the read-back of
+        ``u, v, a`` / ``np.mean(f_frame)`` per realisation as ONE call whose host<->device copies
+        overlap the kernels (chunks of realisations on internal streams of the handle). Arrays
+        are C-contiguous float64 of the ensemble's shape (pinned memory gives real overlap);
+        ``None`` keeps the current array / skips the read-back."""
+        self._no_dynamics()
+
+        def ptr(x, shape, writable):
+            if x is None:
+                return None
+            if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous
+                    and x.shape == shape and (x.flags.writeable or not writable)):
+                raise RuntimeError("assertion failed (xt::has_shape(arg, m_u.shape()))")
+            return x.ctypes.data
+
+        sh = self._user_shape
+        check(lib.fqsb_run_from_host(
+            self._h, ptr(u, sh, False), ptr(v, sh, False), ptr(a, sh, False),
+            int(np.prod(self._full_shape)), int(n), ptr(out_u, sh, True), ptr(out_v, sh, True),
+            ptr(out_a, sh, True),
+            ptr(mean_f_frame, () if self._squeeze_realisation else (self._R,), True)))
+
     def timeStepsUntilEvent(self, tol=1e-5, niter_tol=10, max_iter=int(1e9)):
         self._no_dynamics()
         ret = np.empty(self._R, dtype=np.int64)

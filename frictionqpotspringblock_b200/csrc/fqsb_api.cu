@@ -94,6 +94,9 @@ struct fqsb_system {
     // member of a slab-decomposed system (fqsb_slab.inl)
     fqsb_slab_state* slab;
     i64* d_mark;     // [R*N] indices kept by fqsb_mark_indices (nullptr until then)
+    // internal streams of fqsb_run_from_host (chunks of realisations in flight side by side)
+    cudaStream_t pipe_stream[4];
+    cudaEvent_t pipe_ev;
     i64 launches, steps;
     const char* last_kernel;
     cudaEvent_t ev0, ev1;    // bracket the stepping-kernel launches of the last dynamics call
@@ -371,6 +374,10 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     s->lr_gemm = false;
     s->slab = nullptr;
     s->d_mark = nullptr;
+    for (int k = 0; k < 4; ++k) {
+        s->pipe_stream[k] = nullptr;
+    }
+    s->pipe_ev = nullptr;
     s->own_lo = 0;
     s->own_hi = 0;
     for (int k = 0; k < 5; ++k) {
@@ -565,6 +572,14 @@ void fqsb_destroy(fqsb_system* s)
         cudaStreamSynchronize(s->stream);
     }
     slab_free(s);
+    for (int k = 0; k < 4; ++k) {
+        if (s->pipe_stream[k]) {
+            cudaStreamDestroy(s->pipe_stream[k]);
+        }
+    }
+    if (s->pipe_ev) {
+        cudaEventDestroy(s->pipe_ev);
+    }
     for (void* p : s->allocs) {
         cudaFree(p);
     }
@@ -1373,6 +1388,152 @@ int fqsb_minimise_truncate(fqsb_system* s, const int64_t* i_n, int64_t A_truncat
     TRY(run(s, A, false, true));
     fill_ret(s, ret);
     return no_convergence(s, max_iter_is_error);
+}
+
+// ---- fused "state in -> timeSteps -> state out" with the copies hidden behind the kernels ---------
+// system.u = u; system.v = v; system.a = a; system.timeSteps(nsteps); out = system.u, ... as ONE
+// call. The realisations of an ensemble are independent, so the handle cuts them into chunks and
+// runs chunk c on internal stream c mod 4: its host-to-device copies, updated_u() (k_align), the
+// resident kernel over its realisations and the device-to-host copies of its results queue up
+// behind each other while the copy engines already move the neighbouring chunks. Same arithmetic,
+// same results as the separate calls (fqsb_set_u / _v / _a, fqsb_time_steps, fqsb_get,
+// fqsb_mean_f_frame), which remain the fallback for systems the resident kernel does not take.
+// u, v, a: [R*size] host (pinned for real overlap) or NULL (keep the current array);
+// out_u, out_v, out_a: [R*size] or NULL; out_mean_f_frame: [R] or NULL.
+int fqsb_run_from_host(fqsb_system* s, const double* u, const double* v, const double* a, int64_t n,
+                       int64_t nsteps, double* out_u, double* out_v, double* out_a,
+                       double* out_mean_f_frame)
+{
+    TRY(enter(s));
+    TRY(require_dynamic(s));
+    if (n != s->n) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(arg, m_u.shape())")); // detail.h:1278
+    }
+    if (nsteps < 0) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("n + 1 < std::numeric_limits<long>::max()"));
+    }
+    ResidentCfg cfg;
+    const bool pipelined = use_resident(s, &cfg, MODE_FIXED) && s->R >= 8 && nsteps > 0 &&
+                           nsteps <= ((i64)1 << 20) && !s->forces_frozen;
+    if (!pipelined) { // the same sequence through the public calls
+        if (u) {
+            TRY(fqsb_set_u(s, u, n));
+        }
+        if (v) {
+            TRY(fqsb_set_v(s, v, n));
+        }
+        if (a) {
+            TRY(fqsb_set_a(s, a, n));
+        }
+        TRY(fqsb_time_steps(s, nsteps));
+        if (out_u) {
+            TRY(fqsb_get(s, FQSB_U, out_u, n));
+        }
+        if (out_v) {
+            TRY(fqsb_get(s, FQSB_V, out_v, n));
+        }
+        if (out_a) {
+            TRY(fqsb_get(s, FQSB_A, out_a, n));
+        }
+        if (out_mean_f_frame) {
+            TRY(fqsb_mean_f_frame(s, out_mean_f_frame));
+        }
+        return FQSB_OK;
+    }
+    constexpr int NS = 4;
+    if (!s->pipe_ev) {
+        for (int k = 0; k < NS; ++k) {
+            CU(cudaStreamCreateWithFlags(&s->pipe_stream[k], cudaStreamNonBlocking));
+        }
+        CU(cudaEventCreateWithFlags(&s->pipe_ev, cudaEventDisableTiming));
+    }
+    // chunk: a whole number of waves of one-CTA-per-SM realisations, ~32 MB per array
+    int sms = 148;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    i64 per = ((i64)32 << 20) / (s->N * 8);
+    per = per < sms ? sms : (per / sms) * sms;
+    if (const char* e = std::getenv("FQSB_PIPE_CHUNK")) {
+        const i64 x = std::atoll(e);
+        per = x > 0 ? x : per;
+    }
+    const i64 nchunks = (s->R + per - 1) / per;
+    CU(cudaEventRecord(s->pipe_ev, s->stream)); // earlier work of the handle comes first
+    for (int k = 0; k < NS; ++k) {
+        CU(cudaStreamWaitEvent(s->pipe_stream[k], s->pipe_ev, 0));
+    }
+    RunArgs A = make_args(MODE_FIXED, nsteps);
+    A.launch_steps = nsteps;
+    A.own_lo = 0;
+    A.own_hi = (int)s->N;
+    s->last_kernel = "resident";
+    invalidate_forces(s);
+    for (i64 c = 0; c < nchunks; ++c) {
+        const i64 r0 = c * per;
+        const i64 cnt = s->R - r0 < per ? s->R - r0 : per;
+        const size_t off = (size_t)(r0 * s->N), cn = (size_t)(cnt * s->N);
+        cudaStream_t st = s->pipe_stream[c % NS];
+        Par Pc = s->P;
+        Pc.R = cnt;
+        State Sc = s->S;
+        Sc.u += off;
+        Sc.v += off;
+        Sc.a += off;
+        Sc.yl += off;
+        Sc.yr += off;
+        Sc.idx += off;
+        Sc.rng += off;
+        Sc.u_frame += r0;
+        Sc.ctl += r0;
+        if (u) {
+            CU(cudaMemcpyAsync(Sc.u, u + off, cn * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (v) {
+            CU(cudaMemcpyAsync(Sc.v, v + off, cn * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (a) {
+            CU(cudaMemcpyAsync(Sc.a, a + off, cn * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (u) {
+            k_align<<<grid_for((i64)cn), 256, 0, st>>>(Pc, Sc, nullptr); // updated_u(), detail.h:1280
+        }
+        k_ctl_begin<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(Pc, Sc, 0, 0, s->d_out);
+        cudaError_t e = launch_resident(cfg, Pc, Sc, A, st);
+        if (e != cudaSuccess) {
+            return cuda_fail(e, "resident kernel launch");
+        }
+        s->launches += u ? 3 : 2;
+        s->kernel_launches++;
+        if (out_mean_f_frame) {
+            dim3 grid((unsigned)s->S.tiles, (unsigned)cnt);
+            double* part = s->d_red + (size_t)r0 * s->S.tiles * 4;
+            k_reduce<<<grid, 256, 0, st>>>(Pc, Sc, s->F, 2, 1, nullptr, part, 0, (int)s->N);
+            k_reduce_final<<<(unsigned)cnt, 32, 0, st>>>(part, s->S.tiles, s->d_out + 4 * r0);
+            CU(cudaMemcpyAsync(s->h_out + 4 * r0, s->d_out + 4 * r0, (size_t)cnt * 4 * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
+            s->launches += 2;
+        }
+        if (out_u) {
+            CU(cudaMemcpyAsync(out_u + off, Sc.u, cn * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (out_v) {
+            CU(cudaMemcpyAsync(out_v + off, Sc.v, cn * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (out_a) {
+            CU(cudaMemcpyAsync(out_a + off, Sc.a, cn * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaGetLastError());
+    }
+    for (int k = 0; k < NS; ++k) {
+        CU(cudaStreamSynchronize(s->pipe_stream[k]));
+    }
+    if (out_mean_f_frame) {
+        for (i64 r = 0; r < s->R; ++r) {
+            out_mean_f_frame[r] = s->h_out[4 * r + 1] / (double)s->N;
+        }
+    }
+    s->steps += s->R * nsteps;
+    s->kernel_ms = 0.0;
+    return check_flags(s);
 }
 
 // ---- event-driven protocol --------------------------------------------------------------------

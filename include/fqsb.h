@@ -166,6 +166,16 @@ int fqsb_flow_steps(fqsb_system* s, int64_t n, double v_frame);  /* ref: 1637-16
 int fqsb_time_steps_until_event(fqsb_system* s, double tol, int64_t niter_tol, int64_t max_iter,
                                 int64_t* ret);
 
+/* `system.u = u; system.v = v; system.a = a; system.timeSteps(nsteps); out = system.u ...` as ONE
+ * call whose host<->device copies overlap the kernels: the realisations are cut into chunks that
+ * run on internal streams of the handle (copy-in, updated_u(), resident kernel, copy-out per
+ * chunk). Same results as the separate calls. u, v, a [R*size] host (pinned for real overlap) or
+ * NULL = keep; out_u, out_v, out_a [R*size] or NULL; out_mean_f_frame [R] or NULL.
+ * ref: detail.h:1276-1305 (setters), 1577-1583 (timeSteps), 1402-1468 (getters) */
+int fqsb_run_from_host(fqsb_system* s, const double* u, const double* v, const double* a, int64_t n,
+                       int64_t nsteps, double* out_u, double* out_v, double* out_a,
+                       double* out_mean_f_frame);
+
 /* minimisation (ref: detail.h:1676-1893) ------------------------------------------------ */
 /* ret [R]: 0 if converged, max_iter+1 otherwise (only reachable with max_iter_is_error == 0).
  * Dynamic systems: velocity-Verlet until the StopList criterion (ref: 1754-1785);

@@ -1007,6 +1007,104 @@ int orc_flow_steps(orc_system* s, int64_t n, double v_frame) /* detail.h:1637-16
     return ORC_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * The FUSED CPU flavour of timeSteps ("best-case CPU"): the same
+ * arithmetic as time_step() above -- every per-block expression in the reference's order, so the
+ * results are bit-identical (tests/test_oracle_fused.py) -- but as two passes per step over four
+ * arrays (new slips; then well test + forces + the three Verlet correctors per block) instead of
+ * the ~69 array passes of the reference's xtensor expression structure (detail.h:1539-1570,
+ * 1321-1395). Cuspy x Laplace1d without thermal forcing (the headline configuration); any other
+ * system takes the faithful path. The force arrays are refreshed once, at the end.
+ * ---------------------------------------------------------------------------------------- */
+int orc_time_steps_fused(orc_system* s, int64_t n)
+{
+    if (s->par.potential != ORC_POT_CUSPY || s->par.interactions != ORC_INT_LAPLACE1D ||
+        s->thermal || n <= 0) {
+        return orc_time_steps(s, n);
+    }
+    const int64_t N = s->N;
+    const double dt = s->par.dt, c2 = 0.5 * dt * dt, hdt = 0.5 * dt;
+    const double inv_m = s->inv_m, meta = -s->par.eta, mu = s->par.mu, k = s->par.k1;
+    const double kf = s->par.k_frame, uf = s->u_frame;
+    double* yl = (double*)malloc((size_t)N * sizeof(double));
+    double* yr = (double*)malloc((size_t)N * sizeof(double));
+    double* un = (double*)malloc((size_t)N * sizeof(double));
+    double *restrict u = s->u, *restrict v = s->v, *restrict a = s->a;
+    for (int64_t p = 0; p < N; ++p) {
+        const block_t* b = &s->blk[p];
+        yl[p] = blk_y(b, b->i);
+        yr[p] = blk_y(b, b->i + 1);
+    }
+    int nan = 0;
+    for (int64_t it = 0; it < n; ++it) {
+        s->inc++;
+        for (int64_t p = 0; p < N; ++p) {
+            un[p] = u[p] + dt * v[p] + c2 * a[p]; /* detail.h:1549 */
+        }
+        for (int64_t p = 0; p < N; ++p) { /* m_chunk->align(u), detail.h:144: rare well changes */
+            const double uc = un[p];
+            if (uc > yr[p] || !(uc > yl[p])) {
+                block_t* b = &s->blk[p];
+                blk_align(s, b, uc);
+                yl[p] = blk_y(b, b->i);
+                yr[p] = blk_y(b, b->i + 1);
+            }
+        }
+#define FUSED_BLOCK(p, ul, ur) \
+    { \
+        const double uc = un[p]; \
+        const double fi = ((ul) - 2 * uc + (ur)) * k;         /* detail.h:474-487 */ \
+        const double fp = (0.5 * (yl[p] + yr[p]) - uc) * mu; /* detail.h:164-169 */ \
+        const double ff = kf * (uf - uc);                    /* detail.h:1360 */ \
+        const double F = ff + fp + fi;                       /* detail.h:1324 */ \
+        const double vn = v[p], an = a[p]; \
+        double vv = vn + dt * an; /* detail.h:1552-1565 */ \
+        double f = F + meta * vv; \
+        double aa = f * inv_m; \
+        vv = vn + hdt * (an + aa); \
+        f = F + meta * vv; \
+        aa = f * inv_m; \
+        vv = vn + hdt * (an + aa); \
+        f = F + meta * vv; \
+        aa = f * inv_m; \
+        v[p] = vv; \
+        a[p] = aa; \
+    }
+        /* branch-free interior (vectorised by the compiler: every lane keeps IEEE semantics and
+           -ffp-contract=off forbids FMA, so the bits do not change), periodic ends apart */
+        for (int64_t p = 1; p < N - 1; ++p) {
+            FUSED_BLOCK(p, un[p - 1], un[p + 1])
+        }
+        if (N > 1) {
+            FUSED_BLOCK(0, un[N - 1], un[1])
+            FUSED_BLOCK(N - 1, un[N - 2], un[0])
+        }
+        else {
+            FUSED_BLOCK(0, un[0], un[0])
+        }
+#undef FUSED_BLOCK
+        double* tmp = u;
+        u = un;
+        un = tmp;
+    }
+    if (u != s->u) { /* odd number of steps: the current slips sit in the scratch array */
+        memcpy(s->u, u, (size_t)N * sizeof(double));
+        un = u;
+    }
+    for (int64_t p = 0; p < N; ++p) {
+        nan |= isnan(s->u[p]);
+    }
+    free(yl);
+    free(yr);
+    free(un);
+    updated_u(s); /* the stored force arrays of the final state */
+    updated_v(s);
+    if (nan) {
+        return fail(ORC_ENAN, "NaN entries found");
+    }
+    return check_landscape(s);
+}
+
 static int any_index_changed(const orc_system* s, const int64_t* i_n)
 {
     for (int64_t p = 0; p < s->N; ++p) {
@@ -1517,6 +1615,10 @@ struct orc_ensemble {
     orc_params par;
     int64_t nsys;
     int nthreads;
+    int fused; /* timeSteps through orc_time_steps_fused */
+    int ftz;   /* flush denormals (x86 MXCSR FTZ | DAZ) in the worker threads: a long un-kicked
+                  run decays into denormal velocities, which x86 executes several times slower;
+                  timing only -- results then differ from the reference below 1e-308 */
     orc_system** sys;
 };
 
@@ -1533,6 +1635,11 @@ static void* ens_worker(void* vp)
     ens_arg* a = (ens_arg*)vp;
     orc_ensemble* e = a->e;
     double cs = 0.0;
+#if defined(__x86_64__) || defined(__i386__)
+    if (e->ftz) {
+        __builtin_ia32_ldmxcsr(__builtin_ia32_stmxcsr() | 0x8040u);
+    }
+#endif
     for (int64_t r = a->tid; r < e->nsys; r += e->nthreads) {
         if (a->prepare == 2) {
             if (e->sys[r]) {
@@ -1558,7 +1665,12 @@ static void* ens_worker(void* vp)
         }
         else if (e->sys[r]) {
             orc_system* s = e->sys[r];
-            orc_time_steps(s, a->nsteps);
+            if (e->fused) {
+                orc_time_steps_fused(s, a->nsteps);
+            }
+            else {
+                orc_time_steps(s, a->nsteps);
+            }
             for (int64_t p = 0; p < s->N; ++p) {
                 cs += s->u[p];
             }
@@ -1606,6 +1718,12 @@ orc_ensemble* orc_ensemble_create(const orc_params* par, int64_t nsys, int nthre
 double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum)
 {
     return ens_run(e, 0, nsteps, checksum);
+}
+
+void orc_ensemble_configure(orc_ensemble* e, int fused, int ftz)
+{
+    e->fused = fused;
+    e->ftz = ftz;
 }
 
 /* eventDrivenStep(eps, false) + eventDrivenStep(eps, true) on every system (untimed by callers) */

@@ -109,6 +109,8 @@ int64_t orc_qs_last(const orc_system* s);
 
 /* dynamics: detail.h:1539-1645 */
 int orc_time_steps(orc_system* s, int64_t n);
+/* the fused single-pass CPU flavour of the same steps (bit-identical results) */
+int orc_time_steps_fused(orc_system* s, int64_t n);
 int orc_flow_steps(orc_system* s, int64_t n, double v_frame);
 int orc_time_steps_until_event(orc_system* s, double tol, int64_t niter_tol, int64_t max_iter,
                                int64_t* ret);
@@ -164,6 +166,8 @@ typedef struct orc_ensemble orc_ensemble;
 orc_ensemble* orc_ensemble_create(const orc_params* par, int64_t nsys, int nthreads);
 double orc_ensemble_time_steps(orc_ensemble* e, int64_t nsteps, double* checksum);
 void orc_ensemble_kick(orc_ensemble* e);
+/* fused: timeSteps as the single-pass flavour; ftz: flush denormals in the workers (timing only) */
+void orc_ensemble_configure(orc_ensemble* e, int fused, int ftz);
 void orc_ensemble_destroy(orc_ensemble* e);
 
 #ifdef __cplusplus

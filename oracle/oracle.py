@@ -99,6 +99,8 @@ def lib():
         L.orc_set_t.argtypes = [C.c_void_p, C.c_double]
         L.orc_set_inc.argtypes = [C.c_void_p, C.c_int64]
         L.orc_time_steps.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_time_steps_fused.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_ensemble_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_flow_steps.argtypes = [C.c_void_p, C.c_int64, C.c_double]
         L.orc_time_steps_until_event.argtypes = [
             C.c_void_p, C.c_double, C.c_int64, C.c_int64, C.c_void_p]
@@ -427,6 +429,11 @@ class System:
     def timeSteps(self, n):
         self._check(lib().orc_time_steps(self._h, int(n)))
 
+    def timeSteps_fused(self, n):
+        """The same steps through the fused single-pass CPU flavour (fqsb_oracle.c:
+        orc_time_steps_fused): bit-identical results, best-case CPU cost."""
+        self._check(lib().orc_time_steps_fused(self._h, int(n)))
+
     def timeStepsUntilEvent(self, tol=1e-5, niter_tol=10, max_iter=int(1e9)):
         ret = C.c_int64()
         self._check(lib().orc_time_steps_until_event(self._h, tol, int(niter_tol), int(max_iter),
@@ -505,6 +512,10 @@ class CpuEnsemble:
         cs = C.c_double()
         sec = lib().orc_ensemble_time_steps(self._e, int(nsteps), C.byref(cs))
         return sec, cs.value
+
+    def configure(self, fused=False, ftz=False):
+        """fused: timeSteps as the single-pass flavour; ftz: flush denormals (timing only)."""
+        lib().orc_ensemble_configure(self._e, int(fused), int(ftz))
 
     def kick(self):
         """eventDrivenStep(1e-3, False) + eventDrivenStep(1e-3, True) on every line."""
