@@ -347,41 +347,60 @@ __global__ void __launch_bounds__(T)
         }
     }
     else {
-        // Per-thread bookkeeping is kept minimal (the decision is taken redundantly by every
-        // warp): the StopList ring, and the running S, A of minimise_truncate. The activity
-        // timestamps (detail.h:1770-1776) are written by thread 0 on the rare steps that change
-        // S; step and increment numbers follow from the loop counter.
-        RingEntry ring = ring_load(ctl, A, lane);
-        double last_sf = 0.0, last_sff = 0.0;
-        i64 S_run = ctl.S, A_run = ctl.A;
-        const i64 inc0 = ctl.inc;
-        i64 its = 0;
+        // The decision is taken redundantly by every warp (one barrier per step), so whatever it
+        // keeps alive competes with the 8 force chains for registers. Hence: the StopList ring is
+        // a CIRCULAR buffer over the lanes (no roll), counters are 32-bit loop-relative, S / A run
+        // as deltas, and everything that is only needed once (increment and step numbers, the
+        // residual) is re-read from the control block after the loop. The activity timestamps
+        // (detail.h:1770-1776) are written by thread 0 on the rare steps that change S.
+        RingEntry ring = ring_load(ctl, A, lane); // lane l = logical entry l (oldest first)
+        const int nring = A.niter_tol;
+        int head = 0; // lane holding the OLDEST entry = the next one to be overwritten
+        int dS_run = 0, dA_run = 0;
+        // truncation thresholds relative to the totals at entry (detail.h:1879-1885)
+        const i64 A_left = A.A_truncate > 0 ? A.A_truncate - ctl.A : (i64)1 << 40;
+        const i64 S_left = A.S_truncate > 0 ? A.S_truncate - ctl.S : (i64)1 << 40;
+        const bool fresh = steps_done == 0 && ctl.S != 0; // "s != s_n" at the first step (s_n = 0)
+        const int nl = (int)nloop;
+        const double tol4 = A.tol2 * A.tol2;
+        int its = 0;
         // One barrier per step: after the forces of step s, the positions of step s+1 are
         // computed speculatively (purely local, into the other slip buffer); the barrier that
         // publishes them also publishes the partial sums of step s, whose stop decision is
         // taken right after it. A stop discards the speculative positions.
-        if (nloop > 0) {
+        if (nl > 0) {
             phase1(prev * NS, (prev ^ 1) * NS);
             __syncthreads();
         }
-        for (i64 it = 0; it < nloop; ++it) {
+        for (int it = 0; it < nl; ++it) {
             double sf = 0.0, sff = 0.0;
             int hops = 0, dS = 0, dA = 0;
             phase2((prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
 
             // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
-            double* rd = red + (int)(it & 1) * 2 * NW;
-            int* ri = redi + (int)(it & 1) * 4 * NW;
-            warp_sum2(sf, sff);
+            double* rd = red + (it & 1) * 2 * NW;
+            int* ri = redi + (it & 1) * 4 * NW;
+            {
+                // one butterfly for the pair: even lanes collect sf, odd lanes sff; lanes 0 / 1
+                // end up with the warp's sums (no broadcast needed)
+                const bool odd = lane & 1;
+                double keep = odd ? sff : sf;
+                keep += __shfl_xor_sync(0xffffffffu, odd ? sf : sff, 1);
+#pragma unroll
+                for (int o = 16; o > 1; o >>= 1) {
+                    keep += __shfl_xor_sync(0xffffffffu, keep, o);
+                }
+                if (lane < 2) {
+                    rd[2 * warp + lane] = keep;
+                }
+            }
             hops = __reduce_add_sync(0xffffffffu, hops);
             if (A.track) {
                 dS = __reduce_add_sync(0xffffffffu, dS);
                 dA = __reduce_add_sync(0xffffffffu, dA);
             }
             if (lane == 0) {
-                rd[2 * warp] = sf;
-                rd[2 * warp + 1] = sff;
                 ri[4 * warp] = hops;
                 ri[4 * warp + 1] = dS;
                 ri[4 * warp + 2] = dA;
@@ -395,60 +414,92 @@ __global__ void __launch_bounds__(T)
                 sf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
                 sff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
             }
-            hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
-            last_sf = sf;
-            last_sff = sff;
             its = it + 1;
-            const i64 step_global = steps_done + its; // steps of this call so far
             if (sf != sf) { // NaN forces <=> NaN positions (detail.h:1567)
                 status = ST_NAN;
                 break;
             }
-            if (A.mode == MODE_UNTIL_EVENT && hops > 0) { // detail.h:1609
-                status = ST_EVENT;
-                break;
+            if (A.mode == MODE_UNTIL_EVENT) { // detail.h:1609
+                hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
+                if (hops > 0) {
+                    status = ST_EVENT;
+                    break;
+                }
             }
-            ring = ring_roll_insert(ring, ring_entry(sf, sff), A.niter_tol, lane);
+            // roll_insert: the newest entry replaces the oldest
+            const RingEntry e = ring_entry(sf, sff);
+            if (lane == head) {
+                ring = e;
+            }
+            head = head + 1 == nring ? 0 : head + 1;
             if (A.track) { // detail.h:1768-1778, 1863-1872
                 dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
                 dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
-                S_run += dS;
-                A_run += dA;
+                dS_run += dS;
+                dA_run += dA;
                 // s != s_n  <=>  S changed in this step (s_n starts at 0 before the first step)
-                if ((dS != 0 || (step_global == 1 && S_run != 0)) && t == 0) {
+                if ((dS != 0 || (fresh && it == 0)) && t == 0) {
+                    const i64 inc_now = ctl.inc + its; // (ctl.inc is only advanced after the loop)
                     if (ctl.init) {
                         ctl.init = 0;
-                        ctl.qs_first = inc0 + its;
+                        ctl.qs_first = inc_now;
                     }
-                    ctl.qs_last = inc0 + its;
+                    ctl.qs_last = inc_now;
                 }
             }
-            if (ring_stop(ring, A.niter_tol, lane, A.tol2, A.tol2 * A.tol2)) {
-                status = ST_CONVERGED;
-                break;
+            // Both criteria need EVERY entry below tol (all_less(tol) resp. all_less(tol^2)),
+            // the newest included: while it is not, nothing can stop (no shuffles, one compare)
+            if (e.num < A.tol2 * e.den) {
+                // lane l's successor in time is lane l + 1 (cyclically), except for the newest
+                // entry, whose cyclic neighbour is the oldest
+                const int succ = lane + 1 == nring ? 0 : lane + 1;
+                RingEntry nxt;
+                nxt.num = __shfl_sync(0xffffffffu, ring.num, succ & 31);
+                nxt.den = __shfl_sync(0xffffffffu, ring.den, succ & 31);
+                const bool in = lane < nring;
+                // std::is_sorted(..., greater): never r_{k+1} > r_k
+                const bool desc = !in || succ == head || !(nxt.num * ring.den > ring.num * nxt.den);
+                const bool less1 = !in || (ring.num < A.tol2 * ring.den); // all_less(tol): strict
+                const bool less2 = !in || (ring.num < tol4 * ring.den);   // all_less(tol * tol)
+                const bool descending = __all_sync(0xffffffffu, desc);
+                const bool all1 = __all_sync(0xffffffffu, less1);
+                const bool all2 = __all_sync(0xffffffffu, less2);
+                if ((descending && all1) || all2) {
+                    status = ST_CONVERGED;
+                    break;
+                }
             }
             if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
-                if ((A.A_truncate > 0 && A_run >= A.A_truncate) ||
-                    (A.S_truncate > 0 && S_run >= A.S_truncate)) {
+                if (dA_run >= A_left || dS_run >= S_left) {
                     status = ST_TRUNCATED;
                     break;
                 }
             }
-            if (step_global >= A.max_steps) {
-                status = ST_EXHAUSTED;
-                break;
-            }
+        }
+        const i64 steps_now = ctl.steps + its; // (re-read: not kept in registers over the loop)
+        if (status == ST_RUNNING && steps_now >= A.max_steps) {
+            status = ST_EXHAUSTED;
         }
         if (t < 32) {
-            ring_store(ctl, A, lane, ring);
+            // back to logical order (oldest first): lane l holds logical entry (l - head) mod n
+            if (lane < nring && lane < FQSB_RING) {
+                const int k = lane - head + (lane < head ? nring : 0);
+                ctl.ring[k] = ring.num;
+                ctl.ring_den[k] = ring.den;
+            }
+            const int newest = head == 0 ? nring - 1 : head - 1;
+            const double last_num = __shfl_sync(0xffffffffu, ring.num, newest & 31);
+            const double last_den = __shfl_sync(0xffffffffu, ring.den, newest & 31);
             if (lane == 0) {
-                ctl.steps = steps_done + its;
-                ctl.inc = inc0 + its; // detail.h:1541
-                ctl.S = S_run;
-                ctl.A = A_run;
-                ctl.s_n = S_run;
+                ctl.steps = steps_now;
+                ctl.inc += its; // detail.h:1541
+                ctl.S += dS_run;
+                ctl.A += dA_run;
+                ctl.s_n = ctl.S;
                 ctl.status = status;
-                ctl.residual = residual_from_sums(last_sf, last_sff);
+                if (its > 0) {
+                    ctl.residual = residual_from_sums(last_num, last_den);
+                }
             }
         }
     }

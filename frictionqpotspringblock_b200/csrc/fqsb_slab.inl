@@ -658,6 +658,7 @@ static int slab_enqueue_steps(fqsb_system* s, i64 k, int mode, int flow, double 
     CU(cudaGetLastError());
     s->launches += nl + 4;
     s->steps += k;
+    s->last_kernel = overdamped ? "slab_stream_nopassing" : "slab_stream";
     invalidate_forces(s);
     return FQSB_OK;
 }
@@ -1286,7 +1287,7 @@ int fqsb_slab_connect(fqsb_system* s, fqsb_system* const* locals, const void* ip
     return FQSB_OK;
 }
 
-int fqsb_slab_info(fqsb_system* s, int64_t* out /* [8] */)
+int fqsb_slab_info(fqsb_system* s, int64_t* out /* [10] */)
 {
     TRY(slab_require(s, false));
     fqsb_slab_state* L = s->slab;
@@ -1296,7 +1297,9 @@ int fqsb_slab_info(fqsb_system* s, int64_t* out /* [8] */)
     out[3] = s->own_lo;
     out[4] = s->own_hi;
     out[5] = L->batches;
-    out[6] = L->redone + (L->wasted << 32);
+    out[6] = L->redone;
+    out[8] = L->wasted;
+    out[9] = L->blocked ? 1 : 0;
     out[7] = 0;
     for (int i = 0; i < FQSB_SLAB_GRAPHS; ++i) {
         out[7] += L->graphs[i].exec ? 1 : 0;

@@ -170,10 +170,10 @@ class SlabSystem:
         return out
 
     def info(self, member=0):
-        out = np.empty(8, dtype=np.int64)
+        out = np.zeros(10, dtype=np.int64)
         check(lib.fqsb_slab_info(self.members[member]._h, out.ctypes.data))
         return dict(zip(("rank", "world", "halo_cells", "own_lo", "own_hi", "batches", "redone",
-                         "graph"), (int(i) for i in out)))
+                         "graphs", "discarded", "blocked"), (int(i) for i in out)))
 
     # ---- reference surface
     @property

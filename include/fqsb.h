@@ -278,7 +278,8 @@ int fqsb_slab_ipc_handle(fqsb_system* s, void* out64);
 /* locals [world] (entries may be NULL) : members living in this process; ipc_handles [world][64]
  * (may be NULL): fqsb_slab_ipc_handle of the others */
 int fqsb_slab_connect(fqsb_system* s, fqsb_system* const* locals, const void* ipc_handles);
-/* out [8]: rank, world, halo_cells, own_lo, own_hi, batches, batches redone, graph in use */
+/* out [10]: rank, world, halo_cells, own_lo, own_hi, batches, batches redone (criterion fired
+ * inside), CUDA graphs in use, speculative batches discarded, 1 if the members run the blocked kernel */
 int fqsb_slab_info(fqsb_system* s, int64_t* out);
 int fqsb_slab_exchange(fqsb_system** members, int nmembers);
 /* timeSteps (flow == 0) / flowSteps (ref: detail.h:1577-1583, 1637-1645), `batch` steps per exchange */

@@ -92,6 +92,7 @@ def test_device_side_avalanche_bookkeeping():
         ens.mark_indices()
         ens.eventDrivenStep(1e-3, False)
         ens.eventDrivenStep(1e-3, True)
+        i_k = ens.chunk.index_at_align  # after the kick: what minimise(time_activity) starts from
         # time_activity=True overwrites the handle's scratch copy of the indices: the mark survives
         assert np.all(ens.minimise(time_activity=True) == 0)
         S, A = ens.avalanche_since_mark()
@@ -100,9 +101,11 @@ def test_device_side_avalanche_bookkeeping():
         assert np.array_equal(A, np.sum(i != i_n, axis=1))
         S2, A2 = ens.avalanche(i_n)
         assert np.array_equal(S, S2) and np.array_equal(A, A2)
+        # the record the stepping kernel keeps itself (detail.h:1768-1778): relative to the start
+        # of the minimisation
         S_abs, A_rec, first, last = ens.event_record()
-        assert np.array_equal(A_rec, A)
-        assert np.all(S_abs >= np.abs(S))
+        assert np.array_equal(S_abs, np.sum(np.abs(i - i_k), axis=1))
+        assert np.array_equal(A_rec, np.sum(i != i_k, axis=1))
         assert np.array_equal(first, ens.quasistaticActivityFirst)
         assert np.array_equal(last, ens.quasistaticActivityLast)
     # the same events on the oracle, realisation 5

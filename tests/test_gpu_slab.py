@@ -126,7 +126,7 @@ def test_slab_flow_steps_and_batch_redo(kernel):
     assert ref.minimise() == 0 and s.minimise() == 0
     assert s.inc == ref.inc
     if kernel == 2:
-        assert (s.info()["redone"] & 0xffffffff) + (s.last_minimise_steps % 16 == 0) >= 1
+        assert s.info()["redone"] + (s.last_minimise_steps % 16 == 0) >= 1
     assert np.array_equal(s.owned("index_at_align"), ref.chunk.index_at_align)
     assert np.allclose(s.owned("u"), ref.u, rtol=0, atol=1e-9)
     assert np.all(s.owned("v") == 0.0)  # quench() on convergence (detail.h:1781)
