@@ -258,22 +258,35 @@ __global__ void __launch_bounds__(T)
 
     // ---- well search (detail.h:144), forces at the new positions (detail.h:1380-1386) and
     //      the Verlet tail (detail.h:1552-1565)
-    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
-                      int& dS, int& dA) {
+    // phase 2a: the new positions of this thread's blocks and the well test -- no side effects,
+    // so the stop modes run it BEFORE the decision about the previous step is known (its
+    // shuffle chain is still in flight then)
+    auto phase2a = [&](const int ocur, double (&uc)[B], unsigned& need) {
         const double* ucur = us + ocur;
-        auto U = [&](int q) { return ucur[q + G]; };
-        double uc[B], wl[B], wr[B];
-        unsigned need = 0u;
+        need = 0u;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = t + j * T;
             const int pc = (FULL || p < N) ? p : N - 1;
             uc[j] = ucur[pc + G];
-            wl[j] = YSMEM ? syl[pc] : yl[j];
-            wr[j] = YSMEM ? syr[pc] : yr[j];
-            if ((FULL || p < N) && (uc[j] > wr[j] || !(uc[j] > wl[j]))) {
+            const double l = YSMEM ? syl[pc] : yl[j];
+            const double rr = YSMEM ? syr[pc] : yr[j];
+            if ((FULL || p < N) && (uc[j] > rr || !(uc[j] > l))) {
                 need |= 1u << j;
             }
+        }
+    };
+    auto phase2b = [&](const int ocur, double (&uc)[B], const unsigned need, auto accumulate,
+                       double& sf, double& sff, int& hops, int& dS, int& dA) {
+        const double* ucur = us + ocur;
+        auto U = [&](int q) { return ucur[q + G]; };
+        double wl[B], wr[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int p = t + j * T;
+            const int pc = (FULL || p < N) ? p : N - 1;
+            wl[j] = YSMEM ? syl[pc] : yl[j];
+            wr[j] = YSMEM ? syr[pc] : yr[j];
         }
         if (need) { // rare: some block of this thread left its well
 #pragma unroll
@@ -311,10 +324,20 @@ __global__ void __launch_bounds__(T)
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
             if (decltype(accumulate)::value) {
-                sf += (FULL || p < N) ? f * f : 0.0;
-                sff += (FULL || p < N) ? ff * ff : 0.0;
+                // residual norms (detail.h:1512-1520): one explicit FMA per term. The sums are
+                // reductions -- their association already differs from the reference's sequential
+                // loop -- so the contraction changes nothing that is compared bit for bit.
+                sf = (FULL || p < N) ? fma(f, f, sf) : sf;
+                sff = (FULL || p < N) ? fma(ff, ff, sff) : sff;
             }
         }
+    };
+    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
+                      int& dS, int& dA) {
+        double uc[B];
+        unsigned need;
+        phase2a(ocur, uc, need);
+        phase2b(ocur, uc, need, accumulate, sf, sff, hops, dS, dA);
     };
 
     int status = ST_RUNNING;
@@ -368,14 +391,95 @@ __global__ void __launch_bounds__(T)
         // computed speculatively (purely local, into the other slip buffer); the barrier that
         // publishes them also publishes the partial sums of step s, whose stop decision is
         // taken right after it. A stop discards the speculative positions.
+        // One barrier per step, and the decision off the critical path: after the forces of step
+        // s the positions of step s+1 are computed speculatively (purely local, into the other
+        // slip buffer); the barrier that publishes them also publishes the partial sums of step
+        // s. Their reduction (a chain of dependent shuffles) is ISSUED right after the barrier but
+        // consumed only after the side-effect-free first part of step s+1 (phase2a), so its
+        // latency hides behind useful work. A stop discards the speculative positions.
+        double gsf = 0.0, gsff = 0.0; // sums of the step whose decision is pending
         if (nl > 0) {
             phase1(prev * NS, (prev ^ 1) * NS);
             __syncthreads();
         }
-        for (int it = 0; it < nl; ++it) {
+        for (int it = 0;; ++it) {
+            double uc[B];
+            unsigned need = 0u;
+            if (it < nl) {
+                phase2a((prev ^ 1) * NS, uc, need);
+            }
+            if (it > 0) { // ---- decision about step `it` (1-based), detail.h:1605-1619, 1764-1784
+                const int* ri = redi + ((it - 1) & 1) * 4 * NW;
+                const double sf = gsf, sff = gsff;
+                its = it;
+                if (sf != sf) { // NaN forces <=> NaN positions (detail.h:1567)
+                    status = ST_NAN;
+                    break;
+                }
+                if (A.mode == MODE_UNTIL_EVENT) { // detail.h:1609
+                    const int hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
+                    if (hops > 0) {
+                        status = ST_EVENT;
+                        break;
+                    }
+                }
+                // roll_insert: the newest entry replaces the oldest
+                const RingEntry e = ring_entry(sf, sff);
+                if (lane == head) {
+                    ring = e;
+                }
+                head = head + 1 == nring ? 0 : head + 1;
+                if (A.track) { // detail.h:1768-1778, 1863-1872
+                    const int dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
+                    const int dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
+                    dS_run += dS;
+                    dA_run += dA;
+                    // s != s_n  <=>  S changed in this step (s_n starts at 0 before the first step)
+                    if ((dS != 0 || (fresh && it == 1)) && t == 0) {
+                        const i64 inc_now = ctl.inc + its; // (ctl.inc is advanced after the loop)
+                        if (ctl.init) {
+                            ctl.init = 0;
+                            ctl.qs_first = inc_now;
+                        }
+                        ctl.qs_last = inc_now;
+                    }
+                }
+                // Both criteria need EVERY entry below tol (all_less(tol) resp. all_less(tol^2)),
+                // the newest included: while it is not, nothing can stop (no shuffles, one compare)
+                if (e.num < A.tol2 * e.den) {
+                    // lane l's successor in time is lane l + 1 (cyclically), except for the newest
+                    // entry, whose cyclic neighbour is the oldest
+                    const int succ = lane + 1 == nring ? 0 : lane + 1;
+                    RingEntry nxt;
+                    nxt.num = __shfl_sync(0xffffffffu, ring.num, succ & 31);
+                    nxt.den = __shfl_sync(0xffffffffu, ring.den, succ & 31);
+                    const bool in = lane < nring;
+                    // std::is_sorted(..., greater): never r_{k+1} > r_k
+                    const bool desc =
+                        !in || succ == head || !(nxt.num * ring.den > ring.num * nxt.den);
+                    const bool less1 = !in || (ring.num < A.tol2 * ring.den); // all_less(tol)
+                    const bool less2 = !in || (ring.num < tol4 * ring.den);   // all_less(tol^2)
+                    const bool descending = __all_sync(0xffffffffu, desc);
+                    const bool all1 = __all_sync(0xffffffffu, less1);
+                    const bool all2 = __all_sync(0xffffffffu, less2);
+                    if ((descending && all1) || all2) {
+                        status = ST_CONVERGED;
+                        break;
+                    }
+                }
+                if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
+                    if (dA_run >= A_left || dS_run >= S_left) {
+                        status = ST_TRUNCATED;
+                        break;
+                    }
+                }
+            }
+            if (it >= nl) {
+                break;
+            }
             double sf = 0.0, sff = 0.0;
             int hops = 0, dS = 0, dA = 0;
-            phase2((prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
+            phase2b((prev ^ 1) * NS, uc, need, std::true_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
 
             // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
@@ -395,85 +499,27 @@ __global__ void __launch_bounds__(T)
                     rd[2 * warp + lane] = keep;
                 }
             }
-            hops = __reduce_add_sync(0xffffffffu, hops);
-            if (A.track) {
-                dS = __reduce_add_sync(0xffffffffu, dS);
-                dA = __reduce_add_sync(0xffffffffu, dA);
-            }
-            if (lane == 0) {
-                ri[4 * warp] = hops;
-                ri[4 * warp + 1] = dS;
-                ri[4 * warp + 2] = dA;
+            if (A.mode == MODE_UNTIL_EVENT || A.track) {
+                hops = __reduce_add_sync(0xffffffffu, hops);
+                if (A.track) {
+                    dS = __reduce_add_sync(0xffffffffu, dS);
+                    dA = __reduce_add_sync(0xffffffffu, dA);
+                }
+                if (lane == 0) {
+                    ri[4 * warp] = hops;
+                    ri[4 * warp + 1] = dS;
+                    ri[4 * warp + 2] = dA;
+                }
             }
             phase1(prev * NS, (prev ^ 1) * NS); // speculative
             __syncthreads();
+            // issue the reduction of this step's partials; consumed in the next iteration
             if (2 * NW == 32) {
-                warp_sum_interleaved(rd[lane], sf, sff);
+                warp_sum_interleaved(rd[lane], gsf, gsff);
             }
             else {
-                sf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
-                sff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
-            }
-            its = it + 1;
-            if (sf != sf) { // NaN forces <=> NaN positions (detail.h:1567)
-                status = ST_NAN;
-                break;
-            }
-            if (A.mode == MODE_UNTIL_EVENT) { // detail.h:1609
-                hops = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane] : 0);
-                if (hops > 0) {
-                    status = ST_EVENT;
-                    break;
-                }
-            }
-            // roll_insert: the newest entry replaces the oldest
-            const RingEntry e = ring_entry(sf, sff);
-            if (lane == head) {
-                ring = e;
-            }
-            head = head + 1 == nring ? 0 : head + 1;
-            if (A.track) { // detail.h:1768-1778, 1863-1872
-                dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
-                dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
-                dS_run += dS;
-                dA_run += dA;
-                // s != s_n  <=>  S changed in this step (s_n starts at 0 before the first step)
-                if ((dS != 0 || (fresh && it == 0)) && t == 0) {
-                    const i64 inc_now = ctl.inc + its; // (ctl.inc is only advanced after the loop)
-                    if (ctl.init) {
-                        ctl.init = 0;
-                        ctl.qs_first = inc_now;
-                    }
-                    ctl.qs_last = inc_now;
-                }
-            }
-            // Both criteria need EVERY entry below tol (all_less(tol) resp. all_less(tol^2)),
-            // the newest included: while it is not, nothing can stop (no shuffles, one compare)
-            if (e.num < A.tol2 * e.den) {
-                // lane l's successor in time is lane l + 1 (cyclically), except for the newest
-                // entry, whose cyclic neighbour is the oldest
-                const int succ = lane + 1 == nring ? 0 : lane + 1;
-                RingEntry nxt;
-                nxt.num = __shfl_sync(0xffffffffu, ring.num, succ & 31);
-                nxt.den = __shfl_sync(0xffffffffu, ring.den, succ & 31);
-                const bool in = lane < nring;
-                // std::is_sorted(..., greater): never r_{k+1} > r_k
-                const bool desc = !in || succ == head || !(nxt.num * ring.den > ring.num * nxt.den);
-                const bool less1 = !in || (ring.num < A.tol2 * ring.den); // all_less(tol): strict
-                const bool less2 = !in || (ring.num < tol4 * ring.den);   // all_less(tol * tol)
-                const bool descending = __all_sync(0xffffffffu, desc);
-                const bool all1 = __all_sync(0xffffffffu, less1);
-                const bool all2 = __all_sync(0xffffffffu, less2);
-                if ((descending && all1) || all2) {
-                    status = ST_CONVERGED;
-                    break;
-                }
-            }
-            if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
-                if (dA_run >= A_left || dS_run >= S_left) {
-                    status = ST_TRUNCATED;
-                    break;
-                }
+                gsf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
+                gsff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
             }
         }
         const i64 steps_now = ctl.steps + its; // (re-read: not kept in registers over the loop)
