@@ -113,6 +113,7 @@ SIGNATURES = {
     "fqsb_chunk_index_at_align": (C.c_int, [_P, _P, C.c_int64]),
     "fqsb_chunk_left_of_align": (C.c_int, [_P, _P, C.c_int64]),
     "fqsb_chunk_right_of_align": (C.c_int, [_P, _P, C.c_int64]),
+    "fqsb_chunk_align": (C.c_int, [_P, _P, C.c_int64]),
     "fqsb_chunk_data": (C.c_int, [_P, _P, C.c_int64, _P]),
     "fqsb_chunk_state_at": (C.c_int, [_P, _P, _P, C.c_int64]),
     "fqsb_chunk_restore": (C.c_int, [_P, _P, _P, _P, C.c_int64]),

@@ -113,6 +113,23 @@ class _Chunk:
         check(lib.fqsb_chunk_data(o._h, first.ctypes.data, o._nchunk, out.ctypes.data))
         return o._squeeze(out)
 
+    def align(self, u):
+        """Align the landscape with positions ``u`` (python-prrng ``align``): afterwards
+        ``index_at_align`` / ``left_of_align`` / ``right_of_align`` refer to ``u``. The system's
+        own slips are untouched (its next ``updated_u`` re-aligns to them)."""
+        o = self._o
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if u.shape != o._user_shape:
+            raise RuntimeError("assertion failed (xt::has_shape(u, m_u.shape()))")
+        check(lib.fqsb_chunk_align(o._h, u.ctypes.data, u.size))
+
+    @property
+    def generators(self):
+        """The per-block pcg32 generators (python-prrng ``pcg32_array`` as far as the systems use
+        it): ``initstate``, ``initseq``, and ``state()`` = the state after the last entry of the
+        current window, i.e. where prrng's own generators stand."""
+        return _Generators(self)
+
     def state_at(self, index):
         o = self._o
         index = np.ascontiguousarray(np.broadcast_to(index, o._user_shape).reshape(o._full_shape),
@@ -129,6 +146,42 @@ class _Chunk:
         check(lib.fqsb_chunk_restore(o._h, state.ctypes.data, value.ctypes.data,
                                      index.ctypes.data, state.size))
         self._start = index.copy()
+
+
+class _Generators:
+    """``system.chunk.generators``: see :attr:`_Chunk.generators`."""
+
+    def __init__(self, chunk):
+        self._c = chunk
+
+    @property
+    def shape(self):
+        return list(self._c._o._user_shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self._c._o._user_shape))
+
+    @property
+    def initstate(self):
+        """seed + flat block index (+ realisation * seed_stride), Line1d.h:148-151."""
+        o = self._c._o
+        n = int(np.prod(o._shape))
+        stride = int(o._par.seed_stride) or n
+        r = np.arange(o._R, dtype=np.uint64).reshape((o._R,) + (1,) * len(o._shape))
+        p = np.arange(n, dtype=np.uint64).reshape(o._shape)
+        if int(o._par.seed_period):
+            p = (np.uint64(int(o._par.seed_first)) + p) % np.uint64(int(o._par.seed_period))
+        return o._squeeze(np.uint64(int(o._par.seed)) + r * np.uint64(stride) + p)
+
+    @property
+    def initseq(self):
+        return np.zeros(self._c._o._user_shape, dtype=np.uint64)  # Line1d.h:151
+
+    def state(self):
+        c = self._c
+        start = c.start
+        return c.state_at(start + c.chunk_size)
 
 
 class _External:

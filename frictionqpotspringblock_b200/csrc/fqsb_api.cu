@@ -324,11 +324,9 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     case FQSB_DIST_POWER:
     case FQSB_DIST_PARETO:
     case FQSB_DIST_WEIBULL:
-        break;
     case FQSB_DIST_GAMMA:
     case FQSB_DIST_NORMAL:
-        return fail(FQSB_EUNSUPPORTED,
-                    "distribution not supported on the device (needs boost special functions)");
+        break;
     default:
         return fail(FQSB_EASSERT, "Unknown distribution: " + std::to_string(par->distribution));
     }
@@ -425,7 +423,12 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     {
         // prrng defaults for omitted parameters
         double def[4] = {1.0, 0.0, 0.0, 0.0};
-        if (par->distribution == FQSB_DIST_PARETO || par->distribution == FQSB_DIST_WEIBULL) {
+        if (par->distribution == FQSB_DIST_PARETO || par->distribution == FQSB_DIST_WEIBULL ||
+            par->distribution == FQSB_DIST_GAMMA) {
+            def[1] = 1.0;
+        }
+        if (par->distribution == FQSB_DIST_NORMAL) { // normal(mu = 0, sigma = 1), offset 0
+            def[0] = 0.0;
             def[1] = 1.0;
         }
         for (int k = 0; k < 4; ++k) {
@@ -952,6 +955,7 @@ static bool use_blocked(const fqsb_system* s, int mode, bool overdamped)
 }
 
 static int ensure_stream_buffers(fqsb_system* s);
+static int run_host_ring(fqsb_system* s, RunArgs A, bool overdamped, bool track_user);
 
 static int ensure_blocked_buffers(fqsb_system* s, const BlockedPlan& plan)
 {
@@ -1082,9 +1086,17 @@ static int ensure_stream_buffers(fqsb_system* s)
 // Runs one dynamics call to completion. On return h_ctl holds the final control blocks.
 static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
 {
-    if (A.mode != MODE_FIXED && A.mode != MODE_LOG &&
-        (A.niter_tol < 1 || A.niter_tol > FQSB_RING)) {
-        return fail(FQSB_EUNSUPPORTED, "niter_tol must be in [1, 32]");
+    if (A.mode != MODE_FIXED && A.mode != MODE_LOG && A.niter_tol < 1) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("niter_tol >= 1"));
+    }
+    if (A.mode != MODE_FIXED && A.mode != MODE_LOG && A.niter_tol > FQSB_RING) {
+        // the device keeps the StopList in the 32 lanes of a warp; longer lists (the reference
+        // takes any size, detail.h:1676-1689) are replayed on the host over logged batches
+        if (s->R != 1) {
+            return fail(FQSB_EUNSUPPORTED,
+                        "niter_tol > 32 is available for single systems (nrealisations == 1)");
+        }
+        return run_host_ring(s, A, overdamped, track_user);
     }
     A.own_lo = (int)s->own_lo;
     A.own_hi = (int)s->own_hi;
@@ -1715,6 +1727,22 @@ int fqsb_chunk_right_of_align(fqsb_system* s, double* out, int64_t n)
     CU(cudaMemcpyAsync(out, s->S.yr, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return FQSB_OK;
+}
+
+int fqsb_chunk_align(fqsb_system* s, const double* u, int64_t n)
+{
+    TRY(enter(s));
+    if (n != s->n || !u) {
+        return fail(FQSB_EASSERT, ASSERT_MSG("xt::has_shape(u, m_u.shape())"));
+    }
+    TRY(scratch(s, (size_t)n * sizeof(double)));
+    CU(cudaMemcpyAsync(s->d_scratch, u, (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                       s->stream));
+    k_align_to<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S, (const double*)s->d_scratch);
+    CU(cudaGetLastError());
+    s->launches++;
+    invalidate_forces(s);
+    return check_flags(s);
 }
 
 int fqsb_chunk_data(fqsb_system* s, const int64_t* first, int64_t nyield, double* out)

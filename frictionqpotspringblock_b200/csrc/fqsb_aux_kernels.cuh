@@ -200,6 +200,30 @@ __global__ void k_align(const Par P, const State S, const double* du)
     }
 }
 
+// `system.chunk.align(u)` (python-prrng pcg32_tensor_cumsum::align): the wells follow the given
+// positions; the system's slips are left alone
+__global__ void k_align_to(const Par P, const State S, const double* u)
+{
+    const i64 n = P.N * P.R;
+    int underflow = 0;
+    for (i64 g = blockIdx.x * (i64)blockDim.x + threadIdx.x; g < n; g += (i64)gridDim.x * blockDim.x) {
+        const double ug = u[g];
+        double yl = S.yl[g], yr = S.yr[g];
+        if (ug > yr || !(ug > yl)) {
+            u64 st = S.rng[g];
+            i64 i0 = S.idx[g];
+            int moved = well_align(P, ug, yl, yr, st, i0, &underflow);
+            S.rng[g] = st;
+            S.idx[g] = i0 + moved;
+            S.yl[g] = yl;
+            S.yr[g] = yr;
+        }
+    }
+    if (underflow) {
+        S.err[0] = 1;
+    }
+}
+
 // K8: materialise force arrays on demand (getters, detail.h:1429-1468).
 // mask bits: 1 potential, 2 interactions, 4 frame, 8 damping; f is always re-summed
 // (detail.h:1324) from the stored components.

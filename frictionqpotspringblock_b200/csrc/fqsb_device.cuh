@@ -297,6 +297,107 @@ __device__ __forceinline__ double erf_inv_dev(double z)
     return p * z;
 }
 
+// ---- inverse of the regularised lower incomplete gamma function P(a, x) = p -----------------------
+// prrng::pcg32::gamma(k, theta) = theta * boost::math::gamma_p_inv(k, r). boost is absent here, so
+// this is an own double-precision solve (parity with the oracle's 80-bit one to ~1e-14): P by its
+// series (x < a + 1) or Lentz's continued fraction for Q = 1 - P, the root by Halley's iteration
+// from the Wilson-Hilferty / small-a starting points. Out of line: only well changes draw.
+static __device__ __noinline__ double gamma_p_dev(double a, double x, double gln)
+{
+    if (x <= 0.0) {
+        return 0.0;
+    }
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 1000; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) {
+                break;
+            }
+        }
+        return sum * exp(-x + a * log(x) - gln);
+    }
+    const double tiny = 1e-300;
+    double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+    for (int i = 1; i < 1000; ++i) {
+        const double an = -(double)i * ((double)i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < tiny) {
+            d = tiny;
+        }
+        c = b + an / c;
+        if (fabs(c) < tiny) {
+            c = tiny;
+        }
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) {
+            break;
+        }
+    }
+    return 1.0 - exp(-x + a * log(x) - gln) * h;
+}
+
+static __device__ __noinline__ double gamma_p_inv_dev(double a, double p)
+{
+    if (!(a > 0.0) || p != p) {
+        return __longlong_as_double(0x7ff8000000000000LL);
+    }
+    if (p <= 0.0) {
+        return 0.0;
+    }
+    if (p >= 1.0) {
+        return __longlong_as_double(0x7ff0000000000000LL);
+    }
+    const double a1 = a - 1.0, gln = lgamma(a);
+    double x, lna1 = 0.0, afac = 0.0;
+    if (a > 1.0) {
+        lna1 = log(a1);
+        afac = exp(a1 * (lna1 - 1.0) - gln);
+        const double pp = p < 0.5 ? p : 1.0 - p;
+        const double t = sqrt(-2.0 * log(pp));
+        x = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
+        if (p < 0.5) {
+            x = -x;
+        }
+        const double w = 1.0 - 1.0 / (9.0 * a) - x / (3.0 * sqrt(a));
+        x = fmax(1e-3, a * w * w * w);
+    }
+    else {
+        const double t = 1.0 - a * (0.253 + a * 0.12);
+        x = p < t ? pow(p / t, 1.0 / a) : 1.0 - log(1.0 - (p - t) / (1.0 - t));
+    }
+    for (int j = 0; j < 30; ++j) {
+        if (x <= 0.0) {
+            return 0.0;
+        }
+        const double err = gamma_p_dev(a, x, gln) - p;
+        double t = a > 1.0 ? afac * exp(-(x - a1) + a1 * (log(x) - lna1))
+                           : exp(-x + a1 * log(x) - gln);
+        const double u = err / t;
+        t = u / (1.0 - 0.5 * fmin(1.0, u * (a1 / x - 1.0)));
+        x -= t;
+        if (x <= 0.0) {
+            x = 0.5 * (x + t);
+        }
+        if (fabs(t) < 1e-15 * x) {
+            break;
+        }
+    }
+    return x;
+}
+
+// prrng::pcg32::normal(mu, sigma) = mu + sigma * sqrt(2) * erf_inv(2 r - 1) (boost's erf_inv there,
+// erf_inv_dev here: a few 1e-16 apart); out of line for the same reason
+static __device__ __noinline__ double normal_from_draw_dev(double r, double mu, double sigma)
+{
+    return mu + (sigma * 1.4142135623730951) * erf_inv_dev(2.0 * r - 1.0);
+}
+
 // ---- distributions -> yield spacing ------------------------------------
 enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DIST_GAMMA = 4,
        DIST_PARETO = 5, DIST_WEIBULL = 6, DIST_NORMAL = 7 };
@@ -315,6 +416,12 @@ __host__ __device__ __forceinline__ double spacing_from_draw(const Par& P, doubl
         return pow(1.0 - r, 1.0 / (P.dpar[0] + 1.0)) + P.dpar[1];
     case DIST_PARETO:
         return P.dpar[1] * pow(1.0 - r, -1.0 / P.dpar[0]) + P.dpar[2];
+#ifdef __CUDA_ARCH__
+    case DIST_NORMAL: // normal(mu, sigma) + offset
+        return normal_from_draw_dev(r, P.dpar[0], P.dpar[1]) + P.dpar[2];
+    case DIST_GAMMA: // gamma(k, theta) + offset
+        return P.dpar[1] * gamma_p_inv_dev(P.dpar[0], r) + P.dpar[2];
+#endif
     default: // DIST_WEIBULL
         return P.dpar[1] * pow(-log(1.0 - r), 1.0 / P.dpar[0]) + P.dpar[2];
     }

@@ -1065,6 +1065,148 @@ static i64 slab_first_stop(const double* log, i64 k, HostRing& ring, double tol)
     return 0;
 }
 
+// ---- StopLists longer than the device ring (niter_tol > 32), single systems -----------------------
+// timeStepsUntilEvent / minimise / minimise_truncate (detail.h:1595-1622, 1754-1792, 1833-1893) as
+// batches of logged steps on the streaming kernels: snapshot, k steps whose per-step sums (and
+// well-change counts) are logged on the device, replay of the reference's per-step decisions on
+// the host with a StopList of any length; a stop inside a batch rolls back and redoes exactly
+// that many steps. Leaves h_ctl / the device control block as the resident kernels would.
+static int run_host_ring(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
+{
+    const i64 K = 64;
+    if ((size_t)K * FQSB_NLOG > s->log_cap) {
+        TRY(dev_alloc(s, &s->d_log, (size_t)K * FQSB_NLOG));
+        s->log_cap = (size_t)K * FQSB_NLOG;
+    }
+    i64 S_run = 0, A_run = 0;
+    if (track_user) { // S, A against the caller's i_n, reduced by the caller into d_out
+        CU(cudaMemcpyAsync(s->h_out, s->d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost,
+                           s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        S_run = (i64)s->h_out[2];
+        A_run = (i64)s->h_out[1];
+    }
+    TRY(pull_ctl(s));
+    const i64 inc0 = s->h_ctl[0].inc;
+    i64 qs_first = overdamped ? inc0 : s->h_ctl[0].qs_first;
+    i64 qs_last = overdamped ? inc0 : s->h_ctl[0].qs_last;
+    int init = 1;
+    i64 s_n = 0, steps = 0;
+    int status = ST_RUNNING;
+    double last_sf = 0.0, last_sff = 0.0;
+    HostRing ring((size_t)A.niter_tol);
+    std::vector<double> log((size_t)K * FQSB_NLOG);
+    auto logged = [&](i64 k) -> int {
+        RunArgs L = make_args(MODE_LOG, k);
+        L.track = A.track;
+        L.i_n = A.i_n;
+        L.log = s->d_log;
+        TRY(run(s, L, overdamped, false));
+        CU(cudaMemcpyAsync(log.data(), s->d_log, (size_t)k * FQSB_NLOG * sizeof(double),
+                           cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        return FQSB_OK;
+    };
+    while (status == ST_RUNNING) {
+        const i64 k = A.max_steps - steps < K ? A.max_steps - steps : K;
+        if (k <= 0) {
+            status = ST_EXHAUSTED;
+            break;
+        }
+        TRY(fqsb_snapshot(s));
+        TRY(logged(k));
+        // state of the bookkeeping at the start of the batch (a redo replays from here)
+        const HostRing ring0 = ring;
+        const i64 S0 = S_run, A0 = A_run, sn0 = s_n, qf0 = qs_first, ql0 = qs_last;
+        const int init0 = init;
+        auto replay = [&](i64 nsteps) -> i64 {
+            for (i64 j = 0; j < nsteps; ++j) {
+                const double* e = &log[(size_t)j * FQSB_NLOG];
+                const i64 inc = inc0 + (overdamped ? 0 : steps + j + 1);
+                last_sf = e[0];
+                last_sff = e[1];
+                if (e[0] != e[0]) { // detail.h:1567
+                    status = ST_NAN;
+                    return j + 1;
+                }
+                if (A.mode == MODE_UNTIL_EVENT && e[2] > 0.0) { // detail.h:1609
+                    status = ST_EVENT;
+                    return j + 1;
+                }
+                ring.roll_insert(e[0], e[1]);
+                if (A.track) { // detail.h:1768-1778, 1863-1872
+                    S_run += (i64)e[3];
+                    A_run += (i64)e[4];
+                    if (S_run != s_n) {
+                        if (init) {
+                            init = 0;
+                            qs_first = inc;
+                        }
+                        qs_last = inc;
+                    }
+                    s_n = S_run;
+                }
+                if (ring.stop(A.tol)) { // detail.h:1615, 1780, 1874
+                    status = ST_CONVERGED;
+                    return j + 1;
+                }
+                if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
+                    if ((A.A_truncate > 0 && A_run >= A.A_truncate) ||
+                        (A.S_truncate > 0 && S_run >= A.S_truncate)) {
+                        status = ST_TRUNCATED;
+                        return j + 1;
+                    }
+                }
+            }
+            return nsteps;
+        };
+        const i64 done = replay(k);
+        if (status != ST_RUNNING && done < k) {
+            // the call ends inside the batch: back to its start, exactly `done` steps
+            TRY(fqsb_rollback(s));
+            ring = ring0;
+            S_run = S0;
+            A_run = A0;
+            s_n = sn0;
+            qs_first = qf0;
+            qs_last = ql0;
+            init = init0;
+            const int want = status;
+            status = ST_RUNNING;
+            TRY(logged(done));
+            if (replay(done) != done || status != want) {
+                return fail(FQSB_EASSERT, "host StopList: the redone batch did not reproduce its log");
+            }
+        }
+        steps += done;
+        if (status == ST_RUNNING && steps >= A.max_steps) {
+            status = ST_EXHAUSTED;
+        }
+    }
+    if (status == ST_CONVERGED) { // quench(), detail.h:1749, 1781
+        k_zero_va<<<grid_for(s->n), 256, 0, s->stream>>>(s->P, s->S);
+        CU(cudaGetLastError());
+        s->launches++;
+    }
+    TRY(pull_ctl(s));
+    Ctl& c = s->h_ctl[0];
+    c.status = status;
+    c.steps = steps;
+    c.S = S_run;
+    c.A = A_run;
+    c.s_n = s_n;
+    c.init = init;
+    c.qs_first = qs_first;
+    c.qs_last = qs_last;
+    c.residual = last_sff != 0.0 ? std::sqrt(last_sf) / std::sqrt(last_sff) : std::sqrt(last_sf);
+    TRY(push_ctl(s));
+    invalidate_forces(s);
+    if (status == ST_NAN) {
+        return fail(FQSB_ENAN, "NaN entries found");
+    }
+    return check_flags(s);
+}
+
 static int slab_check_group(fqsb_system** m, int nm)
 {
     if (!m || nm < 1) {

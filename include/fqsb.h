@@ -71,10 +71,10 @@ typedef enum {
     FQSB_DIST_DELTA = 1,
     FQSB_DIST_EXPONENTIAL = 2,
     FQSB_DIST_POWER = 3,
-    FQSB_DIST_GAMMA = 4, /* unsupported: needs boost inverse incomplete gamma */
+    FQSB_DIST_GAMMA = 4, /* (k, theta, offset): theta * gamma_p_inv(k, r) + offset; own solver */
     FQSB_DIST_PARETO = 5,
     FQSB_DIST_WEIBULL = 6,
-    FQSB_DIST_NORMAL = 7 /* unsupported: needs boost erf_inv */
+    FQSB_DIST_NORMAL = 7 /* (mu, sigma, offset): mu + sigma*sqrt(2)*erf_inv(2r - 1) + offset */
 } fqsb_distribution;
 
 /* Constructor arguments of every Line1d / Line2d System_* class
@@ -200,6 +200,9 @@ int fqsb_advance_to_fixed_force(fqsb_system* s, const double* f_frame, int allow
 int fqsb_chunk_index_at_align(fqsb_system* s, int64_t* out, int64_t n); /* global well index i */
 int fqsb_chunk_left_of_align(fqsb_system* s, double* out, int64_t n);   /* y[i]   */
 int fqsb_chunk_right_of_align(fqsb_system* s, double* out, int64_t n);  /* y[i+1] */
+/* chunk.align(u): the wells follow the positions u [R*size] (the system's own slips are untouched;
+ * the next updated_u() re-aligns to them) */
+int fqsb_chunk_align(fqsb_system* s, const double* u, int64_t n);
 /* y[p, first[p] + j], j < nyield, row-major [R*size][nyield]; first [R*size] >= 0 */
 int fqsb_chunk_data(fqsb_system* s, const int64_t* first, int64_t nyield, double* out);
 /* pcg32 state positioned so that the next draw is global draw index[p] */

@@ -100,10 +100,112 @@ void orc_pcg32_draws(uint64_t initstate, uint64_t initseq, int64_t n, double* ou
     }
 }
 
+static double erf_inv_ld(double zd);
+
+/* Inverse of the regularised lower incomplete gamma function P(a, x) = p -- what prrng's
+ * pcg32::gamma maps its uniform draws through (boost::math::gamma_p_inv; boost is absent here,
+ * "parity unpinned"). Restated in 80-bit long double: P by its series (x < a + 1) or Lentz's
+ * continued fraction for Q = 1 - P, the root by Halley's iteration from the Wilson-Hilferty /
+ * small-a starting points (Numerical Recipes, 3rd ed., section 6.2.1), run to 1e-19 relative. */
+static long double gamma_p_ld(long double a, long double x, long double gln)
+{
+    if (x <= 0.0L) {
+        return 0.0L;
+    }
+    if (x < a + 1.0L) {
+        long double ap = a, del = 1.0L / a, sum = del;
+        for (int n = 0; n < 2000; ++n) {
+            ap += 1.0L;
+            del *= x / ap;
+            sum += del;
+            if (fabsl(del) < fabsl(sum) * 1e-21L) {
+                break;
+            }
+        }
+        return sum * expl(-x + a * logl(x) - gln);
+    }
+    const long double tiny = 1e-4000L;
+    long double b = x + 1.0L - a, c = 1.0L / tiny, d = 1.0L / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        const long double an = -(long double)i * ((long double)i - a);
+        b += 2.0L;
+        d = an * d + b;
+        if (fabsl(d) < tiny) {
+            d = tiny;
+        }
+        c = b + an / c;
+        if (fabsl(c) < tiny) {
+            c = tiny;
+        }
+        d = 1.0L / d;
+        const long double del = d * c;
+        h *= del;
+        if (fabsl(del - 1.0L) < 1e-21L) {
+            break;
+        }
+    }
+    return 1.0L - expl(-x + a * logl(x) - gln) * h;
+}
+
+static double gamma_p_inv_ld(double ad, double pd)
+{
+    if (!(ad > 0.0) || isnan(pd)) {
+        return NAN;
+    }
+    if (pd <= 0.0) {
+        return 0.0;
+    }
+    if (pd >= 1.0) {
+        return INFINITY;
+    }
+    const long double a = ad, p = pd, a1 = a - 1.0L, gln = lgammal(a);
+    long double x, lna1 = 0.0L, afac = 0.0L;
+    if (a > 1.0L) {
+        lna1 = logl(a1);
+        afac = expl(a1 * (lna1 - 1.0L) - gln);
+        const long double pp = p < 0.5L ? p : 1.0L - p;
+        const long double t = sqrtl(-2.0L * logl(pp));
+        x = (2.30753L + t * 0.27061L) / (1.0L + t * (0.99229L + t * 0.04481L)) - t;
+        if (p < 0.5L) {
+            x = -x;
+        }
+        const long double w = 1.0L - 1.0L / (9.0L * a) - x / (3.0L * sqrtl(a));
+        x = fmaxl(1e-3L, a * w * w * w);
+    }
+    else {
+        const long double t = 1.0L - a * (0.253L + a * 0.12L);
+        x = p < t ? powl(p / t, 1.0L / a) : 1.0L - logl(1.0L - (p - t) / (1.0L - t));
+    }
+    for (int j = 0; j < 40; ++j) {
+        if (x <= 0.0L) {
+            return 0.0;
+        }
+        const long double err = gamma_p_ld(a, x, gln) - p;
+        long double t = a > 1.0L ? afac * expl(-(x - a1) + a1 * (logl(x) - lna1))
+                                 : expl(-x + a1 * logl(x) - gln);
+        const long double u = err / t;
+        t = u / (1.0L - 0.5L * fminl(1.0L, u * (a1 / x - 1.0L)));
+        x -= t;
+        if (x <= 0.0L) {
+            x = 0.5L * (x + t);
+        }
+        if (fabsl(t) < 1e-19L * x) {
+            break;
+        }
+    }
+    return (double)x;
+}
+
+double orc_gamma_p_inv(double a, double p) { return gamma_p_inv_ld(a, p); }
+
 /* distributions -> yield spacing (App. A.2; detail.h:31-66 lists the names) */
 double orc_draw_to_spacing(double r, int32_t dist, const double* p)
 {
     switch (dist) {
+    case ORC_DIST_NORMAL: /* prrng::pcg32::normal(mu, sigma) (+ offset) */
+        return p[0] + (p[1] * sqrt(2.0)) * erf_inv_ld(2.0 * r - 1.0) + p[2];
+    case ORC_DIST_GAMMA: /* prrng::pcg32::gamma(k, theta) (+ offset) */
+        return p[1] * gamma_p_inv_ld(p[0], r) + p[2];
     case ORC_DIST_RANDOM:
         return r * p[0] + p[1];
     case ORC_DIST_DELTA:
@@ -126,7 +228,11 @@ static void default_parameters(int32_t dist, int32_t n, const double* in, double
     /* prrng defaults: random(scale=1,offset=0) delta(scale=1,offset=0) exponential(scale=1,
      * offset=0) power(k=1,offset=0) pareto(k=1,scale=1,offset=0) weibull(k=1,scale=1,offset=0) */
     double def[4] = {1.0, 0.0, 0.0, 0.0};
-    if (dist == ORC_DIST_PARETO || dist == ORC_DIST_WEIBULL) {
+    if (dist == ORC_DIST_PARETO || dist == ORC_DIST_WEIBULL || dist == ORC_DIST_GAMMA) {
+        def[1] = 1.0;
+    }
+    if (dist == ORC_DIST_NORMAL) { /* normal(mu = 0, sigma = 1), offset 0 */
+        def[0] = 0.0;
         def[1] = 1.0;
     }
     for (int k = 0; k < 4; ++k) {
@@ -615,9 +721,11 @@ int orc_create(const orc_params* par, orc_system** out)
     case ORC_DIST_POWER:
     case ORC_DIST_PARETO:
     case ORC_DIST_WEIBULL:
+    case ORC_DIST_GAMMA:
+    case ORC_DIST_NORMAL:
         break;
     default:
-        return fail(ORC_EUNSUPPORTED, "distribution needs boost special functions (gamma, normal)");
+        return fail(ORC_EASSERT, "Unknown distribution");
     }
     orc_system* s = (orc_system*)calloc(1, sizeof *s);
     s->par = *par;

@@ -157,6 +157,7 @@ void orc_pcg32_randint(uint64_t initstate, uint64_t initseq, int64_t n, uint32_t
 double orc_erf_inv(double z);
 void orc_pcg32_draws(uint64_t initstate, uint64_t initseq, int64_t n, double* out);
 double orc_draw_to_spacing(double r, int32_t distribution, const double* par);
+double orc_gamma_p_inv(double a, double p);
 
 /* bounded multi-threaded CPU arm for bench.py: `nsys` independent lines (seed = seed0 + r*N),
  * one realisation per thread round-robin; create() prepares them with minimise() and one

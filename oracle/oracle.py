@@ -136,6 +136,8 @@ def lib():
         L.orc_pcg32_randint.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_void_p]
         L.orc_erf_inv.argtypes = [C.c_double]
         L.orc_erf_inv.restype = C.c_double
+        L.orc_gamma_p_inv.argtypes = [C.c_double, C.c_double]
+        L.orc_gamma_p_inv.restype = C.c_double
         _LIB = L
     return _LIB
 

@@ -486,7 +486,10 @@ def test_shape_and_argument_validation():
     with pytest.raises(RuntimeError, match="direction == 1"):
         p.eventDrivenStep(1e-3, True, direction=2)
     with pytest.raises(RuntimeError, match="niter_tol"):
-        p.minimise(niter_tol=33)
+        p.minimise(niter_tol=0)
+    ens = F.Line1d.Ensemble_Cuspy_Laplace(shape=[8], nrealisations=3, **kw)
+    with pytest.raises(RuntimeError, match="niter_tol > 32 is available for single systems"):
+        ens.minimise(niter_tol=33)
     with pytest.raises(TypeError):
         F.Line1d.System_Cuspy_Laplace(shape=[8], seed=0)
     with pytest.raises(AttributeError):
@@ -497,3 +500,51 @@ def test_shape_and_argument_validation():
     assert p.inc == 123 and np.isclose(p.t, 12.3)
     p.inc = 7
     assert p.quasistaticActivityFirst == 7 and p.quasistaticActivityLast == 7
+
+
+@pytest.mark.parametrize("module,cls,extra", [
+    ("Line1d", "System_Cuspy_Laplace", dict(k_interactions=1.0)),
+    ("Line1d", "System_Cuspy_Quartic", dict(a1=1.0, a2=0.5)),
+    ("Line1d", "System_Cuspy_Laplace_Nopassing", dict(k_interactions=1.0)),
+    ("Line2d", "System_Cuspy_Laplace", dict(k_interactions=1.0)),
+])
+@pytest.mark.parametrize("niter_tol", [33, 100])
+def test_stoplists_longer_than_the_device_ring(module, cls, extra, niter_tol):
+    """The reference's StopList takes any length (detail.h:1676-1689); beyond the 32 entries the
+    device keeps in the lanes of a warp the decisions are replayed on the host over logged
+    batches. Step counts, well indices, S/A and the activity timestamps equal the oracle's."""
+    shape = [24, 20] if module == "Line2d" else [300]
+    n = int(np.prod(shape))
+    kw = dict(mu=1.0, k_frame=1.0 / n, shape=shape, seed=5, distribution="random",
+              parameters=[2.0], offset=-50, **extra)
+    nopassing = "Nopassing" in cls
+    if not nopassing:
+        kw.update(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, dt=0.1)
+    o, p = pair(module, cls, **kw)
+    for s in (o, p):
+        s.u_frame = 0.7
+        assert s.minimise(niter_tol=niter_tol) == 0
+    assert o.inc == p.inc
+    assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+    for _ in range(3):
+        for s in (o, p):
+            s.eventDrivenStep(1e-3, False)
+            s.eventDrivenStep(1e-3, True)
+            assert s.minimise(niter_tol=niter_tol, time_activity=not nopassing) == 0
+        assert o.inc == p.inc
+        assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+        assert o.quasistaticActivityFirst == p.quasistaticActivityFirst
+        assert o.quasistaticActivityLast == p.quasistaticActivityLast
+        assert np.allclose(o.u, p.u, rtol=0, atol=1e-9)
+    assert np.all(p.v == 0.0)  # quench() on convergence
+    if nopassing:
+        return
+    # not converging is reported the same way (quirk Q4) and timeStepsUntilEvent agrees
+    for s in (o, p):
+        s.eventDrivenStep(1e-3, False)
+        s.eventDrivenStep(1e-3, True)
+    assert o.minimise(niter_tol=niter_tol, max_iter=70, max_iter_is_error=False) == \
+        p.minimise(niter_tol=niter_tol, max_iter=70, max_iter_is_error=False) == 71
+    assert o.timeStepsUntilEvent(niter_tol=niter_tol) == p.timeStepsUntilEvent(niter_tol=niter_tol)
+    assert o.inc == p.inc
+    assert np.array_equal(o.u, p.u)
