@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+// the helper kernels of this unit (k_init, k_align, k_chunk_data, ...) draw from every distribution
+#define FQSB_SLOW_DISTS
 #include "../../include/fqsb.h"
 #include "fqsb_host.h"
 #include "fqsb_aux_kernels.cuh"
@@ -527,8 +529,8 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
             // kernel (bit-identical to the reference's loop) would leave the tensor cores idle
             const bool stream_path = (par->kernel & 15) == 2 || resident_cfg(P.N).B == 0 ||
                                      ((par->kernel & 15) == 0 && P.R >= 32);
-            if (stream_path && P.N % 2 == 0 && P.N >= 256 &&
-                lr_gemm_smem(P.N) <= 227 * 1024) {
+            if (stream_path && P.N % 2 == 0 && P.N >= 256 && lr_gemm_smem(P.N) <= 227 * 1024 &&
+                P.dist != DIST_GAMMA && P.dist != DIST_NORMAL) {
                 std::vector<double> tab((size_t)P.N, 0.0);
                 double rowsum = 0.0;
                 for (i64 k = 1; k < P.N; ++k) {
@@ -912,9 +914,18 @@ __global__ void k_ctl_begin(const Par P, const State S, int track_user, int over
     }
 }
 
+// `gamma` / `normal` landscapes only exist in the generic streaming kernels (fqsb_slowdist.cu)
+static bool slow_distribution(const fqsb_system* s)
+{
+    return s->P.dist == DIST_GAMMA || s->P.dist == DIST_NORMAL;
+}
+
 static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
 {
     *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
+    if (slow_distribution(s)) {
+        return false;
+    }
     if (mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N) {
         return false; // slab batches run on the streaming kernels
     }
@@ -931,7 +942,7 @@ static bool use_resident(const fqsb_system* s, ResidentCfg* cfg, int mode)
 static bool use_resident_thermal(const fqsb_system* s, ResidentCfg* cfg, int mode)
 {
     if (!s->thermal || mode != MODE_FIXED || (s->par.kernel & 15) == 2 || s->own_lo != 0 ||
-        s->own_hi != s->N) {
+        s->own_hi != s->N || slow_distribution(s)) {
         return false;
     }
     *cfg = resident_cfg(s->N, (s->par.kernel >> 4) & 15);
@@ -945,7 +956,7 @@ static bool use_blocked(const fqsb_system* s, int mode, bool overdamped)
 {
     const int sel = s->par.kernel & 15;
     if (overdamped || mode == MODE_LOG || s->own_lo != 0 || s->own_hi != s->N || s->lr_gemm ||
-        s->thermal) {
+        s->thermal || slow_distribution(s)) {
         return false;
     }
     if (!blocked_supported(s->P)) {
@@ -1155,7 +1166,7 @@ static int run(fqsb_system* s, RunArgs A, bool overdamped, bool track_user)
         }
     }
     else {
-        if ((s->par.kernel & 15) == 1) {
+        if ((s->par.kernel & 15) == 1 && !slow_distribution(s)) {
             return fail(FQSB_EUNSUPPORTED, "system too large for the resident kernel");
         }
         TRY(ensure_stream_buffers(s));

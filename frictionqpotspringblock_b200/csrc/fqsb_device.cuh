@@ -297,6 +297,13 @@ __device__ __forceinline__ double erf_inv_dev(double z)
     return p * z;
 }
 
+// `gamma` and `normal` spacings need long special-function code (a series / continued-fraction
+// solve, erf_inv). Compiled into the hot kernels -- even out of line, on a path that never runs --
+// it cost them ~20 % (deeper call graph: larger frames, more registers saved around the hop path).
+// It therefore exists only in translation units that define FQSB_SLOW_DISTS: the helper kernels of
+// fqsb_api.cu and the generic streaming kernels of fqsb_slowdist.cu, which systems with these two
+// distributions are routed to (fqsb_stream.cu: launch_stream_step / launch_stream_sweep).
+#ifdef FQSB_SLOW_DISTS
 // ---- inverse of the regularised lower incomplete gamma function P(a, x) = p -----------------------
 // prrng::pcg32::gamma(k, theta) = theta * boost::math::gamma_p_inv(k, r). boost is absent here, so
 // this is an own double-precision solve (parity with the oracle's 80-bit one to ~1e-14): P by its
@@ -398,6 +405,8 @@ static __device__ __noinline__ double normal_from_draw_dev(double r, double mu, 
     return mu + (sigma * 1.4142135623730951) * erf_inv_dev(2.0 * r - 1.0);
 }
 
+#endif // FQSB_SLOW_DISTS
+
 // ---- distributions -> yield spacing ------------------------------------
 enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DIST_GAMMA = 4,
        DIST_PARETO = 5, DIST_WEIBULL = 6, DIST_NORMAL = 7 };
@@ -416,7 +425,7 @@ __host__ __device__ __forceinline__ double spacing_from_draw(const Par& P, doubl
         return pow(1.0 - r, 1.0 / (P.dpar[0] + 1.0)) + P.dpar[1];
     case DIST_PARETO:
         return P.dpar[1] * pow(1.0 - r, -1.0 / P.dpar[0]) + P.dpar[2];
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && defined(FQSB_SLOW_DISTS)
     case DIST_NORMAL: // normal(mu, sigma) + offset
         return normal_from_draw_dev(r, P.dpar[0], P.dpar[1]) + P.dpar[2];
     case DIST_GAMMA: // gamma(k, theta) + offset

@@ -1285,7 +1285,7 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
     // 1-D nearest-neighbour lines: the temporally blocked kernel (one launch per batch) unless the
     // streaming kernels are forced; everything else streams
     const bool blocked = ksel != 2 && s->P.rank == 1 && blocked_supported(s->P) &&
-                         s->par.minimisation == FQSB_MIN_DYNAMIC;
+                         s->par.minimisation == FQSB_MIN_DYNAMIC && !slow_distribution(s);
     if (ksel == 3 && !blocked) {
         return fail(FQSB_EUNSUPPORTED, "no blocked kernel for this system");
     }

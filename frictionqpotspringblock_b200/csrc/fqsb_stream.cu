@@ -5,7 +5,15 @@
 #include "fqsb_host.h"
 #include "fqsb_kernels.cuh"
 
+// fqsb_slowdist.cu: the generic kernels compiled with the `gamma` / `normal` distributions
+cudaError_t launch_stream_step_slowdist(const void* P, const void* S, const void* A,
+                                        cudaStream_t stream, int flip, int finalise);
+cudaError_t launch_stream_sweep_slowdist(const void* P, const void* S, const void* A,
+                                         cudaStream_t stream, int flip, int first, int sweep_arg);
+
 namespace fqsb {
+
+static bool slow_dist(const Par& P) { return P.dist == DIST_GAMMA || P.dist == DIST_NORMAL; }
 
 #define FQSB_DECL(k) \
     cudaError_t launch_resident_##k(const ResidentCfg&, const Par&, const State&, \
@@ -79,10 +87,13 @@ cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
 // (thermal systems -- External = RandomNormalForcing -- take the generic kernel)
 static bool use_tiled_1d(const Par& P)
 {
-    return !P.thermal && P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0;
+    return !P.thermal && !slow_dist(P) && P.inter <= INT_QUARTICGRADIENT1D && P.N % 2 == 0;
 }
 
-static bool use_tiled_2d(const Par& P) { return !P.thermal && P.rank == 2 && P.cols % 2 == 0; }
+static bool use_tiled_2d(const Par& P)
+{
+    return !P.thermal && !slow_dist(P) && P.rank == 2 && P.cols % 2 == 0;
+}
 
 int stream_step_tiles(const Par& P, int generic_tiles)
 {
@@ -222,6 +233,9 @@ cudaError_t launch_stream_step(const Par& P, const State& S, const RunArgs& A,
         }
         return cudaGetLastError();
     }
+    if (slow_dist(P)) {
+        return launch_stream_step_slowdist(&P, &S, &A, stream, flip, finalise);
+    }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
     if (P.thermal) { // Line1d.h:261-330, 486-556; Particles.h System_Cuspy_RandomForcing
         switch (combo_of(P.pot, P.inter)) {
@@ -280,6 +294,9 @@ cudaError_t launch_stream_sweep(const Par& P, const State& S, const RunArgs& A,
         k_stream_np_2d<FQSB_S2_NP_CTAS><<<grid2, FQSB_S2_THREADS, 0, stream>>>(P, S, A, flip, first,
                                                                              do_sweep);
         return cudaGetLastError();
+    }
+    if (slow_dist(P)) {
+        return launch_stream_sweep_slowdist(&P, &S, &A, stream, flip, first, do_sweep);
     }
     dim3 grid((unsigned)S.tiles, (unsigned)P.R);
     if (P.inter == INT_LAPLACE2D) {

@@ -43,13 +43,15 @@ def test_landscape_and_driven_run(dist, par, exact, kernel):
     if exact:
         assert np.array_equal(yo, yp)
     else:  # device log / pow / erf_inv / gamma_p_inv against glibc / the 80-bit restatements
-        assert np.allclose(yo, yp, rtol=1e-13, atol=1e-12), np.abs(yo - yp).max()
-    assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
+        # (1e-13 of the scale of the landscape: the sums of 300 spacings differ by a few ulp each)
+        assert np.abs(yo - yp).max() <= 1e-13 * np.abs(yo).max(), np.abs(yo - yp).max()
+    i0 = o.chunk.index_at_align
+    assert np.array_equal(i0, p.chunk.index_at_align)
     for s in (o, p):
-        s.u_frame = 60.0
+        s.u_frame = 1500.0  # k_frame = 1/257: far beyond the pinning force, everything slides
         s.timeSteps(400)
     assert np.array_equal(o.chunk.index_at_align, p.chunk.index_at_align)
-    assert np.sum(o.chunk.index_at_align) > 40 * 257  # every block changed wells many times
+    assert np.sum(o.chunk.index_at_align - i0) > 3 * 257  # the blocks changed wells many times
     for name in ("u", "v", "f_potential"):
         x, y = getattr(o, name), getattr(p, name)
         if exact:
