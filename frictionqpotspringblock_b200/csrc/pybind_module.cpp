@@ -76,6 +76,9 @@ void mySystemNd(Binder& cls) // main.cpp:46-151
         std::copy(i.begin(), i.end(), out.mutable_data());
         return out;
     });
+    cls.def_property_readonly(
+        "chunk", [](System& s) -> M::detail::Chunk& { return s.chunk(); },
+        py::return_value_policy::reference_internal, "Chunk of random numbers"); // main.cpp:65-70
     cls.def("refresh", &System::refresh, "refresh");
     cls.def("quench", &System::quench, "quench");
     cls.def("maxUniformDisplacement", &System::maxUniformDisplacement, py::arg("direction") = 1);
@@ -143,6 +146,57 @@ PYBIND11_MODULE(_FrictionQPotSpringBlock, m)
 
     { // main.cpp:246-276
         py::module sm = m.def_submodule("detail", "detail");
+        { // the prrng::pcg32_tensor_cumsum surface the systems expose as `system.chunk`
+            using Ch = M::detail::Chunk;
+            py::class_<Ch> ch(sm, "Chunk");
+            auto ints = [](const std::vector<int64_t>& v) {
+                return py::array_t<int64_t>(static_cast<py::ssize_t>(v.size()), v.data());
+            };
+            auto dbls = [](const std::vector<double>& v) {
+                return py::array_t<double>(static_cast<py::ssize_t>(v.size()), v.data());
+            };
+            ch.def_property_readonly("chunk_size", &Ch::chunk_size);
+            ch.def_property_readonly("index_at_align",
+                                     [ints](const Ch& c) { return ints(c.index_at_align()); });
+            ch.def_property_readonly(
+                "chunk_index_at_align",
+                [ints](const Ch& c) { return ints(c.chunk_index_at_align()); });
+            ch.def_property_readonly("start", [ints](const Ch& c) { return ints(c.start()); });
+            ch.def_property_readonly("left_of_align",
+                                     [dbls](const Ch& c) { return dbls(c.left_of_align()); });
+            ch.def_property_readonly("right_of_align",
+                                     [dbls](const Ch& c) { return dbls(c.right_of_align()); });
+            ch.def_property_readonly("data", [](const Ch& c) {
+                const auto& v = c.data();
+                const py::ssize_t nc = static_cast<py::ssize_t>(c.chunk_size());
+                py::array_t<double> out({static_cast<py::ssize_t>(v.size()) / nc, nc});
+                std::copy(v.begin(), v.end(), out.mutable_data());
+                return out;
+            });
+            ch.def("align",
+                   [](Ch& c, const py::array_t<double, py::array::c_style | py::array::forcecast>& u) {
+                       c.align(as_vector(u));
+                   },
+                   py::arg("u"));
+            ch.def("state_at",
+                   [](const Ch& c,
+                      const py::array_t<int64_t, py::array::c_style | py::array::forcecast>& index) {
+                       const auto& v = c.state_at(
+                           std::vector<int64_t>(index.data(), index.data() + index.size()));
+                       return py::array_t<uint64_t>(static_cast<py::ssize_t>(v.size()), v.data());
+                   },
+                   py::arg("index"));
+            ch.def("restore",
+                   [](Ch& c,
+                      const py::array_t<uint64_t, py::array::c_style | py::array::forcecast>& state,
+                      const py::array_t<double, py::array::c_style | py::array::forcecast>& value,
+                      const py::array_t<int64_t, py::array::c_style | py::array::forcecast>& index) {
+                       c.restore(std::vector<uint64_t>(state.data(), state.data() + state.size()),
+                                 as_vector(value),
+                                 std::vector<int64_t>(index.data(), index.data() + index.size()));
+                   },
+                   py::arg("state"), py::arg("value"), py::arg("index"));
+        }
         using S = M::detail::RandomNormalForcing;
         py::class_<S> cls(sm, "RandomNormalForcing_1");
         cls.def_property("state", &S::state, &S::set_state, "State of RNG");
@@ -326,6 +380,14 @@ PYBIND11_MODULE(_FrictionQPotSpringBlock, m)
                     py::arg("m"), py::arg("eta"), py::arg("mu"), py::arg("k2"), py::arg("k4"),
                     py::arg("k_frame"), py::arg("dt"), FQSB_COMMON_ARGS);
             mySystemNdDynamics(cls);
+        }
+        { // 2-D generalisation of Line1d.System_Cuspy_Laplace_Nopassing (new)
+            py::class_<SM::System_Cuspy_Laplace_Nopassing, System> cls(
+                sm, "System_Cuspy_Laplace_Nopassing");
+            cls.def(py::init<double, double, double, S2, uint64_t, Str, Par, double, size_t,
+                             double, double>(),
+                    py::arg("mu"), py::arg("k_interactions"), py::arg("k_frame"),
+                    FQSB_COMMON_ARGS, py::arg("eta") = 0.0, py::arg("dt") = 0.0);
         }
     }
 }

@@ -37,6 +37,8 @@ def test_cpp_host_reproduces_golden(golden_dir):
     assert np.allclose([float(r[1]) for r in rows], golden["x_frame"][:n])
     assert np.allclose([float(r[2]) for r in rows], golden["f_frame"][:n])
     assert "error fqsb: assertion failed (tol < 1.0)" in out
+    # system.chunk(), Ensemble<S> and Slab<S, 1> of include/fqsb.hpp
+    assert "chunk ok" in out and "ensemble ok" in out and "slab ok" in out
 
 
 def _pybind():
@@ -79,29 +81,24 @@ def test_pybind_module_reproduces_golden(golden_dir):
 
     P = _pybind()
 
-    class Chunk:  # the examples read system.chunk.index_at_align
-        def __init__(self, s):
-            self._s = s
-
-        @property
-        def index_at_align(self):
-            return self._s.index_at_align
-
     system = P.Line1d.System_Cuspy_Laplace(k_interactions=1.0, **protocol.BASE)
-    system_proxy = type("Proxy", (), {})()
     golden = np.load(golden_dir / "Line1d_Cuspy_Laplace.npz")
-
-    class Wrapped:
-        chunk = Chunk(system)
-
-        def __getattr__(self, k):
-            return getattr(system, k)
-
-        def __setattr__(self, k, v):
-            setattr(system, k, v)
-
-    protocol.check(golden, *protocol.run(Wrapped(), 60))
-    del system_proxy
+    # the examples read system.chunk.index_at_align (python/main.cpp:65-70)
+    protocol.check(golden, *protocol.run(system, 60))
+    ch = system.chunk
+    i, st, data = ch.index_at_align, ch.start, ch.data
+    rows = np.arange(i.size)
+    assert data.shape == (i.size, ch.chunk_size)
+    assert np.array_equal(data[rows, i - st], ch.left_of_align)
+    assert np.array_equal(data[rows, i - st + 1], ch.right_of_align)
+    assert np.array_equal(ch.chunk_index_at_align, i - st)
+    state = ch.state_at(st)
+    ch.restore(state, data[:, 0].copy(), st)
+    assert np.array_equal(ch.index_at_align, i)
+    ch.align(system.u + 1.0)
+    assert np.all(ch.index_at_align >= i)
+    system.refresh()
+    assert np.array_equal(ch.index_at_align, i)
 
 
 @pytest.mark.gpu
