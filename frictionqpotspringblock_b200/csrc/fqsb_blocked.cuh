@@ -29,11 +29,12 @@ namespace fqsb {
 // rare path: a block of the tile left its well. The global index is idx_in + sdidx (the delta
 // accumulated during this launch); the input set is never written.
 static __device__ __noinline__ int hop_blocked(const Par& P, double un, double* yl, double* yr,
-                                               u64* st, i64 i0, int* underflow)
+                                               u64* st, const i64* gidx, int d0, int* underflow)
 {
     double l = *yl, r = *yr;
     u64 s = *st;
-    int moved = well_align(P, un, l, r, s, i0, underflow);
+    // (the global index is only read when the block moves left: boundary check of the landscape)
+    int moved = well_align_lazy(P, un, l, r, s, [gidx, d0]() { return *gidx + d0; }, underflow);
     *yl = l;
     *yr = r;
     *st = s;
@@ -168,10 +169,24 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                 if ((need >> j) & 1u) {
                     const int q = t + j * T;
                     const int gp = GP(q);
-                    const i64 i0 = idxi[gp] + sdidx[q];
                     int uflag = 0;
                     double l = yl[j], rr = yr[j];
-                    int moved = hop_blocked(P, uc[j], &l, &rr, sst + q, i0, &uflag);
+                    const int d0 = sdidx[q];
+                    int moved = 0;
+                    // inline fast path: one well to the right on a `random` landscape
+                    if (P.dist == DIST_RANDOM && uc[j] > rr) {
+                        const u64 st = sst[q];
+                        const double r2 = rr + (pcg_double(st) * P.dpar[0] + P.dpar[1]);
+                        if (!(uc[j] > r2)) {
+                            sst[q] = pcg_next(st);
+                            l = rr;
+                            rr = r2;
+                            moved = 1;
+                        }
+                    }
+                    if (moved == 0) {
+                        moved = hop_blocked(P, uc[j], &l, &rr, sst + q, idxi + gp, d0, &uflag);
+                    }
                     yl[j] = l;
                     yr[j] = rr;
                     sdidx[q] += moved;
@@ -180,7 +195,9 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                     }
                     if ((summask >> j) & 1u) {
                         hops += moved != 0;
-                        track_hop(A, base + gp, i0, moved, dS, dA);
+                        if (A.track) {
+                            track_hop(A, base + gp, idxi[gp] + d0, moved, dS, dA);
+                        }
                     }
                 }
             }

@@ -445,12 +445,20 @@ __host__ __device__ __forceinline__ double spacing_peek(const Par& P, u64 st)
 // ---- the yield landscape: prrng::pcg32_tensor_cumsum without a chunk ------------------------
 // A block keeps only its current well: yl = y[i], yr = y[i+1], the global index i and the
 // generator state st whose next draw is d_{i+2}. Leaving the well regenerates the neighbouring
-// yield position from the pcg32 stream (forward: one LCG step; backward: one inverse-LCG step),
-// so y[j] = y[j-1] + d_j exactly as a sequential cumsum. This replaces
+// yield position from the pcg32 stream. Forward (one LCG step): y[j] = y[j-1] + d_j, exactly the
+// sequential cumsum of the reference. Backward (one inverse-LCG step):
+// y[i-1] = y[i] - d_i, which is the exact inverse only where the partial sums are exact in
+// floating point (`random` / `delta` landscapes: multiples of 2^-31 -- all named configs); for the
+// other distributions a left move re-associates the sum by an ulp, as prrng's own backward
+// redraw does (the reference's tests only require allclose there). This replaces
 // m_chunk->align(u) (detail.h:144,180,197) and align(p,u) (detail.h:1732).
 // Returns the signed number of wells moved; sets *underflow when i would drop below 0.
-__host__ __device__ __forceinline__ int well_align(const Par& P, double u, double& yl, double& yr,
-                                          u64& st, i64 i_now, int* underflow)
+// `index_now()` is only called when the block moves LEFT (the check that the landscape has a
+// position there): callers whose index lives in global memory pay that load on backward moves only.
+template <class IndexNow>
+__host__ __device__ __forceinline__ int well_align_lazy(const Par& P, double u, double& yl,
+                                                        double& yr, u64& st, IndexNow&& index_now,
+                                                        int* underflow)
 {
     int moved = 0;
     if (!(fabs(u) <= 1.7976931348623157e308)) { // NaN / inf: reported by the NaN check
@@ -465,23 +473,32 @@ __host__ __device__ __forceinline__ int well_align(const Par& P, double u, doubl
         yr = yr + d;
         ++moved;
     }
-    while (!(u > yl)) {
-        if (i_now + moved <= 0) {
-            *underflow = 1;
-            break;
-        }
-        // y[i-1] = y[i] - d_i ; d_i is the draw two positions behind st
-        u64 sb = st;
-        if (P.consumes) {
-            st = pcg_prev(st);
-            sb = pcg_prev(st);
-        }
-        double d = spacing_peek(P, sb);
-        yr = yl;
-        yl = yl - d;
-        --moved;
+    if (!(u > yl)) {
+        const i64 i_now = index_now();
+        do {
+            if (i_now + moved <= 0) {
+                *underflow = 1;
+                break;
+            }
+            // y[i-1] = y[i] - d_i ; d_i is the draw two positions behind st
+            u64 sb = st;
+            if (P.consumes) {
+                st = pcg_prev(st);
+                sb = pcg_prev(st);
+            }
+            double d = spacing_peek(P, sb);
+            yr = yl;
+            yl = yl - d;
+            --moved;
+        } while (!(u > yl));
     }
     return moved;
+}
+
+__host__ __device__ __forceinline__ int well_align(const Par& P, double u, double& yl, double& yr,
+                                                   u64& st, i64 i_now, int* underflow)
+{
+    return well_align_lazy(P, u, yl, yr, st, [i_now]() { return i_now; }, underflow);
 }
 
 // ---- correctly rounded a / b for a loop-invariant divisor ------------------------------------

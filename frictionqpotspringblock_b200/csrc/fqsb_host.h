@@ -58,7 +58,7 @@ inline size_t resident_smem(const Par& P, const ResidentCfg& c)
     const size_t ghosts = P.inter < INT_LAPLACE2D ? 2 : 0;
     size_t words = 2 * (n + ghosts) + n + (c.ysmem ? 2 * n : 0) +
                    (P.inter == INT_LONGRANGE1D ? n : 0) + 4 * (size_t)(c.T / 32);
-    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int);
+    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int) + n * sizeof(int);
 }
 
 // dynamic shared memory of k_resident_nopassing: us[2][N], sst[N], red[NW][2]

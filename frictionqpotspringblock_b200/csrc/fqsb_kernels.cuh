@@ -140,9 +140,33 @@ __device__ __forceinline__ void track_hop(const RunArgs& A, i64 gp, i64 i_before
 // DRAM is touched at entry/exit and on the rare well change (idx, i_n).
 // =============================================================================================
 
-// rare path: a block left its well (out of line: keeps the hot loop's register budget small)
+// a block left its well (out of line: keeps the hot loop's register budget small). The global
+// well index stays in DRAM: only the number of wells moved since the launch began is kept on chip
+// (`sd`), so a forward move -- the common one, and in driven flow every block makes one every few
+// steps -- touches no global memory at all; the index itself is read for the left-boundary check
+// of a backward move and for the S / A bookkeeping of the tracking modes.
 static __device__ __noinline__ int hop_shared(const Par& P, double un, double* yl, double* yr, u64* st,
-                                       i64* gidx, int* underflow, i64* i_before)
+                                       const i64* gidx, int* sd, int* underflow, int track,
+                                       i64* i_before)
+{
+    double l = *yl, r = *yr;
+    u64 s = *st;
+    const int d0 = *sd;
+    int moved = well_align_lazy(P, un, l, r, s, [gidx, d0]() { return *gidx + d0; }, underflow);
+    *yl = l;
+    *yr = r;
+    *st = s;
+    *sd = d0 + moved;
+    if (track) {
+        *i_before = *gidx + d0;
+    }
+    return moved;
+}
+
+// the same with generator state and well index updated in place in global memory (the thermal
+// resident kernel, whose shared memory is taken by its forcing arrays)
+static __device__ __noinline__ int hop_global(const Par& P, double un, double* yl, double* yr, u64* st,
+                                       i64* gidx, int* underflow)
 {
     double l = *yl, r = *yr;
     u64 s = *st;
@@ -152,13 +176,17 @@ static __device__ __noinline__ int hop_shared(const Par& P, double un, double* y
     *yr = r;
     *st = s;
     *gidx = i0 + moved;
-    *i_before = i0;
     return moved;
 }
 
 // STOP = false: timeSteps / flowSteps only (MODE_FIXED); STOP = true: the stop modes. Two
 // instantiations so that the bookkeeping of the stop modes costs the fixed-step loop no registers.
-template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT, bool STOP>
+// HOPINL = true: the common well change (one well to the right on a `random` landscape) is taken
+// inline. It pays whenever blocks change wells regularly (flowSteps, avalanches inside the stop
+// modes: +60 % at 0.07 well changes per block-update) but costs the quiescent fixed-step loop
+// ~5 %, so timeSteps() launches the variant without it.
+template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT, bool STOP,
+          bool HOPINL = STOP>
 __global__ void __launch_bounds__(T)
     k_resident(const __grid_constant__ Par P, const __grid_constant__ State S,
                const __grid_constant__ RunArgs A)
@@ -185,6 +213,7 @@ __global__ void __launch_bounds__(T)
     double* spref = syr + (YSMEM ? N : 0);                     // [N] if LongRange
     double* red = spref + (INT == INT_LONGRANGE1D ? N : 0);    // [2][NW][2]
     int* redi = reinterpret_cast<int*>(red + 4 * NW);          // [2][NW][4]
+    int* sdidx = redi + 8 * NW;                                // [N] wells moved in this launch
 
     const i64 base = (i64)r * P.N;
     double v[B], a[B];
@@ -212,6 +241,7 @@ __global__ void __launch_bounds__(T)
                 syr[p] = S.yr[base + p];
             }
             sst[p] = S.rng[base + p];
+            sdidx[p] = 0;
             if (INT == INT_LONGRANGE1D) {
                 spref[p] = S.pref[p];
             }
@@ -294,9 +324,26 @@ __global__ void __launch_bounds__(T)
                 if ((need >> j) & 1u) {
                     const int p = t + j * T;
                     double l = wl[j], rr = wr[j];
-                    i64 i_before;
-                    int moved = hop_shared(P, uc[j], &l, &rr, sst + p, S.idx + base + p,
-                                           &underflow, &i_before);
+                    i64 i_before = 0;
+                    int moved = 0;
+                    // inline fast path -- one well to the right on a `random` landscape, no S / A
+                    // tracking: what nearly every well change of a driven line is. No call, no
+                    // global memory; everything else goes out of line.
+                    if (HOPINL && P.dist == DIST_RANDOM && !A.track && uc[j] > rr) {
+                        const u64 st = sst[p];
+                        const double r2 = rr + (pcg_double(st) * P.dpar[0] + P.dpar[1]);
+                        if (!(uc[j] > r2)) {
+                            sst[p] = pcg_next(st);
+                            sdidx[p] += 1;
+                            l = rr;
+                            rr = r2;
+                            moved = 1;
+                        }
+                    }
+                    if (moved == 0) {
+                        moved = hop_shared(P, uc[j], &l, &rr, sst + p, S.idx + base + p,
+                                           sdidx + p, &underflow, A.track, &i_before);
+                    }
                     wl[j] = l;
                     wr[j] = rr;
                     if (YSMEM) {
@@ -566,6 +613,9 @@ __global__ void __launch_bounds__(T)
             S.yl[base + p] = YSMEM ? syl[p] : yl[j];
             S.yr[base + p] = YSMEM ? syr[p] : yr[j];
             S.rng[base + p] = sst[p];
+            if (sdidx[p] != 0) {
+                S.idx[base + p] += sdidx[p];
+            }
         }
     }
     if (nan) {

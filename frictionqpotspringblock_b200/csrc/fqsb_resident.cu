@@ -65,9 +65,13 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
     const bool full = (i64)c.B * c.T == P.N;
     const bool unit = unit_parameters(P);
     const bool stop = A.mode != MODE_FIXED;
+    const bool flow = A.flow != 0; // driven: blocks change wells all the time (inline hop path)
 #define FQSB_TRY_MODE(b, t, full_, unit_) \
-    return stop ? launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, true>, t, smem, P, S, A, stream) \
-                : launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false>, t, smem, P, S, A, stream);
+    if (stop) \
+        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, true, true>, t, smem, P, S, A, stream); \
+    if (flow) \
+        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, true>, t, smem, P, S, A, stream); \
+    return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, false>, t, smem, P, S, A, stream);
 #define FQSB_TRY_CFG(b, t) \
     if (c.B == b && c.T == t) { \
         if (full && unit) { \

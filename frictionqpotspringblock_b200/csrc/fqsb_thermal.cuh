@@ -253,9 +253,7 @@ __global__ void __launch_bounds__(T + 32)
             const double uc = ucur[pc + 1];
             if ((FULL || p < N) && (uc > yr[j] || !(uc > yl[j]))) { // rare: left its well
                 double l = yl[j], rr = yr[j];
-                i64 i_before;
-                hop_shared(P, uc, &l, &rr, S.rng + base + p, S.idx + base + p, &underflow,
-                           &i_before);
+                hop_global(P, uc, &l, &rr, S.rng + base + p, S.idx + base + p, &underflow);
                 yl[j] = l;
                 yr[j] = rr;
             }
