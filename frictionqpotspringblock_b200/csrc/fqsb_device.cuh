@@ -59,6 +59,9 @@ enum Mode : int {
 #define FQSB_NLOG 5 // logged per step: sum f^2, sum f_frame^2, hops, dS, dA
 
 #define FQSB_RING 32
+// resident stop modes: while the residual is >= tol it is only reduced every
+// min(niter_tol, FQSB_SKIP_K) steps (k_resident, "residual sampling")
+#define FQSB_SKIP_K 8
 
 struct Ctl {
     int status;

@@ -52,13 +52,15 @@ inline ResidentCfg resident_cfg(i64 N, int variant = 0)
 inline bool unit_parameters(const Par& P) { return P.mu == 1.0 && P.m == 1.0 && P.k1 == 1.0; }
 
 // dynamic shared memory of k_resident (must mirror the carve-up in the kernel)
-inline size_t resident_smem(const Par& P, const ResidentCfg& c)
+inline size_t resident_smem(const Par& P, const ResidentCfg& c, bool stop = true)
 {
     const size_t n = (size_t)P.N;
     const size_t ghosts = P.inter < INT_LAPLACE2D ? 2 : 0;
     size_t words = 2 * (n + ghosts) + n + (c.ysmem ? 2 * n : 0) +
                    (P.inter == INT_LONGRANGE1D ? n : 0) + 4 * (size_t)(c.T / 32);
-    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int) + n * sizeof(int);
+    // + the parked partial sums of the stop modes ([FQSB_SKIP_K - 1][T] pairs + their warp sums)
+    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int) + n * sizeof(int) + 16 +
+           (stop ? (size_t)(FQSB_SKIP_K - 1) * (c.T * 16 + (c.T / 32) * 16) : 0);
 }
 
 // dynamic shared memory of k_resident_nopassing: us[2][N], sst[N], red[NW][2]

@@ -214,6 +214,11 @@ __global__ void __launch_bounds__(T)
     double* red = spref + (INT == INT_LONGRANGE1D ? N : 0);    // [2][NW][2]
     int* redi = reinterpret_cast<int*>(red + 4 * NW);          // [2][NW][4]
     int* sdidx = redi + 8 * NW;                                // [N] wells moved in this launch
+    // stop modes: per-thread sums of the steps whose residual has not been reduced yet
+    // [FQSB_SKIP_K - 1][T] pairs, and the per-warp sums of a backlog being evaluated
+    double2* sback = reinterpret_cast<double2*>(
+        (reinterpret_cast<uintptr_t>(sdidx + N) + 15) & ~(uintptr_t)15);
+    double* rdb = reinterpret_cast<double*>(sback + (STOP ? (FQSB_SKIP_K - 1) * T : 0)); // [K-1][2 NW]
 
     const i64 base = (i64)r * P.N;
     double v[B], a[B];
@@ -445,6 +450,56 @@ __global__ void __launch_bounds__(T)
         // consumed only after the side-effect-free first part of step s+1 (phase2a), so its
         // latency hides behind useful work. A stop discards the speculative positions.
         double gsf = 0.0, gsff = 0.0; // sums of the step whose decision is pending
+        // Residual sampling (plain minimise): both criteria need ALL niter_tol newest residuals
+        // below tol, so a residual >= tol at step s rules out a stop at steps s .. s+niter_tol-1.
+        // While the residual is that large it is therefore only reduced every kskip <= niter_tol
+        // steps; in between a thread just parks its two partial sums in shared memory (no
+        // shuffles, no cross-warp sum, no decision). A sample below tol first evaluates the parked
+        // steps (every residual after the last one >= tol enters the ring, in order: the ring is
+        // then exact wherever it can matter) and switches back to per-step decisions.
+        const int kskip = (A.mode == MODE_MINIMISE && !A.track)
+                              ? (nring < FQSB_SKIP_K ? nring : FQSB_SKIP_K) : 1;
+        bool skip = false;    // sampling mode
+        bool pending = false; // gsf, gsff hold the sums of the step before
+        int nback = 0;        // parked steps
+        // ring insert: the newest entry replaces the oldest
+        auto ring_push = [&](const RingEntry& e) {
+            if (lane == head) {
+                ring = e;
+            }
+            head = head + 1 == nring ? 0 : head + 1;
+        };
+        // evaluate the parked steps (CTA-uniform; rare)
+        auto flush_parked = [&]() {
+#pragma unroll 1
+            for (int b = 0; b < nback; ++b) {
+                const double2 x = sback[b * T + t];
+                const bool odd = lane & 1;
+                double keep = odd ? x.y : x.x;
+                keep += __shfl_xor_sync(0xffffffffu, odd ? x.x : x.y, 1);
+#pragma unroll
+                for (int o = 16; o > 1; o >>= 1) {
+                    keep += __shfl_xor_sync(0xffffffffu, keep, o);
+                }
+                if (lane < 2) {
+                    rdb[b * 2 * NW + 2 * warp + lane] = keep;
+                }
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int b = 0; b < nback; ++b) {
+                double s1, s2;
+                if (2 * NW == 32) {
+                    warp_sum_interleaved(rdb[b * 2 * NW + lane], s1, s2);
+                }
+                else {
+                    s1 = warp_sum(lane < NW ? rdb[b * 2 * NW + 2 * lane] : 0.0);
+                    s2 = warp_sum(lane < NW ? rdb[b * 2 * NW + 2 * lane + 1] : 0.0);
+                }
+                ring_push(ring_entry(s1, s2));
+            }
+            nback = 0;
+        };
         if (nl > 0) {
             phase1(prev * NS, (prev ^ 1) * NS);
             __syncthreads();
@@ -455,10 +510,12 @@ __global__ void __launch_bounds__(T)
             if (it < nl) {
                 phase2a((prev ^ 1) * NS, uc, need);
             }
-            if (it > 0) { // ---- decision about step `it` (1-based), detail.h:1605-1619, 1764-1784
+            if (it > 0) {
+                its = it;
+            }
+            if (pending) { // ---- decision about step `it` (1-based), detail.h:1605-1619, 1764-1784
                 const int* ri = redi + ((it - 1) & 1) * 4 * NW;
                 const double sf = gsf, sff = gsff;
-                its = it;
                 if (sf != sf) { // NaN forces <=> NaN positions (detail.h:1567)
                     status = ST_NAN;
                     break;
@@ -470,12 +527,18 @@ __global__ void __launch_bounds__(T)
                         break;
                     }
                 }
-                // roll_insert: the newest entry replaces the oldest
                 const RingEntry e = ring_entry(sf, sff);
-                if (lane == head) {
-                    ring = e;
+                const bool below = e.num < A.tol2 * e.den;
+                if (skip) { // a sampled step
+                    if (below) {
+                        flush_parked();
+                        skip = false;
+                    }
+                    else {
+                        nback = 0; // no window that could stop contains the parked steps
+                    }
                 }
-                head = head + 1 == nring ? 0 : head + 1;
+                ring_push(e);
                 if (A.track) { // detail.h:1768-1778, 1863-1872
                     const int dS = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 1] : 0);
                     const int dA = __reduce_add_sync(0xffffffffu, lane < NW ? ri[4 * lane + 2] : 0);
@@ -493,7 +556,7 @@ __global__ void __launch_bounds__(T)
                 }
                 // Both criteria need EVERY entry below tol (all_less(tol) resp. all_less(tol^2)),
                 // the newest included: while it is not, nothing can stop (no shuffles, one compare)
-                if (e.num < A.tol2 * e.den) {
+                if (below) {
                     // lane l's successor in time is lane l + 1 (cyclically), except for the newest
                     // entry, whose cyclic neighbour is the oldest
                     const int succ = lane + 1 == nring ? 0 : lane + 1;
@@ -514,6 +577,10 @@ __global__ void __launch_bounds__(T)
                         break;
                     }
                 }
+                else if (kskip > 1) {
+                    skip = true;
+                    nback = 0;
+                }
                 if (A.mode == MODE_TRUNCATE) { // detail.h:1879-1885
                     if (dA_run >= A_left || dS_run >= S_left) {
                         status = ST_TRUNCATED;
@@ -532,7 +599,12 @@ __global__ void __launch_bounds__(T)
             // ---- residual + index-change reductions (detail.h:1512-1520, 1609, 1863-1864)
             double* rd = red + (it & 1) * 2 * NW;
             int* ri = redi + (it & 1) * 4 * NW;
-            {
+            pending = !(skip && nback < kskip - 1);
+            if (!pending) { // sampling mode, not a sampled step: park the thread's sums
+                sback[nback * T + t] = make_double2(sf, sff);
+                ++nback;
+            }
+            else {
                 // one butterfly for the pair: even lanes collect sf, odd lanes sff; lanes 0 / 1
                 // end up with the warp's sums (no broadcast needed)
                 const bool odd = lane & 1;
@@ -545,29 +617,34 @@ __global__ void __launch_bounds__(T)
                 if (lane < 2) {
                     rd[2 * warp + lane] = keep;
                 }
-            }
-            if (A.mode == MODE_UNTIL_EVENT || A.track) {
-                hops = __reduce_add_sync(0xffffffffu, hops);
-                if (A.track) {
-                    dS = __reduce_add_sync(0xffffffffu, dS);
-                    dA = __reduce_add_sync(0xffffffffu, dA);
-                }
-                if (lane == 0) {
-                    ri[4 * warp] = hops;
-                    ri[4 * warp + 1] = dS;
-                    ri[4 * warp + 2] = dA;
+                if (A.mode == MODE_UNTIL_EVENT || A.track) {
+                    hops = __reduce_add_sync(0xffffffffu, hops);
+                    if (A.track) {
+                        dS = __reduce_add_sync(0xffffffffu, dS);
+                        dA = __reduce_add_sync(0xffffffffu, dA);
+                    }
+                    if (lane == 0) {
+                        ri[4 * warp] = hops;
+                        ri[4 * warp + 1] = dS;
+                        ri[4 * warp + 2] = dA;
+                    }
                 }
             }
             phase1(prev * NS, (prev ^ 1) * NS); // speculative
             __syncthreads();
             // issue the reduction of this step's partials; consumed in the next iteration
-            if (2 * NW == 32) {
-                warp_sum_interleaved(rd[lane], gsf, gsff);
+            if (pending) {
+                if (2 * NW == 32) {
+                    warp_sum_interleaved(rd[lane], gsf, gsff);
+                }
+                else {
+                    gsf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
+                    gsff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
+                }
             }
-            else {
-                gsf = warp_sum(lane < NW ? rd[2 * lane] : 0.0);
-                gsff = warp_sum(lane < NW ? rd[2 * lane + 1] : 0.0);
-            }
+        }
+        if (nback > 0) { // parked steps at the end of the launch: the ring must know them
+            flush_parked();
         }
         const i64 steps_now = ctl.steps + its; // (re-read: not kept in registers over the loop)
         if (status == ST_RUNNING && steps_now >= A.max_steps) {

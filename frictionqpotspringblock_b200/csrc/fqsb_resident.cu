@@ -61,10 +61,10 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
                                                    const State& S, const RunArgs& A,
                                                    cudaStream_t stream)
 {
-    const size_t smem = resident_smem(P, c);
+    const bool stop = A.mode != MODE_FIXED;
+    const size_t smem = resident_smem(P, c, stop);
     const bool full = (i64)c.B * c.T == P.N;
     const bool unit = unit_parameters(P);
-    const bool stop = A.mode != MODE_FIXED;
     const bool flow = A.flow != 0; // driven: blocks change wells all the time (inline hop path)
 #define FQSB_TRY_MODE(b, t, full_, unit_) \
     if (stop) \
