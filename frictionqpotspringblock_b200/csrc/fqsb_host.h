@@ -56,10 +56,12 @@ inline size_t resident_smem(const Par& P, const ResidentCfg& c, bool stop = true
 {
     const size_t n = (size_t)P.N;
     const size_t ghosts = P.inter < INT_LAPLACE2D ? 2 : 0;
-    size_t words = 2 * (n + ghosts) + n + (c.ysmem ? 2 * n : 0) +
+    // slip buffers: nearest-neighbour lines use the transposed slots j*T + t (B*T of them)
+    const bool nn1d = P.inter < INT_LAPLACE2D && P.inter != INT_LONGRANGE1D;
+    size_t words = 2 * (nn1d ? (size_t)c.B * c.T : n + ghosts) + n + (c.ysmem ? 2 * n : 0) +
                    (P.inter == INT_LONGRANGE1D ? n : 0) + 4 * (size_t)(c.T / 32);
     // + the parked partial sums of the stop modes ([FQSB_SKIP_K - 1][T] pairs + their warp sums)
-    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int) + n * sizeof(int) + 16 +
+    return words * 8 + (size_t)(c.T / 32) * 8 * sizeof(int) + n * sizeof(int) +
            (stop ? (size_t)(FQSB_SKIP_K - 1) * (c.T * 16 + (c.T / 32) * 16) : 0);
 }
 

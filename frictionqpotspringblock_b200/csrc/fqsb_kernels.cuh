@@ -195,11 +195,19 @@ __global__ void __launch_bounds__(T)
     constexpr bool ONE_D = INT < INT_LAPLACE2D;
     constexpr int G = ONE_D ? 1 : 0; // ghost cells on each side of a 1-D line
     constexpr int NW = T / 32;
+    // Ownership. Nearest-neighbour lines (NN1D): thread t owns the B CONSECUTIVE blocks
+    // p = t*B + j, so B - 1 of the 2B stencil neighbours are the thread's own new slips
+    // (registers) and only the two edge neighbours come from shared memory; the slips sit in
+    // shared memory transposed (slot j*T + t: conflict-free). Everything else (2-D stencils,
+    // LongRange): p = t + j*T, slot p (+ ghost), neighbours all from shared memory.
+    constexpr bool NN1D = ONE_D && INT != INT_LONGRANGE1D;
     const int N = (int)P.N;
-    const int NS = N + 2 * G;
+    const int NS = NN1D ? B * T : N + 2 * G; // slots of one slip buffer
     const int r = blockIdx.x;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
+    auto POF = [&](int j) { return NN1D ? t * B + j : t + j * T; };            // block of (t, j)
+    auto SLOT = [&](int q) { return NN1D ? (q % B) * T + q / B : q + G; };     // its slip slot
 
     Ctl& ctl = S.ctl[r];
     if (ctl.status != ST_RUNNING) {
@@ -207,18 +215,17 @@ __global__ void __launch_bounds__(T)
     }
 
     double* us = reinterpret_cast<double*>(smem_raw);          // [2][NS]
-    u64* sst = reinterpret_cast<u64*>(us + 2 * (size_t)NS);    // [N]
+    // stop modes: per-thread sums of the steps whose residual has not been reduced yet
+    // ([FQSB_SKIP_K - 1][T] pairs; 16-byte aligned: 2 NS is even)
+    double2* sback = reinterpret_cast<double2*>(us + 2 * (size_t)NS);
+    u64* sst = reinterpret_cast<u64*>(sback + (STOP ? (FQSB_SKIP_K - 1) * T : 0)); // [N]
     double* syl = reinterpret_cast<double*>(sst + N);          // [N] if YSMEM
     double* syr = syl + (YSMEM ? N : 0);                       // [N] if YSMEM
     double* spref = syr + (YSMEM ? N : 0);                     // [N] if LongRange
     double* red = spref + (INT == INT_LONGRANGE1D ? N : 0);    // [2][NW][2]
-    int* redi = reinterpret_cast<int*>(red + 4 * NW);          // [2][NW][4]
+    double* rdb = red + 4 * NW;                                // [K-1][2 NW] warp sums of parked steps
+    int* redi = reinterpret_cast<int*>(rdb + (STOP ? (FQSB_SKIP_K - 1) * 2 * NW : 0)); // [2][NW][4]
     int* sdidx = redi + 8 * NW;                                // [N] wells moved in this launch
-    // stop modes: per-thread sums of the steps whose residual has not been reduced yet
-    // [FQSB_SKIP_K - 1][T] pairs, and the per-warp sums of a backlog being evaluated
-    double2* sback = reinterpret_cast<double2*>(
-        (reinterpret_cast<uintptr_t>(sdidx + N) + 15) & ~(uintptr_t)15);
-    double* rdb = reinterpret_cast<double*>(sback + (STOP ? (FQSB_SKIP_K - 1) * T : 0)); // [K-1][2 NW]
 
     const i64 base = (i64)r * P.N;
     double v[B], a[B];
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(T)
 
 #pragma unroll
     for (int j = 0; j < B; ++j) {
-        const int p = t + j * T;
+        const int p = POF(j);
         const int pc = (FULL || p < N) ? p : N - 1;
         v[j] = S.v[base + pc];
         a[j] = S.a[base + pc];
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(T)
             ij[j] = (i << 16) | (pc - i * P.cols);
         }
         if (FULL || p < N) {
-            us[p + G] = S.u[base + p];
+            us[SLOT(p)] = S.u[base + p];
             if (YSMEM) {
                 syl[p] = S.yl[base + p];
                 syr[p] = S.yr[base + p];
@@ -270,16 +277,16 @@ __global__ void __launch_bounds__(T)
         double un[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int p = t + j * T;
+            const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
-            un[j] = uprev[pc + G] + P.dt * v[j] + c2 * a[j];
+            un[j] = uprev[SLOT(pc)] + P.dt * v[j] + c2 * a[j];
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int p = t + j * T;
+            const int p = POF(j);
             if (FULL || p < N) {
-                ucur[p + G] = un[j];
-                if (ONE_D) {
+                ucur[SLOT(p)] = un[j];
+                if (ONE_D && !NN1D) {
                     if (j == 0 && t == 0) {
                         ucur[N + 1] = un[j];
                     }
@@ -301,9 +308,9 @@ __global__ void __launch_bounds__(T)
         need = 0u;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int p = t + j * T;
+            const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
-            uc[j] = ucur[pc + G];
+            uc[j] = ucur[SLOT(pc)];
             const double l = YSMEM ? syl[pc] : yl[j];
             const double rr = YSMEM ? syr[pc] : yr[j];
             if ((FULL || p < N) && (uc[j] > rr || !(uc[j] > l))) {
@@ -314,11 +321,14 @@ __global__ void __launch_bounds__(T)
     auto phase2b = [&](const int ocur, double (&uc)[B], const unsigned need, auto accumulate,
                        double& sf, double& sff, int& hops, int& dS, int& dA) {
         const double* ucur = us + ocur;
-        auto U = [&](int q) { return ucur[q + G]; };
+        auto U = [&](int q) { return ucur[NN1D ? SLOT(q) : q + G]; };
+        // NN1D && FULL: the slots of the two edge neighbours (periodic line)
+        const int slot_left = (B - 1) * T + (t == 0 ? T - 1 : t - 1);
+        const int slot_right = t == T - 1 ? 0 : t + 1;
         double wl[B], wr[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int p = t + j * T;
+            const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
             wl[j] = YSMEM ? syl[pc] : yl[j];
             wr[j] = YSMEM ? syr[pc] : yr[j];
@@ -327,7 +337,7 @@ __global__ void __launch_bounds__(T)
 #pragma unroll
             for (int j = 0; j < B; ++j) {
                 if ((need >> j) & 1u) {
-                    const int p = t + j * T;
+                    const int p = POF(j);
                     double l = wl[j], rr = wr[j];
                     i64 i_before = 0;
                     int moved = 0;
@@ -366,11 +376,23 @@ __global__ void __launch_bounds__(T)
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int p = t + j * T;
+            const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
             const int qi = ONE_D ? 0 : (ij[ONE_D ? 0 : j] >> 16);
             const int qj = ONE_D ? 0 : (ij[ONE_D ? 0 : j] & 0xffff);
-            double fi = f_interactions<INT, !ONE_D, UNIT>(P, U, spref, pc, qi, qj, uc[j]);
+            double fi;
+            if (NN1D && FULL) {
+                const double ul = j > 0 ? uc[j > 0 ? j - 1 : 0] : ucur[slot_left];
+                const double ur = j < B - 1 ? uc[j < B - 1 ? j + 1 : 0] : ucur[slot_right];
+                auto UE = [&](int q) { return q < pc ? ul : ur; };
+                fi = f_interactions<INT, false, UNIT>(P, UE, spref, pc, qi, qj, uc[j]);
+            }
+            else if (NN1D) { // ragged line: periodic indices resolved per block
+                fi = f_interactions<INT, true, UNIT>(P, U, spref, pc, qi, qj, uc[j]);
+            }
+            else {
+                fi = f_interactions<INT, !ONE_D, UNIT>(P, U, spref, pc, qi, qj, uc[j]);
+            }
             double fp = f_potential<POT, UNIT>(P, uc[j], wl[j], wr[j]);
             double ff = P.k_frame * (uf - uc[j]);
             double F = ff + fp + fi;
@@ -679,10 +701,10 @@ __global__ void __launch_bounds__(T)
     bool nan = false;
 #pragma unroll
     for (int j = 0; j < B; ++j) {
-        const int p = t + j * T;
+        const int p = POF(j);
         if (p < N) {
             const bool q = status == ST_CONVERGED;
-            const double uu = ufin[p + G];
+            const double uu = ufin[SLOT(p)];
             S.u[base + p] = uu;
             S.v[base + p] = q ? 0.0 : v[j];
             S.a[base + p] = q ? 0.0 : a[j];
