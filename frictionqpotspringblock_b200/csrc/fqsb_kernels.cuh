@@ -271,10 +271,11 @@ __global__ void __launch_bounds__(T)
     // floating-point chains of a thread interleave.
 
     // ---- positions (detail.h:1549): purely local; ghosts keep the line periodic
-    auto phase1 = [&](const int oprev, const int ocur) {
+    // (the new slips also stay in the caller's registers: the well test and the forces of the
+    // thread's own blocks need no reload after the barrier)
+    auto phase1 = [&](const int oprev, const int ocur, double (&un)[B]) {
         const double* uprev = us + oprev;
         double* ucur = us + ocur;
-        double un[B];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = POF(j);
@@ -303,14 +304,12 @@ __global__ void __launch_bounds__(T)
     // phase 2a: the new positions of this thread's blocks and the well test -- no side effects,
     // so the stop modes run it BEFORE the decision about the previous step is known (its
     // shuffle chain is still in flight then)
-    auto phase2a = [&](const int ocur, double (&uc)[B], unsigned& need) {
-        const double* ucur = us + ocur;
+    auto phase2a = [&](const double (&uc)[B], unsigned& need) {
         need = 0u;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
-            uc[j] = ucur[SLOT(pc)];
             const double l = YSMEM ? syl[pc] : yl[j];
             const double rr = YSMEM ? syr[pc] : yr[j];
             if ((FULL || p < N) && (uc[j] > rr || !(uc[j] > l))) {
@@ -406,11 +405,10 @@ __global__ void __launch_bounds__(T)
             }
         }
     };
-    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
-                      int& dS, int& dA) {
-        double uc[B];
+    auto phase2 = [&](const int ocur, double (&uc)[B], auto accumulate, double& sf, double& sff,
+                      int& hops, int& dS, int& dA) {
         unsigned need;
-        phase2a(ocur, uc, need);
+        phase2a(uc, need);
         phase2b(ocur, uc, need, accumulate, sf, sff, hops, dS, dA);
     };
 
@@ -427,9 +425,10 @@ __global__ void __launch_bounds__(T)
             if (A.flow) {
                 uf += A.v_frame * P.dt; // detail.h:1642
             }
-            phase1(prev * NS, (prev ^ 1) * NS);
+            double uc[B];
+            phase1(prev * NS, (prev ^ 1) * NS, uc);
             __syncthreads();
-            phase2((prev ^ 1) * NS, std::false_type{}, sf, sff, hops, dS, dA);
+            phase2((prev ^ 1) * NS, uc, std::false_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
         }
         steps_done += nloop;
@@ -522,15 +521,15 @@ __global__ void __launch_bounds__(T)
             }
             nback = 0;
         };
+        double uc[B]; // slips of the step being computed (from phase 1, in registers)
         if (nl > 0) {
-            phase1(prev * NS, (prev ^ 1) * NS);
+            phase1(prev * NS, (prev ^ 1) * NS, uc);
             __syncthreads();
         }
         for (int it = 0;; ++it) {
-            double uc[B];
             unsigned need = 0u;
             if (it < nl) {
-                phase2a((prev ^ 1) * NS, uc, need);
+                phase2a(uc, need);
             }
             if (it > 0) {
                 its = it;
@@ -652,7 +651,7 @@ __global__ void __launch_bounds__(T)
                     }
                 }
             }
-            phase1(prev * NS, (prev ^ 1) * NS); // speculative
+            phase1(prev * NS, (prev ^ 1) * NS, uc); // speculative
             __syncthreads();
             // issue the reduction of this step's partials; consumed in the next iteration
             if (pending) {
