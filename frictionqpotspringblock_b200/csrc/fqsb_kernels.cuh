@@ -179,6 +179,10 @@ static __device__ __noinline__ int hop_global(const Par& P, double un, double* y
     return moved;
 }
 
+#ifndef FQSB_UREG
+#define FQSB_UREG 1
+#endif
+
 // STOP = false: timeSteps / flowSteps only (MODE_FIXED); STOP = true: the stop modes. Two
 // instantiations so that the bookkeeping of the stop modes costs the fixed-step loop no registers.
 // HOPINL = true: the common well change (one well to the right on a `random` landscape) is taken
@@ -273,6 +277,11 @@ __global__ void __launch_bounds__(T)
     // ---- positions (detail.h:1549): purely local; ghosts keep the line periodic
     // (the new slips also stay in the caller's registers: the well test and the forces of the
     // thread's own blocks need no reload after the barrier)
+    // UREG (full nearest-neighbour lines): a thread carries the slips of its blocks in registers
+    // from step to step. The fixed-step loop then only publishes the two edge blocks of a thread
+    // for its neighbours; the stop modes still store all of them (a stop falls back to the slips
+    // of the step before, which are only in shared memory by then).
+    constexpr bool UREG = FQSB_UREG && NN1D && FULL;
     auto phase1 = [&](const int oprev, const int ocur, double (&un)[B]) {
         const double* uprev = us + oprev;
         double* ucur = us + ocur;
@@ -280,11 +289,14 @@ __global__ void __launch_bounds__(T)
         for (int j = 0; j < B; ++j) {
             const int p = POF(j);
             const int pc = (FULL || p < N) ? p : N - 1;
-            un[j] = uprev[SLOT(pc)] + P.dt * v[j] + c2 * a[j];
+            un[j] = (UREG ? un[j] : uprev[SLOT(pc)]) + P.dt * v[j] + c2 * a[j];
         }
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int p = POF(j);
+            if (UREG && !STOP && j != 0 && j != B - 1) {
+                continue;
+            }
             if (FULL || p < N) {
                 ucur[SLOT(p)] = un[j];
                 if (ONE_D && !NN1D) {
@@ -421,15 +433,27 @@ __global__ void __launch_bounds__(T)
         // timeSteps / flowSteps: no stop test, one barrier per step
         double sf = 0.0, sff = 0.0;
         int hops = 0, dS = 0, dA = 0;
+        double uc[B];
+        if (UREG) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                uc[j] = us[prev * NS + SLOT(POF(j))];
+            }
+        }
         for (i64 it = 0; it < nloop; ++it) {
             if (A.flow) {
                 uf += A.v_frame * P.dt; // detail.h:1642
             }
-            double uc[B];
             phase1(prev * NS, (prev ^ 1) * NS, uc);
             __syncthreads();
             phase2((prev ^ 1) * NS, uc, std::false_type{}, sf, sff, hops, dS, dA);
             prev ^= 1;
+        }
+        if (UREG) { // (the write-back below reads the slips from shared memory)
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                us[prev * NS + SLOT(POF(j))] = uc[j];
+            }
         }
         steps_done += nloop;
         if (steps_done >= A.max_steps) {
@@ -522,6 +546,12 @@ __global__ void __launch_bounds__(T)
             nback = 0;
         };
         double uc[B]; // slips of the step being computed (from phase 1, in registers)
+        if (UREG) {
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                uc[j] = us[prev * NS + SLOT(POF(j))];
+            }
+        }
         if (nl > 0) {
             phase1(prev * NS, (prev ^ 1) * NS, uc);
             __syncthreads();
