@@ -179,6 +179,9 @@ static __device__ __noinline__ int hop_global(const Par& P, double un, double* y
     return moved;
 }
 
+#ifndef FQSB_YMID
+#define FQSB_YMID 1
+#endif
 #ifndef FQSB_UREG
 #define FQSB_UREG 1
 #endif
@@ -234,6 +237,11 @@ __global__ void __launch_bounds__(T)
     const i64 base = (i64)r * P.N;
     double v[B], a[B];
     double yl[YSMEM ? 1 : B], yr[YSMEM ? 1 : B];
+    // Cuspy potential: the midpoint of the well, 0.5 * (y_l + y_r), only changes with the well;
+    // kept beside it, the force costs one subtraction instead of three operations (same bits).
+    // Measured: +2.6 % in the stop modes, -0.7 % in the fixed-step loop (register pressure), hence STOP
+    constexpr bool YMID = FQSB_YMID && POT == POT_CUSPY && !YSMEM && STOP;
+    double ym[YMID ? B : 1];
     int ij[ONE_D ? 1 : B];
 
 #pragma unroll
@@ -245,6 +253,9 @@ __global__ void __launch_bounds__(T)
         if (!YSMEM) {
             yl[j] = S.yl[base + pc];
             yr[j] = S.yr[base + pc];
+            if (YMID) {
+                ym[j] = 0.5 * (yl[j] + yr[j]);
+            }
         }
         if (!ONE_D) {
             int i = pc / P.cols;
@@ -379,6 +390,9 @@ __global__ void __launch_bounds__(T)
                     else {
                         yl[j] = l;
                         yr[j] = rr;
+                        if (YMID) {
+                            ym[j] = 0.5 * (l + rr);
+                        }
                     }
                     hops += moved != 0;
                     track_hop(A, base + p, i_before, moved, dS, dA);
@@ -404,7 +418,13 @@ __global__ void __launch_bounds__(T)
             else {
                 fi = f_interactions<INT, !ONE_D, UNIT>(P, U, spref, pc, qi, qj, uc[j]);
             }
-            double fp = f_potential<POT, UNIT>(P, uc[j], wl[j], wr[j]);
+            double fp;
+            if (YMID) { // detail.h:164-169
+                fp = UNIT ? (ym[j] - uc[j]) : (ym[j] - uc[j]) * P.mu;
+            }
+            else {
+                fp = f_potential<POT, UNIT>(P, uc[j], wl[j], wr[j]);
+            }
             double ff = P.k_frame * (uf - uc[j]);
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
