@@ -35,7 +35,13 @@ if str(ROOT) not in sys.path:
 N_BLOCKS = 4096
 R_CONFIG = 16384  # realisations of BASELINE configs[1]
 ALGO_BYTES_PER_UPDATE = 64.0  # u,v,a read + write (48) + y_left,y_right read (16); SURVEY 8(d)
-FP64_INSTR_PER_UPDATE = 32    # 30 DADD/DMUL (reference's evaluation order, no FMA) + 2 DSETP
+# FP64-pipe instructions per block-update of k_resident<Cuspy,Laplace1d,unit>, counted by ncu
+# (profiles/r2d_ncu_resident_fixed.txt: 145 DADD + 84 DMUL + 16 DSETP per warp-step of 8 blocks;
+# the reference's evaluation order, no FMA contraction)
+FP64_INSTR_PER_UPDATE = 245.0 / 8.0
+# DADD/DMUL issue rate a B200 SM sustains in a register-only loop (tools/fp64_peak.cu, measured:
+# 1.934 of the nominal 2.0 warp-instructions per SM per clock)
+FP64_PRACTICAL_ISSUE = 1.934 / 2.0
 METRIC = "block_updates_per_s"
 UNIT = "block-updates/s"
 
@@ -518,7 +524,7 @@ def main():
 
     # ---- roofline of the dominant kernel (k_resident). Its state never leaves the chip within a
     #      launch, so HBM is not its roof: it is bound by the FP64 pipe's ISSUE rate (64 lanes per
-    #      SM per clock; 32 FP64-pipe instructions per block-update without FMA). The algorithmic
+    #      SM per clock; 30.6 FP64-pipe instructions per block-update without FMA). The algorithmic
     #      HBM figure of SURVEY 8(d) is the sub-entry "hbm".
     peak, peak_src = measured_peaks()
     kernel_avg = kernel_sec / max(1, kernel_launches)
@@ -534,6 +540,9 @@ def main():
         "frac": fp64_rate / fp64_peak,
         "peak_source": "148 SMs x 64 FP64 lanes x SM clock sampled during the timed region",
         "instr_per_block_update": FP64_INSTR_PER_UPDATE,
+        "frac_of_measured_issue_peak": fp64_rate / (fp64_peak * FP64_PRACTICAL_ISSUE),
+        "measured_issue_peak_source": "tools/fp64_peak.cu: 1.934 of 2.0 warp-instr/SM/clock "
+                                      "(DMUL+DADD chains, 512 threads/SM)",
         "launch_ms": 1e3 * kernel_avg, "traffic": None,
         "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": peak, "unit": "GB/s",
                 "frac": hbm_ach / peak, "peak_source": peak_src,

@@ -66,14 +66,18 @@ __global__ void __launch_bounds__(FQSB_BK_T)
     const int cnt = N - own0 < K.own ? N - own0 : K.own;
     const int H = K.H;
     const int L = cnt + 2 * H; // local blocks q = 0..L-1 are global blocks own0 - H + q (mod N)
-    const int NS = LMAX + 2;   // slip buffer stride: one ghost cell on each side
     auto GP = [&](int q) {
         int p = own0 - H + q;
         return p < 0 ? p + N : (p >= N ? p - N : p);
     };
 
-    double* us = reinterpret_cast<double*>(smem_raw);          // [2][NS]
-    u64* sst = reinterpret_cast<u64*>(us + 2 * (size_t)NS);    // [LMAX]
+    // On-chip layout: thread t holds the B CONSECUTIVE local blocks q = t*B + j with all their
+    // state (u, v, a, wells) in registers, so B - 1 of the 2B stencil neighbours are the thread's
+    // own registers; per step a thread only publishes its first and last slip for its two
+    // neighbouring threads (double-buffered edge arrays) and reads one slip from each of them.
+    double* eL = reinterpret_cast<double*>(smem_raw);          // [2][T + 1] first slip of a thread
+    double* eR = eL + 2 * (T + 1);                             // [2][T + 1] last slip of a thread
+    u64* sst = reinterpret_cast<u64*>(eR + 2 * (T + 1));       // [LMAX]
     double* slog = reinterpret_cast<double*>(sst + LMAX);      // [MAXSTEPS][NW][2]
     int* ilog = reinterpret_cast<int*>(slog + FQSB_BK_MAXSTEPS * NW * 2); // [MAXSTEPS][NW][4]
     int* sdidx = ilog + FQSB_BK_MAXSTEPS * NW * 4;             // [LMAX]
@@ -88,23 +92,27 @@ __global__ void __launch_bounds__(FQSB_BK_T)
     const u64* __restrict__ rngi = (flip ? K.rng2 : S.rng) + base;
     double uf = (flip ? K.uf2 : S.u_frame)[r];
 
-    double v[B], a[B], yl[B], yr[B];
+    double u[B], v[B], a[B], yl[B], yr[B];
     // ownmask: blocks this tile writes back; summask: those of them that enter the sums (a member
-    // of a slab-decomposed line leaves out the halo copies of its neighbours' blocks)
-    unsigned ownmask = 0u, summask = 0u;
+    // of a slab-decomposed line leaves out the halo copies of its neighbours' blocks);
+    // ghostmask: blocks whose right neighbour is the frozen cell just outside the tile
+    unsigned ownmask = 0u, summask = 0u, ghostmask = 0u;
 #pragma unroll
     for (int j = 0; j < B; ++j) {
-        const int q = t + j * T;
+        const int q = t * B + j;
         const int qc = q < L ? q : L - 1;
         const int gp = GP(qc);
+        u[j] = ui[gp];
         v[j] = vi[gp];
         a[j] = ai[gp];
         yl[j] = yli[gp];
         yr[j] = yri[gp];
         if (q < L) {
-            us[q + 1] = ui[gp];
             sst[q] = rngi[gp];
             sdidx[q] = 0;
+        }
+        if (q + 1 >= L) {
+            ghostmask |= 1u << j;
         }
         if (q >= H && q < H + cnt) {
             ownmask |= 1u << j;
@@ -115,51 +123,30 @@ __global__ void __launch_bounds__(FQSB_BK_T)
     }
     // the cells just outside the tile stay frozen at their input value: the error this makes
     // enters at the outermost halo block and moves inwards one block per step
-    if (t < 2) {
-        const double g = ui[GP(t == 0 ? -1 : L)];
-        const int cell = t == 0 ? 0 : L + 1;
-        us[cell] = g;
-        us[NS + cell] = g;
-    }
-    __syncthreads();
+    const double ghost_l = ui[GP(-1)], ghost_r = ui[GP(L)];
 
     const double c2 = 0.5 * P.dt * P.dt; // (0.5*dt)*dt, detail.h:1549
     int underflow = 0;
-    int prev = 0;
+    int par = 0;
 
-    // ---- positions (detail.h:1549)
-    auto phase1 = [&](const int oprev, const int ocur) {
-        const double* uprev = us + oprev;
-        double* ucur = us + ocur;
-        double un[B];
+    // ---- positions (detail.h:1549); the edge slips go to the neighbouring threads
+    auto phase1 = [&](const int pb) {
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int q = t + j * T;
-            const int qc = q < L ? q : L - 1;
-            un[j] = uprev[qc + 1] + P.dt * v[j] + c2 * a[j];
+            u[j] = u[j] + P.dt * v[j] + c2 * a[j];
         }
-#pragma unroll
-        for (int j = 0; j < B; ++j) {
-            const int q = t + j * T;
-            if (q < L) {
-                ucur[q + 1] = un[j];
-            }
-        }
+        eL[pb * (T + 1) + t] = u[0];
+        eR[pb * (T + 1) + t] = u[B - 1];
     };
 
     // ---- well search (detail.h:144), forces (detail.h:1380-1386), Verlet tail (1552-1565)
-    auto phase2 = [&](const int ocur, auto accumulate, double& sf, double& sff, int& hops,
+    auto phase2 = [&](const int pb, auto accumulate, double& sf, double& sff, int& hops,
                       int& dS, int& dA) {
-        const double* ucur = us + ocur;
-        auto U = [&](int q) { return ucur[q + 1]; };
-        double uc[B];
         unsigned need = 0u;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int q = t + j * T;
-            const int qc = q < L ? q : L - 1;
-            uc[j] = ucur[qc + 1];
-            if (q < L && (uc[j] > yr[j] || !(uc[j] > yl[j]))) {
+            const int q = t * B + j;
+            if (q < L && (u[j] > yr[j] || !(u[j] > yl[j]))) {
                 need |= 1u << j;
             }
         }
@@ -167,17 +154,17 @@ __global__ void __launch_bounds__(FQSB_BK_T)
 #pragma unroll
             for (int j = 0; j < B; ++j) {
                 if ((need >> j) & 1u) {
-                    const int q = t + j * T;
+                    const int q = t * B + j;
                     const int gp = GP(q);
                     int uflag = 0;
                     double l = yl[j], rr = yr[j];
                     const int d0 = sdidx[q];
                     int moved = 0;
                     // inline fast path: one well to the right on a `random` landscape
-                    if (P.dist == DIST_RANDOM && uc[j] > rr) {
+                    if (P.dist == DIST_RANDOM && u[j] > rr) {
                         const u64 st = sst[q];
                         const double r2 = rr + (pcg_double(st) * P.dpar[0] + P.dpar[1]);
-                        if (!(uc[j] > r2)) {
+                        if (!(u[j] > r2)) {
                             sst[q] = pcg_next(st);
                             l = rr;
                             rr = r2;
@@ -185,7 +172,7 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                         }
                     }
                     if (moved == 0) {
-                        moved = hop_blocked(P, uc[j], &l, &rr, sst + q, idxi + gp, d0, &uflag);
+                        moved = hop_blocked(P, u[j], &l, &rr, sst + q, idxi + gp, d0, &uflag);
                     }
                     yl[j] = l;
                     yr[j] = rr;
@@ -202,13 +189,20 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                 }
             }
         }
+        // slips of the two neighbouring threads (thread T-1 never reads beyond the arrays: its
+        // last block is always the last of the tile or beyond)
+        const double from_left = t == 0 ? ghost_l : eR[pb * (T + 1) + t - 1];
+        const double from_right = eL[pb * (T + 1) + t + 1];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int q = t + j * T;
-            const int qc = q < L ? q : L - 1;
-            double fi = f_interactions<INT, false, UNIT>(P, U, nullptr, qc, 0, 0, uc[j]);
-            double fp = f_potential<POT, UNIT>(P, uc[j], yl[j], yr[j]);
-            double ff = P.k_frame * (uf - uc[j]);
+            const int q = t * B + j;
+            const double ul = j > 0 ? u[j > 0 ? j - 1 : 0] : from_left;
+            const double ur = ((ghostmask >> j) & 1u) ? ghost_r
+                                                      : (j < B - 1 ? u[j < B - 1 ? j + 1 : 0] : from_right);
+            auto UE = [&](int qq) { return qq < q ? ul : ur; };
+            double fi = f_interactions<INT, false, UNIT>(P, UE, nullptr, q, 0, 0, u[j]);
+            double fp = f_potential<POT, UNIT>(P, u[j], yl[j], yr[j]);
+            double ff = P.k_frame * (uf - u[j]);
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
             if (decltype(accumulate)::value) {
@@ -226,20 +220,20 @@ __global__ void __launch_bounds__(FQSB_BK_T)
             if (A.flow) {
                 uf += A.v_frame * P.dt; // detail.h:1642
             }
-            phase1(prev * NS, (prev ^ 1) * NS);
+            phase1(par);
             __syncthreads();
-            phase2((prev ^ 1) * NS, std::false_type{}, sf, sff, hops, dS, dA);
-            prev ^= 1;
+            phase2(par, std::false_type{}, sf, sff, hops, dS, dA);
+            par ^= 1;
         }
     }
     else {
         for (int it = 0; it < nsteps; ++it) {
             double sf = 0.0, sff = 0.0;
             int hops = 0, dS = 0, dA = 0;
-            phase1(prev * NS, (prev ^ 1) * NS);
+            phase1(par);
             __syncthreads();
-            phase2((prev ^ 1) * NS, std::true_type{}, sf, sff, hops, dS, dA);
-            prev ^= 1;
+            phase2(par, std::true_type{}, sf, sff, hops, dS, dA);
+            par ^= 1;
             // per-warp partials of this step; nobody waits for them before the launch ends
             warp_sum2(sf, sff);
             hops = __reduce_add_sync(0xffffffffu, hops);
@@ -266,14 +260,13 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         double* __restrict__ yro = (flip ? S.yr : K.yr2) + base;
         i64* __restrict__ idxo = (flip ? S.idx : K.idx2) + base;
         u64* __restrict__ rngo = (flip ? S.rng : K.rng2) + base;
-        const double* ufin = us + (size_t)prev * NS;
         bool nan = false;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             if ((ownmask >> j) & 1u) {
-                const int q = t + j * T;
+                const int q = t * B + j;
                 const int gp = own0 - H + q; // owned: no wrap
-                const double uu = ufin[q + 1];
+                const double uu = u[j];
                 uo[gp] = uu;
                 vo[gp] = v[j];
                 ao[gp] = a[j];

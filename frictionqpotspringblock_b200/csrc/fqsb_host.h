@@ -91,7 +91,8 @@ BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint);
 inline size_t blocked_smem(int B)
 {
     const size_t lmax = (size_t)B * FQSB_BK_T, nw = FQSB_BK_T / 32;
-    return 2 * (lmax + 2) * 8 + lmax * 8 + FQSB_BK_MAXSTEPS * nw * (2 * 8 + 4 * 4) + lmax * 4;
+    // edge slips [2][2][T + 1], pcg32 states, per-step logs, well-move counters
+    return 4 * ((size_t)FQSB_BK_T + 1) * 8 + lmax * 8 + FQSB_BK_MAXSTEPS * nw * (2 * 8 + 4 * 4) + lmax * 4;
 }
 cudaError_t launch_blocked(const BlockedPlan& plan, const Par& P, const State& S,
                            const RunArgs& A, const BlockedArgs& K, cudaStream_t stream);
