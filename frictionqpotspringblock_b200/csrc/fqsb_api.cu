@@ -413,6 +413,7 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     P.N = (i64)P.rows * P.cols;
     P.R = par->nrealisations > 0 ? par->nrealisations : 1;
     P.consumes = par->distribution != FQSB_DIST_DELTA;
+    P.fma = (par->kernel & FQSB_KERNEL_FMA) ? 1 : 0;
     P.m = par->m;
     P.inv_m = 1.0 / par->m; // detail.h:1110
     P.eta = par->eta;

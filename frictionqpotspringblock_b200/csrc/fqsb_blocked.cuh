@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(FQSB_BK_T)
                     // inline fast path: one well to the right on a `random` landscape
                     if (P.dist == DIST_RANDOM && u[j] > rr) {
                         const u64 st = sst[q];
-                        const double r2 = rr + (pcg_double(st) * P.dpar[0] + P.dpar[1]);
+                        const double r2 = FQSB_XADD(
+                            rr, FQSB_XADD(FQSB_XMUL(pcg_double(st), P.dpar[0]), P.dpar[1]));
                         if (!(u[j] > r2)) {
                             sst[q] = pcg_next(st);
                             l = rr;

@@ -27,6 +27,9 @@ struct Par {
     // rows per CTA of the 2-D row-marching kernels (Verlet step / no-passing sweep), chosen per
     // handle so that the grid fills whole waves of resident CTAs (plan_band_rows)
     int s2_ty, s2_ty_np;
+    // opt-in contracted arithmetic (fqsb_params.kernel bit 7): the resident Verlet kernels built
+    // with FMA contraction (fqsb_resident.cu, FQSB_FMA_BUILD). Not bit-identical to the oracle.
+    int fma;
     i64 N; // blocks per realisation
     i64 R; // realisations
     double m, inv_m, eta, mu, kappa, k1, k2, k_frame, dt;
@@ -410,6 +413,18 @@ static __device__ __noinline__ double normal_from_draw_dev(double r, double mu, 
 
 #endif // FQSB_SLOW_DISTS
 
+// ---- arithmetic of the yield landscape: never contracted ------------------------------------
+// The landscape is part of the system's definition (pcg32 stream -> spacings -> cumulative sum),
+// so its multiply-adds keep their two roundings even in the translation units that are built with
+// FMA contraction for the dynamics (FQSB_FMA_BUILD).
+#ifdef __CUDA_ARCH__
+#define FQSB_XMUL(a, b) __dmul_rn((a), (b))
+#define FQSB_XADD(a, b) __dadd_rn((a), (b))
+#else
+#define FQSB_XMUL(a, b) ((a) * (b))
+#define FQSB_XADD(a, b) ((a) + (b))
+#endif
+
 // ---- distributions -> yield spacing ------------------------------------
 enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DIST_GAMMA = 4,
        DIST_PARETO = 5, DIST_WEIBULL = 6, DIST_NORMAL = 7 };
@@ -417,25 +432,25 @@ enum { DIST_RANDOM = 0, DIST_DELTA = 1, DIST_EXPONENTIAL = 2, DIST_POWER = 3, DI
 __host__ __device__ __forceinline__ double spacing_from_draw(const Par& P, double r)
 {
     if (P.dist == DIST_RANDOM) {
-        return r * P.dpar[0] + P.dpar[1];
+        return FQSB_XADD(FQSB_XMUL(r, P.dpar[0]), P.dpar[1]);
     }
     switch (P.dist) {
     case DIST_DELTA:
         return P.dpar[0] + P.dpar[1];
     case DIST_EXPONENTIAL:
-        return -log(1.0 - r) * P.dpar[0] + P.dpar[1];
+        return FQSB_XADD(FQSB_XMUL(-log(1.0 - r), P.dpar[0]), P.dpar[1]);
     case DIST_POWER:
         return pow(1.0 - r, 1.0 / (P.dpar[0] + 1.0)) + P.dpar[1];
     case DIST_PARETO:
-        return P.dpar[1] * pow(1.0 - r, -1.0 / P.dpar[0]) + P.dpar[2];
+        return FQSB_XADD(FQSB_XMUL(P.dpar[1], pow(1.0 - r, -1.0 / P.dpar[0])), P.dpar[2]);
 #if defined(__CUDA_ARCH__) && defined(FQSB_SLOW_DISTS)
     case DIST_NORMAL: // normal(mu, sigma) + offset
         return normal_from_draw_dev(r, P.dpar[0], P.dpar[1]) + P.dpar[2];
     case DIST_GAMMA: // gamma(k, theta) + offset
-        return P.dpar[1] * gamma_p_inv_dev(P.dpar[0], r) + P.dpar[2];
+        return FQSB_XADD(FQSB_XMUL(P.dpar[1], gamma_p_inv_dev(P.dpar[0], r)), P.dpar[2]);
 #endif
     default: // DIST_WEIBULL
-        return P.dpar[1] * pow(-log(1.0 - r), 1.0 / P.dpar[0]) + P.dpar[2];
+        return FQSB_XADD(FQSB_XMUL(P.dpar[1], pow(-log(1.0 - r), 1.0 / P.dpar[0])), P.dpar[2]);
     }
 }
 
@@ -473,7 +488,7 @@ __host__ __device__ __forceinline__ int well_align_lazy(const Par& P, double u, 
             st = pcg_next(st);
         }
         yl = yr;
-        yr = yr + d;
+        yr = FQSB_XADD(yr, d);
         ++moved;
     }
     if (!(u > yl)) {
@@ -491,7 +506,7 @@ __host__ __device__ __forceinline__ int well_align_lazy(const Par& P, double u, 
             }
             double d = spacing_peek(P, sb);
             yr = yl;
-            yl = yl - d;
+            yl = FQSB_XADD(yl, -d);
             --moved;
         } while (!(u > yl));
     }

@@ -192,8 +192,10 @@ static __device__ __noinline__ int hop_global(const Par& P, double un, double* y
 // inline. It pays whenever blocks change wells regularly (flowSteps, avalanches inside the stop
 // modes: +60 % at 0.07 well changes per block-update) but costs the quiescent fixed-step loop
 // ~5 %, so timeSteps() launches the variant without it.
+// FMA only names the instantiations of the translation units that are compiled with FMA
+// contraction (-fmad=true, FQSB_FMA_BUILD): same source, contracted by the compiler.
 template <int POT, int INT, int B, int T, bool YSMEM, bool FULL, bool UNIT, bool STOP,
-          bool HOPINL = STOP>
+          bool HOPINL = STOP, bool FMA = false>
 __global__ void __launch_bounds__(T)
     k_resident(const __grid_constant__ Par P, const __grid_constant__ State S,
                const __grid_constant__ RunArgs A)
@@ -368,7 +370,8 @@ __global__ void __launch_bounds__(T)
                     // global memory; everything else goes out of line.
                     if (HOPINL && P.dist == DIST_RANDOM && !A.track && uc[j] > rr) {
                         const u64 st = sst[p];
-                        const double r2 = rr + (pcg_double(st) * P.dpar[0] + P.dpar[1]);
+                        const double r2 = FQSB_XADD(
+                            rr, FQSB_XADD(FQSB_XMUL(pcg_double(st), P.dpar[0]), P.dpar[1]));
                         if (!(uc[j] > r2)) {
                             sst[p] = pcg_next(st);
                             sdidx[p] += 1;

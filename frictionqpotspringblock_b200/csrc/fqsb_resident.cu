@@ -8,6 +8,19 @@
 #error "compile with -DFQSB_COMBO=<0..9>"
 #endif
 
+#define FQSB_CAT2(a, b) a##b
+#define FQSB_CAT(a, b) FQSB_CAT2(a, b)
+
+// FQSB_FMA_BUILD: the same kernels compiled with -fmad=true (the opt-in "contracted arithmetic" of
+// fqsb_params.kernel bit 7): distinct instantiations (template flag FMA) behind launch_resident_fma_<k>
+#ifdef FQSB_FMA_BUILD
+#define C_FMA true
+#define FQSB_LAUNCH_NAME(k) FQSB_CAT(launch_resident_fma_, k)
+#else
+#define C_FMA false
+#define FQSB_LAUNCH_NAME(k) FQSB_CAT(launch_resident_, k)
+#endif
+
 namespace fqsb {
 
 #if FQSB_COMBO == 0
@@ -54,12 +67,8 @@ static cudaError_t launch(K kernel, int T, size_t smem, const Par& P, const Stat
 
 #if FQSB_COMBO < 9
 
-#define FQSB_CAT2(a, b) a##b
-#define FQSB_CAT(a, b) FQSB_CAT2(a, b)
-
-cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const Par& P,
-                                                   const State& S, const RunArgs& A,
-                                                   cudaStream_t stream)
+cudaError_t FQSB_LAUNCH_NAME(FQSB_COMBO)(const ResidentCfg& c, const Par& P, const State& S,
+                                         const RunArgs& A, cudaStream_t stream)
 {
     const bool stop = A.mode != MODE_FIXED;
     const size_t smem = resident_smem(P, c, stop);
@@ -68,10 +77,10 @@ cudaError_t FQSB_CAT(launch_resident_, FQSB_COMBO)(const ResidentCfg& c, const P
     const bool flow = A.flow != 0; // driven: blocks change wells all the time (inline hop path)
 #define FQSB_TRY_MODE(b, t, full_, unit_) \
     if (stop) \
-        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, true, true>, t, smem, P, S, A, stream); \
+        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, true, true, C_FMA>, t, smem, P, S, A, stream); \
     if (flow) \
-        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, true>, t, smem, P, S, A, stream); \
-    return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, false>, t, smem, P, S, A, stream);
+        return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, true, C_FMA>, t, smem, P, S, A, stream); \
+    return launch(k_resident<C_POT, C_INT, b, t, false, full_, unit_, false, false, C_FMA>, t, smem, P, S, A, stream);
 #define FQSB_TRY_CFG(b, t) \
     if (c.B == b && c.T == t) { \
         if (full && unit) { \

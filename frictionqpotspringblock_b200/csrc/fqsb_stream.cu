@@ -20,6 +20,7 @@ static bool slow_dist(const Par& P) { return P.dist == DIST_GAMMA || P.dist == D
                                     const RunArgs&, cudaStream_t);
 FQSB_DECL(0) FQSB_DECL(1) FQSB_DECL(2) FQSB_DECL(3) FQSB_DECL(4)
 FQSB_DECL(5) FQSB_DECL(6) FQSB_DECL(7) FQSB_DECL(8)
+FQSB_DECL(fma_0) FQSB_DECL(fma_1) FQSB_DECL(fma_2)
 
 // the systems of Line1d.h:112-677 and Line2d.h:77-162 (+ interaction-free, Particles.h)
 static int combo_of(int pot, int inter)
@@ -69,6 +70,13 @@ static cudaError_t ensure_dynamic_smem(K kernel, size_t smem, bool (&done)[64])
 cudaError_t launch_resident(const ResidentCfg& c, const Par& P, const State& S,
                             const RunArgs& A, cudaStream_t stream)
 {
+    if (P.fma) { // opt-in contracted arithmetic: Cuspy lines with nearest-neighbour stencils
+        switch (combo_of(P.pot, P.inter)) {
+        case 0: return launch_resident_fma_0(c, P, S, A, stream);
+        case 1: return launch_resident_fma_1(c, P, S, A, stream);
+        case 2: return launch_resident_fma_2(c, P, S, A, stream);
+        }
+    }
     switch (combo_of(P.pot, P.inter)) {
     case 0: return launch_resident_0(c, P, S, A, stream);
     case 1: return launch_resident_1(c, P, S, A, stream);

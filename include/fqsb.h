@@ -102,12 +102,20 @@ typedef struct {
     int32_t kernel;        /* low 4 bits: 0 auto, 1 force resident (one CTA per realisation), 2 force
                               streaming (one step per launch), 3 force the temporally blocked tiles
                               (1-D nearest-neighbour lines; bits 8..15 steps per launch, bits 16..31
-                              owned blocks per tile, 0 = planner's choice); bits 4..7 resident variant */
+                              owned blocks per tile, 0 = planner's choice); bits 4..6 resident variant;
+                              bit 7 (FQSB_KERNEL_FMA): opt in to the resident kernels built with FMA
+                              contraction (Cuspy lines with Laplace / Quartic / QuarticGradient
+                              interactions; ~1.4x fewer FP64 instructions per step). The yield
+                              landscape stays exact; u, v, a then agree with the reference to
+                              rounding (~1e-13 relative after 1000 steps) instead of bit for bit.
+                              Default off: bit-identical arithmetic. */
     /* slab decomposition: local block p is global block (seed_first + p) mod seed_period and draws
      * the global block's pcg32 stream; seed_period == 0 disables the mapping */
     int64_t seed_first;
     int64_t seed_period;
 } fqsb_params;
+
+#define FQSB_KERNEL_FMA 0x80
 
 typedef struct fqsb_system fqsb_system;
 
