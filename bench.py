@@ -378,6 +378,7 @@ def main():
     ap.add_argument("--no-stream", action="store_true")
     ap.add_argument("--no-events", action="store_true")
     ap.add_argument("--no-driven", action="store_true")
+    ap.add_argument("--no-contracted", action="store_true")
     ap.add_argument("--no-slab", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short device-timed lines of BASELINE configs #3-#5 and the "
@@ -587,9 +588,44 @@ def main():
                   "blocks_that_moved": float(np.mean(A_d)) / N,
                   "how": f"flowSteps({T}, {v_frame}) x {Kd} in sliding motion, device-timed"}
 
+    # ---- opt-in contracted arithmetic (contracted=True = FQSB_KERNEL_FMA): the same kernel built
+    #      with FMA contraction. NOT part of `value` (the default stays bit-identical to the
+    #      reference arithmetic); parity of this mode: tests/test_gpu_contracted.py (landscape
+    #      exact, trajectories to rounding, goldens S-exact).
+    contracted = None
+    del ens
+    if not args.no_contracted:
+        ensc = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=R, seed=first * N, device=local_rank,
+                                               kernel=1, contracted=True, **kw)
+        ensc.set_stream(stream.cuda_stream)
+        assert np.all(ensc.minimise() == 0)
+        ensc.eventDrivenStep(1e-3, False)
+        ensc.eventDrivenStep(1e-3, True)
+        for _ in range(2):
+            ensc.timeSteps(T)
+        csec, cl = 0.0, 0
+        for _ in range(3):
+            ensc.timeSteps(T)
+            csec += ensc.last_kernel_seconds
+            cl += ensc.last_kernel_launches
+        csec = max_over_ranks(csec)
+        ensc.eventDrivenStep(1e-3, False)
+        ensc.eventDrivenStep(1e-3, True)
+        steps0 = ensc.step_count  # (steps over all realisations of the handle)
+        assert np.all(ensc.minimise() == 0)
+        msec = max_over_ranks(ensc.last_kernel_seconds)
+        msteps = float(ensc.step_count - steps0)
+        contracted = {"value": R_total * N * T * 3 / csec, "unit": UNIT,
+                      "ms_per_step": 1e3 * csec / 3,
+                      "minimise_block_updates_per_s": world * msteps * N / msec,
+                      "how": "the same ensemble, protocol and timeSteps(T) calls with "
+                             "contracted=True (resident kernel compiled with -fmad=true: ~21.6 "
+                             "instead of 30.6 FP64-pipe instructions per block-update); "
+                             "device-timed; results equal to rounding, not bit for bit"}
+        del ensc
+
     # ---- the streaming kernel K1 on the same ensemble (one fused step per launch, HBM-bound)
     roofline_stream = None
-    del ens
     if not args.no_stream:
         ens2 = F.Line1d.Ensemble_Cuspy_Laplace(nrealisations=R, seed=first * N,
                                                device=local_rank, kernel=2, **kw)
@@ -736,7 +772,7 @@ def main():
                                        "how": "set_u, set_v, set_a, time_steps, get, mean_f_frame "
                                               "as six calls (copies and kernel serialise)"}},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
-            "driven": driven, "strong_scaling": strong,
+            "driven": driven, "contracted_arithmetic": contracted, "strong_scaling": strong,
             "quasistatic_events": events, "slab": slab,
             "other_configs": other,
         }

@@ -244,8 +244,10 @@ class Ensemble:
                  k1=0.0, k2=0.0, k_frame=1.0, dt=0.0, seed=0, distribution="random",
                  parameters=(), offset=-100.0, nchunk=5000, minimisation=0, nrealisations=1,
                  seed_stride=0, device=-1, kernel=0, seed_first=0, seed_period=0, forcing=None,
-                 seed_forcing_stride=1):
+                 seed_forcing_stride=1, contracted=False):
         self._h = C.c_void_p()
+        if contracted:  # FQSB_KERNEL_FMA: resident kernels built with FMA contraction (opt-in; the
+            kernel = int(kernel) | 0x80  # dynamics then agree with the reference to rounding only)
         self._par = _params(potential, interactions, minimisation, shape, m, eta, mu, kappa, k1,
                             k2, k_frame, dt, seed, distribution, parameters, offset, nchunk,
                             nrealisations, seed_stride, device, kernel, seed_first, seed_period)
