@@ -102,6 +102,9 @@ struct Options {
     int64_t seed_stride = 0;
     int device = -1;
     int kernel = 0;
+    /** opt in to the resident kernels built with FMA contraction (FQSB_KERNEL_FMA): same yield
+     *  landscape, trajectories equal to rounding instead of bit for bit; default off */
+    bool contracted = false;
     int64_t seed_first = 0;
     int64_t seed_period = 0;
 };
@@ -281,7 +284,7 @@ protected:
         m_par.nrealisations = opt.nrealisations > 0 ? opt.nrealisations : 1;
         m_par.seed_stride = opt.seed_stride;
         m_par.device = opt.device;
-        m_par.kernel = opt.kernel;
+        m_par.kernel = opt.kernel | (opt.contracted ? FQSB_KERNEL_FMA : 0);
         m_par.seed_first = opt.seed_first;
         m_par.seed_period = opt.seed_period;
         check(fqsb_create(&m_par, &m_h));
