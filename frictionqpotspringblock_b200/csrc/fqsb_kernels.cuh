@@ -473,8 +473,10 @@ __global__ void __launch_bounds__(T)
             prev ^= 1;
         }
         if (UREG) { // (the write-back below reads the slips from shared memory)
+            // the two edge slips are already there (published in phase 1; neighbours may still
+            // be reading them)
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
+            for (int j = 1; j < B - 1; ++j) {
                 us[prev * NS + SLOT(POF(j))] = uc[j];
             }
         }
