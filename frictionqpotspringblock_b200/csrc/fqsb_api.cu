@@ -981,8 +981,14 @@ static int ensure_blocked_buffers(fqsb_system* s, const BlockedPlan& plan)
         s->bk_ready = true;
     }
     if (plan.ntiles > s->bk_log_tiles) { // (the geometry depends on the batch length)
+        const size_t ngroups = ((size_t)plan.ntiles + FQSB_BK_GROUP - 1) / FQSB_BK_GROUP;
+        CU(cudaStreamSynchronize(s->stream)); // (no launch may still count in the old buffer)
         TRY(dev_alloc(s, &s->bk.log,
                       (size_t)s->R * FQSB_BK_MAXSTEPS * (size_t)plan.ntiles * FQSB_NLOG));
+        TRY(dev_alloc(s, &s->bk.glog, (size_t)s->R * FQSB_BK_MAXSTEPS * ngroups * FQSB_NLOG));
+        TRY(dev_alloc(s, &s->bk.gcount, (size_t)s->R * ngroups));
+        CU(cudaMemsetAsync(s->bk.gcount, 0, (size_t)s->R * ngroups * sizeof(unsigned int),
+                           s->stream));
         s->bk_log_tiles = plan.ntiles;
     }
     s->bk.own = plan.own;

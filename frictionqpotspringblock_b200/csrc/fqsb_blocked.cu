@@ -39,11 +39,21 @@ namespace fqsb {
 #define FQSB_CAT2(a, b) a##b
 #define FQSB_CAT(a, b) FQSB_CAT2(a, b)
 
+// FQSB_FMA_BUILD: the same kernels compiled with -fmad=true (opt-in contracted arithmetic,
+// fqsb_params.kernel bit 7; Cuspy combinations 0, 1, 2) behind launch_blocked_fma_<k>
+#ifdef FQSB_FMA_BUILD
+#define C_FMA true
+#define FQSB_BK_LAUNCH_NAME(k) FQSB_CAT(launch_blocked_fma_, k)
+#else
+#define C_FMA false
+#define FQSB_BK_LAUNCH_NAME(k) FQSB_CAT(launch_blocked_, k)
+#endif
+
 template <class Kern>
 static cudaError_t launch(Kern kernel, const BlockedPlan& plan, const Par& P, const State& S,
                           const RunArgs& A, const BlockedArgs& K, cudaStream_t stream)
 {
-    const size_t smem = blocked_smem(plan.B);
+    const size_t smem = blocked_smem(plan.B, A.mode != MODE_FIXED);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) {
@@ -54,20 +64,20 @@ static cudaError_t launch(Kern kernel, const BlockedPlan& plan, const Par& P, co
     return cudaGetLastError();
 }
 
-cudaError_t FQSB_CAT(launch_blocked_, FQSB_COMBO)(const BlockedPlan& plan, const Par& P,
-                                                  const State& S, const RunArgs& A,
-                                                  const BlockedArgs& K, cudaStream_t stream)
+cudaError_t FQSB_BK_LAUNCH_NAME(FQSB_COMBO)(const BlockedPlan& plan, const Par& P,
+                                            const State& S, const RunArgs& A,
+                                            const BlockedArgs& K, cudaStream_t stream)
 {
     const bool unit = unit_parameters(P);
     const bool stop = A.mode != MODE_FIXED;
 #define FQSB_BK_CFG(b) \
     if (plan.B == b) { \
         if (unit) { \
-            return stop ? launch(k_blocked<C_POT, C_INT, b, true, true>, plan, P, S, A, K, stream) \
-                        : launch(k_blocked<C_POT, C_INT, b, true, false>, plan, P, S, A, K, stream); \
+            return stop ? launch(k_blocked<C_POT, C_INT, b, true, true, C_FMA>, plan, P, S, A, K, stream) \
+                        : launch(k_blocked<C_POT, C_INT, b, true, false, C_FMA>, plan, P, S, A, K, stream); \
         } \
-        return stop ? launch(k_blocked<C_POT, C_INT, b, false, true>, plan, P, S, A, K, stream) \
-                    : launch(k_blocked<C_POT, C_INT, b, false, false>, plan, P, S, A, K, stream); \
+        return stop ? launch(k_blocked<C_POT, C_INT, b, false, true, C_FMA>, plan, P, S, A, K, stream) \
+                    : launch(k_blocked<C_POT, C_INT, b, false, false, C_FMA>, plan, P, S, A, K, stream); \
     }
     FQSB_BK_CFG(2)
     FQSB_BK_CFG(3)
@@ -85,6 +95,7 @@ cudaError_t FQSB_CAT(launch_blocked_, FQSB_COMBO)(const BlockedPlan& plan, const
     cudaError_t launch_blocked_##k(const BlockedPlan&, const Par&, const State&, const RunArgs&, \
                                    const BlockedArgs&, cudaStream_t);
 FQSB_DECL(0) FQSB_DECL(1) FQSB_DECL(2) FQSB_DECL(6) FQSB_DECL(7) FQSB_DECL(8)
+FQSB_DECL(fma_0) FQSB_DECL(fma_1) FQSB_DECL(fma_2)
 
 static int blocked_combo(const Par& P)
 {
@@ -110,9 +121,9 @@ static int blocked_combo(const Par& P)
 
 bool blocked_supported(const Par& P) { return blocked_combo(P) >= 0 && P.N >= 2; }
 
-// Tile geometry. A CTA of 512 threads x B blocks per thread holds own + 2 H <= 512 B local
+// Tile geometry. A CTA of FQSB_BK_T threads x B blocks per thread holds own + 2 H <= T B local
 // blocks and costs ~B time units per step whatever its fill, and the grid of ntiles x R CTAs
-// runs in ceil(ntiles R / SMs) waves (one CTA per SM): pick the (B, ntiles) with the cheapest
+// runs in ceil(ntiles R / (FQSB_BK_CTAS SMs)) waves: pick the (B, ntiles) with the cheapest
 // waves x B, ties broken towards fewer tiles (less halo). `own_hint` > 0 fixes the tile size
 // (tests), `ksteps_hint` > 0 the steps per launch.
 BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
@@ -142,6 +153,7 @@ BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
             sms = n;
         }
     }
+    sms *= FQSB_BK_CTAS; // tiles resident at a time
     if (own_hint > 0) {
         i64 own = own_hint < N ? own_hint : N;
         int B = (int)((own + 2 * H + FQSB_BK_T - 1) / FQSB_BK_T);
@@ -187,7 +199,15 @@ BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
 cudaError_t launch_blocked(const BlockedPlan& plan, const Par& P, const State& S,
                            const RunArgs& A, const BlockedArgs& K, cudaStream_t stream)
 {
-    switch (blocked_combo(P)) {
+    const int combo = blocked_combo(P);
+    if (P.fma && combo >= 0 && combo <= 2) { // opt-in contracted arithmetic (Cuspy lines)
+        switch (combo) {
+        case 0: return launch_blocked_fma_0(plan, P, S, A, K, stream);
+        case 1: return launch_blocked_fma_1(plan, P, S, A, K, stream);
+        case 2: return launch_blocked_fma_2(plan, P, S, A, K, stream);
+        }
+    }
+    switch (combo) {
     case 0: return launch_blocked_0(plan, P, S, A, K, stream);
     case 1: return launch_blocked_1(plan, P, S, A, K, stream);
     case 2: return launch_blocked_2(plan, P, S, A, K, stream);

@@ -41,8 +41,10 @@ static __device__ __noinline__ int hop_blocked(const Par& P, double un, double* 
     return moved;
 }
 
-template <int POT, int INT, int B, bool UNIT, bool STOP>
-__global__ void __launch_bounds__(FQSB_BK_T)
+// FMA only names the instantiations of the translation units built with FMA contraction
+// (-fmad=true, FQSB_FMA_BUILD; fqsb_params.kernel bit 7): same source, contracted by the compiler.
+template <int POT, int INT, int B, bool UNIT, bool STOP, bool FMA = false>
+__global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     k_blocked(const __grid_constant__ Par P, const __grid_constant__ State S,
               const __grid_constant__ RunArgs A, const __grid_constant__ BlockedArgs K)
 {
@@ -75,12 +77,16 @@ __global__ void __launch_bounds__(FQSB_BK_T)
     // state (u, v, a, wells) in registers, so B - 1 of the 2B stencil neighbours are the thread's
     // own registers; per step a thread only publishes its first and last slip for its two
     // neighbouring threads (double-buffered edge arrays) and reads one slip from each of them.
-    double* eL = reinterpret_cast<double*>(smem_raw);          // [2][T + 1] first slip of a thread
-    double* eR = eL + 2 * (T + 1);                             // [2][T + 1] last slip of a thread
-    u64* sst = reinterpret_cast<u64*>(eR + 2 * (T + 1));       // [LMAX]
-    double* slog = reinterpret_cast<double*>(sst + LMAX);      // [MAXSTEPS][NW][2]
-    int* ilog = reinterpret_cast<int*>(slog + FQSB_BK_MAXSTEPS * NW * 2); // [MAXSTEPS][NW][4]
-    int* sdidx = ilog + FQSB_BK_MAXSTEPS * NW * 4;             // [LMAX]
+    double* eL = reinterpret_cast<double*>(smem_raw);          // [2][T + 2] first slip of a thread
+    double* eR = eL + 2 * (T + 2);                             // [2][T + 2] last slip of a thread
+    u64* sst = reinterpret_cast<u64*>(eR + 2 * (T + 2));       // [LMAX]
+    // stop modes: the per-thread sums of a step are PARKED (one 16-byte store) and reduced over
+    // the tile once every FQSB_BK_PARK steps, one warp per step, instead of a butterfly per warp
+    // and step (whose shuffle / add chain sat on the critical path of every step's barrier)
+    double2* park = reinterpret_cast<double2*>(sst + LMAX);    // [2 FQSB_BK_PARK][T]
+    double* slog = reinterpret_cast<double*>(park + (STOP ? 2 * FQSB_BK_PARK * T : 0)); // [MAXSTEPS][2]
+    int* ilog = reinterpret_cast<int*>(slog + FQSB_BK_MAXSTEPS * 2); // [MAXSTEPS][4] hops, dS, dA
+    int* sdidx = ilog + FQSB_BK_MAXSTEPS * 4;                  // [LMAX]
 
     const i64 base = (i64)r * P.N;
     const double* __restrict__ ui = (flip ? S.u2 : S.u) + base;
@@ -135,8 +141,8 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         for (int j = 0; j < B; ++j) {
             u[j] = u[j] + P.dt * v[j] + c2 * a[j];
         }
-        eL[pb * (T + 1) + t] = u[0];
-        eR[pb * (T + 1) + t] = u[B - 1];
+        eL[pb * (T + 2) + t] = u[0];
+        eR[pb * (T + 2) + t] = u[B - 1];
     };
 
     // ---- well search (detail.h:144), forces (detail.h:1380-1386), Verlet tail (1552-1565)
@@ -192,8 +198,8 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         }
         // slips of the two neighbouring threads (thread T-1 never reads beyond the arrays: its
         // last block is always the last of the tile or beyond)
-        const double from_left = t == 0 ? ghost_l : eR[pb * (T + 1) + t - 1];
-        const double from_right = eL[pb * (T + 1) + t + 1];
+        const double from_left = t == 0 ? ghost_l : eR[pb * (T + 2) + t - 1];
+        const double from_right = eL[pb * (T + 2) + t + 1];
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const int q = t * B + j;
@@ -206,10 +212,11 @@ __global__ void __launch_bounds__(FQSB_BK_T)
             double ff = P.k_frame * (uf - u[j]);
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);
-            if (decltype(accumulate)::value) {
-                const bool own = (summask >> j) & 1u;
-                sf += own ? f * f : 0.0;
-                sff += own ? ff * ff : 0.0;
+            // accumulate: 0 = no sums, 1 = blocks of `summask` only (an unmasked variant for the
+            // interior warps saves 16 selects per warp-step and measured no faster)
+            if (decltype(accumulate)::value == 1 && ((summask >> j) & 1u)) {
+                sf += f * f;
+                sff += ff * ff;
             }
         }
     };
@@ -223,32 +230,68 @@ __global__ void __launch_bounds__(FQSB_BK_T)
             }
             phase1(par);
             __syncthreads();
-            phase2(par, std::false_type{}, sf, sff, hops, dS, dA);
+            phase2(par, std::integral_constant<int, 0>{}, sf, sff, hops, dS, dA);
             par ^= 1;
         }
     }
     else {
+        for (int i = t; i < FQSB_BK_MAXSTEPS * 4; i += T) {
+            ilog[i] = 0;
+        }
+        // sums of steps s0 .. s0 + cnt - 1 over the tile: warp w takes step s0 + w (threads added
+        // in a fixed order: 8 strided terms per lane, then the butterfly)
+        auto reduce_parked = [&](const int s0, const int cnt) {
+            if (warp < cnt) {
+                const int s = s0 + warp;
+                const double2* e = park + (s & (2 * FQSB_BK_PARK - 1)) * T;
+                double x = 0.0, y = 0.0;
+#pragma unroll
+                for (int i = 0; i < T / 32; ++i) {
+                    const double2 z = e[lane + 32 * i];
+                    x += z.x;
+                    y += z.y;
+                }
+                warp_sum2(x, y);
+                if (lane == 0) {
+                    slog[s * 2] = x;
+                    slog[s * 2 + 1] = y;
+                }
+            }
+        };
+        static_assert(FQSB_BK_PARK <= NW, "one warp per parked step");
         for (int it = 0; it < nsteps; ++it) {
             double sf = 0.0, sff = 0.0;
             int hops = 0, dS = 0, dA = 0;
             phase1(par);
             __syncthreads();
-            phase2(par, std::true_type{}, sf, sff, hops, dS, dA);
+            if (it > 0 && (it & (FQSB_BK_PARK - 1)) == 0) {
+                // (the slots being read are rewritten FQSB_BK_PARK steps from now, i.e. after the
+                // next barrier at the earliest)
+                reduce_parked(it - FQSB_BK_PARK, FQSB_BK_PARK);
+            }
+            phase2(par, std::integral_constant<int, 1>{}, sf, sff, hops, dS, dA);
             par ^= 1;
-            // per-warp partials of this step; nobody waits for them before the launch ends
-            warp_sum2(sf, sff);
-            hops = __reduce_add_sync(0xffffffffu, hops);
-            if (A.track) {
-                dS = __reduce_add_sync(0xffffffffu, dS);
-                dA = __reduce_add_sync(0xffffffffu, dA);
+            park[(it & (2 * FQSB_BK_PARK - 1)) * T + t] = make_double2(sf, sff);
+            // well changes are rare: integer sums straight into the per-step log
+            if (__any_sync(0xffffffffu, hops != 0)) {
+                hops = __reduce_add_sync(0xffffffffu, hops);
+                if (A.track) {
+                    dS = __reduce_add_sync(0xffffffffu, dS);
+                    dA = __reduce_add_sync(0xffffffffu, dA);
+                }
+                if (lane == 0) {
+                    atomicAdd(ilog + it * 4, hops);
+                    if (A.track) {
+                        atomicAdd(ilog + it * 4 + 1, dS);
+                        atomicAdd(ilog + it * 4 + 2, dA);
+                    }
+                }
             }
-            if (lane == 0) {
-                slog[(it * NW + warp) * 2] = sf;
-                slog[(it * NW + warp) * 2 + 1] = sff;
-                ilog[(it * NW + warp) * 4] = hops;
-                ilog[(it * NW + warp) * 4 + 1] = dS;
-                ilog[(it * NW + warp) * 4 + 2] = dA;
-            }
+        }
+        __syncthreads();
+        {
+            const int s0 = ((nsteps - 1) / FQSB_BK_PARK) * FQSB_BK_PARK;
+            reduce_parked(s0, nsteps - s0);
         }
     }
 
@@ -292,62 +335,79 @@ __global__ void __launch_bounds__(FQSB_BK_T)
         return;
     }
 
-    // ---- this tile's per-step sums (warps added in order) -> global log
+    // ---- this tile's per-step sums (warps added in order) -> global log, tile-major
+    //      [r][tile][step][FQSB_NLOG]. The totals per step are formed in two levels, both in a
+    //      fixed order (deterministic: a redone batch decides exactly as the revoked one): the
+    //      last tile of a GROUP of FQSB_BK_GROUP consecutive tiles to finish adds the group up,
+    //      the last group to finish adds the groups up. (One level -- the last tile reading
+    //      ntiles x nsteps entries alone -- was a serial tail of ~150 us per launch on a line
+    //      of 2^20 blocks: 1171 tiles x 64 steps x 40 B through one SM.)
+    constexpr int G = FQSB_BK_GROUP, LOGSZ = FQSB_BK_MAXSTEPS * FQSB_NLOG;
+    const int ngroups = (K.ntiles + G - 1) / G;
+    const int grp = c / G;
+    const int gsize = K.ntiles - grp * G < G ? K.ntiles - grp * G : G;
     __syncthreads();
-    for (int s = t; s < nsteps; s += T) {
-        double a0 = 0.0, a1 = 0.0;
-        int h = 0, ds = 0, da = 0;
-        for (int w = 0; w < NW; ++w) {
-            a0 += slog[(s * NW + w) * 2];
-            a1 += slog[(s * NW + w) * 2 + 1];
-            h += ilog[(s * NW + w) * 4];
-            ds += ilog[(s * NW + w) * 4 + 1];
-            da += ilog[(s * NW + w) * 4 + 2];
+    {
+        double* e = K.log + ((size_t)r * K.ntiles + c) * LOGSZ;
+        for (int s = t; s < nsteps; s += T) {
+            __stcg(e + s * FQSB_NLOG, slog[s * 2]);
+            __stcg(e + s * FQSB_NLOG + 1, slog[s * 2 + 1]);
+            __stcg(e + s * FQSB_NLOG + 2, (double)ilog[s * 4]);
+            __stcg(e + s * FQSB_NLOG + 3, (double)ilog[s * 4 + 1]);
+            __stcg(e + s * FQSB_NLOG + 4, (double)ilog[s * 4 + 2]);
         }
-        double* e = K.log + (((size_t)r * FQSB_BK_MAXSTEPS + s) * K.ntiles + c) * FQSB_NLOG;
-        e[0] = a0;
-        e[1] = a1;
-        e[2] = (double)h;
-        e[3] = (double)ds;
-        e[4] = (double)da;
     }
+    unsigned int* gcount = K.gcount + (size_t)r * ngroups + grp;
     __threadfence();
     __syncthreads();
     if (t == 0) {
-        unsigned int ticket = atomicAdd(&ctl.count, 1u);
-        s_last = ticket == (unsigned)K.ntiles - 1u;
+        unsigned int ticket = atomicAdd(gcount, 1u);
+        s_last = ticket == (unsigned)gsize - 1u;
     }
     __syncthreads();
     if (!s_last) {
         return;
     }
-    // ---- the last tile of the realisation: totals per step (tiles added in order: lane-strided
-    //      partial sums, then a fixed butterfly), then the sequential replay of the decisions
+    // ---- the last tile of its group: group totals (tiles added in order)
     __threadfence();
-    double* tot = slog; // [MAXSTEPS][FQSB_NLOG] (the warp partials have been consumed)
-    for (int s = warp; s < nsteps; s += NW) {
-        double x[FQSB_NLOG];
-#pragma unroll
-        for (int k = 0; k < FQSB_NLOG; ++k) {
-            x[k] = 0.0;
-        }
-        const volatile double* e =
-            K.log + ((size_t)r * FQSB_BK_MAXSTEPS + s) * K.ntiles * FQSB_NLOG;
-        for (int cc = lane; cc < K.ntiles; cc += 32) {
-#pragma unroll
-            for (int k = 0; k < FQSB_NLOG; ++k) {
-                x[k] += e[cc * FQSB_NLOG + k];
+    {
+        const double* src = K.log + ((size_t)r * K.ntiles + (size_t)grp * G) * LOGSZ;
+        double* dst = K.glog + ((size_t)r * ngroups + grp) * LOGSZ;
+        for (int i = t; i < nsteps * FQSB_NLOG; i += T) {
+            double x = 0.0;
+#pragma unroll 8
+            for (int cc = 0; cc < gsize; ++cc) {
+                x += __ldcg(src + (size_t)cc * LOGSZ + i);
             }
+            __stcg(dst + i, x);
         }
-#pragma unroll
-        for (int k = 0; k < FQSB_NLOG; ++k) {
-            x[k] = warp_sum(x[k]);
+        if (t == 0) {
+            *gcount = 0u;
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < FQSB_NLOG; ++k) {
-                tot[s * FQSB_NLOG + k] = x[k];
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        unsigned int ticket = atomicAdd(&ctl.count, 1u);
+        s_last = ticket == (unsigned)ngroups - 1u;
+    }
+    __syncthreads();
+    if (!s_last) {
+        return;
+    }
+    // ---- the last group of the realisation: totals per step (groups added in order), then the
+    //      sequential replay of the decisions
+    __threadfence();
+    double* tot = reinterpret_cast<double*>(park); // [MAXSTEPS][FQSB_NLOG] (the parked sums have been consumed)
+    {
+        const double* src = K.glog + (size_t)r * ngroups * LOGSZ;
+        for (int i = t; i < nsteps * FQSB_NLOG; i += T) {
+            double x = 0.0;
+#pragma unroll 8
+            for (int gg = 0; gg < ngroups; ++gg) {
+                x += __ldcg(src + (size_t)gg * LOGSZ + i);
             }
+            tot[i] = x;
         }
     }
     __syncthreads();

@@ -131,8 +131,11 @@ struct Thermal {
 };
 
 // ---- K2b (fqsb_blocked.cuh): temporally blocked tiles of a long 1-D line ----------------------
-#define FQSB_BK_T 512       // threads per tile
+#define FQSB_BK_T 256       // threads per tile
+#define FQSB_BK_CTAS 2    // resident tiles per SM: the load / store phase of one overlaps the steps of the other
 #define FQSB_BK_MAXSTEPS 64 // upper bound of steps per launch (size of the per-step log)
+#define FQSB_BK_PARK 8      // stop modes: steps whose per-thread sums are parked before a reduction (power of 2)
+#define FQSB_BK_GROUP 32    // tiles per group of the two-level reduction of the per-step logs
 
 struct BlockedArgs {
     int own;    // owned blocks per tile (the last tile may own fewer)
@@ -146,7 +149,9 @@ struct BlockedArgs {
     i64* idx2;
     u64* rng2;
     double* uf2; // [R]
-    double* log; // [R][FQSB_BK_MAXSTEPS][ntiles][FQSB_NLOG]
+    double* log;  // [R][ntiles][FQSB_BK_MAXSTEPS][FQSB_NLOG] per-step sums of every tile
+    double* glog; // [R][ngroups][FQSB_BK_MAXSTEPS][FQSB_NLOG] ... of every group of tiles
+    unsigned int* gcount; // [R][ngroups] tiles of a group that have finished (0 between launches)
 };
 
 // ---- prrng::pcg32 ------------------------------------------------------

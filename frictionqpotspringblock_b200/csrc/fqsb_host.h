@@ -88,11 +88,14 @@ struct BlockedPlan {
 bool blocked_supported(const Par& P);
 BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint);
 // dynamic shared memory of k_blocked (must mirror the carve-up in the kernel)
-inline size_t blocked_smem(int B)
+inline size_t blocked_smem(int B, bool stop = true)
 {
-    const size_t lmax = (size_t)B * FQSB_BK_T, nw = FQSB_BK_T / 32;
-    // edge slips [2][2][T + 1], pcg32 states, per-step logs, well-move counters
-    return 4 * ((size_t)FQSB_BK_T + 1) * 8 + lmax * 8 + FQSB_BK_MAXSTEPS * nw * (2 * 8 + 4 * 4) + lmax * 4;
+    const size_t lmax = (size_t)B * FQSB_BK_T;
+    // edge slips [2][2][T + 2], pcg32 states, parked sums (stop modes), per-step logs, well-move
+    // counters
+    return 4 * ((size_t)FQSB_BK_T + 2) * 8 + lmax * 8 +
+           (stop ? (size_t)2 * FQSB_BK_PARK * FQSB_BK_T * 16 : 0) +
+           FQSB_BK_MAXSTEPS * (2 * 8 + 4 * 4) + lmax * 4;
 }
 cudaError_t launch_blocked(const BlockedPlan& plan, const Par& P, const State& S,
                            const RunArgs& A, const BlockedArgs& K, cudaStream_t stream);

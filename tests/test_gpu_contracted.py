@@ -51,6 +51,34 @@ def test_contracted_trajectory_agrees_with_the_oracle_to_rounding(cls, extra, N)
     assert not np.array_equal(gpu.v, cpu.v)  # (it really is a different arithmetic)
 
 
+@pytest.mark.parametrize("cls,extra", CASES)
+def test_contracted_blocked_kernel_agrees_with_the_oracle_to_rounding(cls, extra):
+    """the temporally blocked kernel (lines beyond one CTA, config #3) has the same opt-in build"""
+    from oracle import oracle as orc
+
+    F = product()
+    N = 6000
+    kw = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, k_frame=1.0 / N, dt=0.1, shape=[N],
+              seed=5, distribution="random", parameters=[2.0], offset=-50, **extra)
+    gpu = getattr(F.Line1d, cls)(contracted=True, **kw)
+    cpu = getattr(orc.Line1d, cls)(**kw)
+    for s in (gpu, cpu):
+        s.u_frame = 3.0
+        s.timeSteps(300)
+    assert gpu.last_kernel == "blocked_1d"
+    assert np.array_equal(gpu.chunk.index_at_align, cpu.chunk.index_at_align)
+    assert np.array_equal(gpu.chunk.right_of_align, cpu.chunk.right_of_align)
+    scale = np.max(np.abs(cpu.u)) + 1.0
+    assert np.max(np.abs(gpu.u - cpu.u)) < 1e-12 * scale
+    assert np.max(np.abs(gpu.v - cpu.v)) < 1e-12 * (np.max(np.abs(cpu.v)) + 1.0)
+    assert not np.array_equal(gpu.v, cpu.v)
+    # the stop modes take the same decisions
+    niter_g = gpu.minimise()
+    niter_c = cpu.minimise()
+    assert niter_g == niter_c
+    assert np.array_equal(gpu.chunk.index_at_align, cpu.chunk.index_at_align)
+
+
 @pytest.mark.parametrize("name", ["Line1d_Cuspy_Laplace", "Line1d_Cuspy_Quartic"])
 def test_goldens_reproduce_with_contracted_arithmetic(name, golden_dir):
     """examples/<name>.py against its committed .h5, full length, with the FMA-contracted kernels:
