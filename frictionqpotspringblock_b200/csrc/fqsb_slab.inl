@@ -91,6 +91,51 @@ __device__ __forceinline__ bool slab_wait(const u64* flag, u64 epoch, const Slab
     return true;
 }
 
+
+// 7 planes x 2 sides of halo cells in one pass: every thread issues its 14 loads before its 14
+// stores (16-byte accesses when everything is 16-byte aligned), so a member's ~15 MB of halo rows
+// (4096^2 interface, 32 rows) move at NVLink / HBM rate instead of at the latency of one
+// load-store pair per thread at a time.
+template <bool LDCG, class SA, class DA, class SB, class DB>
+__device__ __forceinline__ void slab_copy14(SA srcA, DA dstA, SB srcB, DB dstB, const i64 cells,
+                                            const bool vec)
+{
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (i64 c = t0; c < (cells >> 1); c += stride) {
+            ulonglong2 x[14];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const ulonglong2* a = reinterpret_cast<const ulonglong2*>(srcA(q)) + c;
+                const ulonglong2* b = reinterpret_cast<const ulonglong2*>(srcB(q)) + c;
+                x[q] = LDCG ? __ldcg(a) : *a;
+                x[7 + q] = LDCG ? __ldcg(b) : *b;
+            }
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                reinterpret_cast<ulonglong2*>(dstA(q))[c] = x[q];
+                reinterpret_cast<ulonglong2*>(dstB(q))[c] = x[7 + q];
+            }
+        }
+    }
+    else {
+        for (i64 c = t0; c < cells; c += stride) {
+            u64 x[14];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                x[q] = LDCG ? __ldcg(srcA(q) + c) : srcA(q)[c];
+                x[7 + q] = LDCG ? __ldcg(srcB(q) + c) : srcB(q)[c];
+            }
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                dstA(q)[c] = x[q];
+                dstB(q)[c] = x[7 + q];
+            }
+        }
+    }
+}
+
 // ---- after a batch: outermost owned rows -> the neighbours' mailboxes, log -> all mailboxes ------
 __global__ void __launch_bounds__(256)
     k_slab_push(const State S, const SlabDev D, const double* log, int nlog, int halos)
@@ -108,33 +153,13 @@ __global__ void __launch_bounds__(256)
                            reinterpret_cast<const u64*>(S.yr), reinterpret_cast<const u64*>(S.idx),
                            S.rng};
     const i64 top = D.hc, bot = D.n - 2 * D.hc;
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (!halos) {
-        // gather only
-    }
-    else if (((D.hc | D.n) & 1) == 0) { // 16-byte stores: every offset is then 16-byte aligned
-        const i64 h2 = D.hc >> 1;
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            const ulonglong2* st = reinterpret_cast<const ulonglong2*>(plane[q] + top);
-            const ulonglong2* sb = reinterpret_cast<const ulonglong2*>(plane[q] + bot);
-            ulonglong2* dp = reinterpret_cast<ulonglong2*>(to_prev + (i64)q * D.hc);
-            ulonglong2* dn = reinterpret_cast<ulonglong2*>(to_next + (i64)q * D.hc);
-            for (i64 c = t0; c < h2; c += stride) {
-                dp[c] = st[c];
-                dn[c] = sb[c];
-            }
-        }
-    }
-    else {
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            for (i64 c = t0; c < D.hc; c += stride) {
-                to_prev[(i64)q * D.hc + c] = plane[q][top + c];
-                to_next[(i64)q * D.hc + c] = plane[q][bot + c];
-            }
-        }
+    if (halos) {
+        const i64 hc = D.hc;
+        slab_copy14<false>([&](int q) { return plane[q] + top; },
+                           [&](int q) { return to_prev + (i64)q * hc; },
+                           [&](int q) { return plane[q] + bot; },
+                           [&](int q) { return to_next + (i64)q * hc; }, hc,
+                           ((D.hc | D.n) & 1) == 0);
     }
     const u64 ge = D.epoch[1] + 1;
     if (nlog > 0 && blockIdx.x == 0) {
@@ -190,16 +215,11 @@ __global__ void __launch_bounds__(256)
             u64* plane[7] = {reinterpret_cast<u64*>(S.u),  reinterpret_cast<u64*>(S.v),
                              reinterpret_cast<u64*>(S.a),  reinterpret_cast<u64*>(S.yl),
                              reinterpret_cast<u64*>(S.yr), reinterpret_cast<u64*>(S.idx), S.rng};
-            const i64 stride = (i64)gridDim.x * blockDim.x;
-            const i64 t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-            const i64 bot = D.n - D.hc;
-#pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                for (i64 c = t0; c < D.hc; c += stride) {
-                    plane[q][c] = __ldcg(from_prev + (i64)q * D.hc + c);
-                    plane[q][bot + c] = __ldcg(from_next + (i64)q * D.hc + c);
-                }
-            }
+            const i64 bot = D.n - D.hc, hc = D.hc;
+            slab_copy14<true>([&](int q) { return from_prev + (i64)q * hc; },
+                              [&](int q) { return plane[q]; },
+                              [&](int q) { return from_next + (i64)q * hc; },
+                              [&](int q) { return plane[q] + bot; }, hc, ((D.hc | D.n) & 1) == 0);
         }
     }
     if (nlog > 0 && blockIdx.x == 0) {
@@ -691,10 +711,9 @@ static int slab_copy_state(fqsb_system* s, int slot, bool restore)
 static int slab_enqueue_push(fqsb_system* s, int nlog, const double* src, int halos)
 {
     fqsb_slab_state* L = s->slab;
-    // enough CTAs to keep the NVLink stores in flight, few enough to coexist with other streams
-    const i64 words = 14 * L->halo_cells;
-    unsigned grid = halos ? (unsigned)((words / 2 + 2047) / 2048) : 1u;
-    grid = grid < 1u ? 1u : (grid > 64u ? 64u : grid);
+    // one 16-byte word of each of the 14 (plane, side) pairs per thread
+    unsigned grid = halos ? (unsigned)((L->halo_cells / 2 + 255) / 256) : 1u;
+    grid = grid < 1u ? 1u : (grid > 592u ? 592u : grid);
     k_slab_push<<<grid, 256, 0, s->stream>>>(s->S, L->dev, src, nlog, halos);
     CU(cudaGetLastError());
     s->launches++;
@@ -706,9 +725,10 @@ static int slab_enqueue_import(fqsb_system* s, int nlog, int raw, int halos,
                                const double** res = nullptr, int ev = -1)
 {
     fqsb_slab_state* L = s->slab;
-    const i64 words = 14 * L->halo_cells;
-    unsigned grid = halos ? (unsigned)((words + 4095) / 4096) : 1u;
-    grid = grid < 1u ? 1u : (grid > 32u ? 32u : grid);
+    // (every CTA spins on the neighbours' flags -- set by OTHER devices, so the CTAs need not be
+    // co-resident -- then moves one 16-byte word of each (plane, side) pair per thread)
+    unsigned grid = halos ? (unsigned)((L->halo_cells / 2 + 255) / 256) : 1u;
+    grid = grid < 1u ? 1u : (grid > 592u ? 592u : grid);
     k_slab_import<<<grid, 256, 0, s->stream>>>(s->S, L->dev, nlog, raw, halos);
     CU(cudaGetLastError());
     s->launches++;
