@@ -423,6 +423,7 @@ int fqsb_create(const fqsb_params* par, fqsb_system** out)
     P.k2 = par->k2;
     P.k_frame = par->k_frame;
     P.dt = par->dt;
+    P.c2 = 0.5 * par->dt * par->dt;
     {
         // prrng defaults for omitted parameters
         double def[4] = {1.0, 0.0, 0.0, 0.0};

@@ -117,6 +117,10 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
             sst[q] = rngi[gp];
             sdidx[q] = 0;
         }
+        else { // padding (never stored): a copy of the last block in one unbounded well
+            yl[j] = -1e300;
+            yr[j] = 1e300;
+        }
         if (q + 1 >= L) {
             ghostmask |= 1u << j;
         }
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     // enters at the outermost halo block and moves inwards one block per step
     const double ghost_l = ui[GP(-1)], ghost_r = ui[GP(L)];
 
-    const double c2 = 0.5 * P.dt * P.dt; // (0.5*dt)*dt, detail.h:1549
+    const double c2 = P.c2; // (0.5*dt)*dt, detail.h:1549
     int underflow = 0;
     int par = 0;
 
@@ -148,18 +152,17 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     // ---- well search (detail.h:144), forces (detail.h:1380-1386), Verlet tail (1552-1565)
     auto phase2 = [&](const int pb, auto accumulate, double& sf, double& sff, int& hops,
                       int& dS, int& dA) {
-        unsigned need = 0u;
+        // one flag, an OR chain through the compares (re-tested per block on the rare path); the
+        // padding blocks beyond the tile sit in an unbounded well and never ask
+        bool need = false;
 #pragma unroll
         for (int j = 0; j < B; ++j) {
-            const int q = t * B + j;
-            if (q < L && (u[j] > yr[j] || !(u[j] > yl[j]))) {
-                need |= 1u << j;
-            }
+            need |= (u[j] > yr[j]) | !(u[j] > yl[j]);
         }
         if (need) { // rare: some block of this thread left its well
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                if ((need >> j) & 1u) {
+                if ((u[j] > yr[j]) | !(u[j] > yl[j])) {
                     const int q = t * B + j;
                     const int gp = GP(q);
                     int uflag = 0;

@@ -33,6 +33,7 @@ struct Par {
     i64 N; // blocks per realisation
     i64 R; // realisations
     double m, inv_m, eta, mu, kappa, k1, k2, k_frame, dt;
+    double c2; // (0.5 * dt) * dt, detail.h:1549 (a kernel parameter: costs the hot loops no register)
     double dpar[4];
     double offset;
     u64 seed, seed_stride;

@@ -279,7 +279,11 @@ __global__ void __launch_bounds__(T)
     __syncthreads(); // clamped threads read block N-1's slip, written by its owner
 
     double uf = S.u_frame[r];
-    const double c2 = 0.5 * P.dt * P.dt; // (0.5*dt)*dt, detail.h:1549
+    // (0.5*dt)*dt, detail.h:1549. The fixed-step loops take it as a kernel parameter (computed on
+    // the host: the same two IEEE products), which costs them neither a register nor the two
+    // multiplications the compiler otherwise repeats every step; the stop variants keep the
+    // expression (their register allocation came out ~10 % slower with the parameter)
+    const double c2 = STOP ? 0.5 * P.dt * P.dt : P.c2;
     int underflow = 0;
     int prev = 0; // buffer holding the current slips
 
@@ -329,6 +333,10 @@ __global__ void __launch_bounds__(T)
     // phase 2a: the new positions of this thread's blocks and the well test -- no side effects,
     // so the stop modes run it BEFORE the decision about the previous step is known (its
     // shuffle chain is still in flight then)
+    // Fixed-step loops: `need` is ONE flag per thread, an OR chain through the compares (a
+    // per-block bit mask costs two integer instructions per block and step); the rare path below
+    // repeats the test per block. The stop modes keep the bit mask (their register allocation
+    // came out 9 % slower with the flag in the FMA build and no faster in the exact one).
     auto phase2a = [&](const double (&uc)[B], unsigned& need) {
         need = 0u;
 #pragma unroll
@@ -337,8 +345,13 @@ __global__ void __launch_bounds__(T)
             const int pc = (FULL || p < N) ? p : N - 1;
             const double l = YSMEM ? syl[pc] : yl[j];
             const double rr = YSMEM ? syr[pc] : yr[j];
-            if ((FULL || p < N) && (uc[j] > rr || !(uc[j] > l))) {
-                need |= 1u << j;
+            if (STOP) {
+                if ((FULL || p < N) && (uc[j] > rr || !(uc[j] > l))) {
+                    need |= 1u << j;
+                }
+            }
+            else {
+                need |= (unsigned)((FULL || p < N) & ((uc[j] > rr) | !(uc[j] > l)));
             }
         }
     };
@@ -360,7 +373,8 @@ __global__ void __launch_bounds__(T)
         if (need) { // rare: some block of this thread left its well
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                if ((need >> j) & 1u) {
+                if (STOP ? (((need >> j) & 1u) != 0u)
+                         : ((FULL || POF(j) < N) && (uc[j] > wr[j] || !(uc[j] > wl[j])))) {
                     const int p = POF(j);
                     double l = wl[j], rr = wr[j];
                     i64 i_before = 0;
@@ -464,7 +478,9 @@ __global__ void __launch_bounds__(T)
             }
         }
         for (i64 it = 0; it < nloop; ++it) {
-            if (A.flow) {
+            // (the fixed-step variant with the inline well change IS the flowSteps variant:
+            // FQSB_TRY_MODE in fqsb_resident.cu; timeSteps' loop carries no frame update at all)
+            if (HOPINL && A.flow) {
                 uf += A.v_frame * P.dt; // detail.h:1642
             }
             phase1(prev * NS, (prev ^ 1) * NS, uc);
