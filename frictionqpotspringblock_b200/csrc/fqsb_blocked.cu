@@ -122,10 +122,13 @@ static int blocked_combo(const Par& P)
 bool blocked_supported(const Par& P) { return blocked_combo(P) >= 0 && P.N >= 2; }
 
 // Tile geometry. A CTA of FQSB_BK_T threads x B blocks per thread holds own + 2 H <= T B local
-// blocks and costs ~B time units per step whatever its fill, and the grid of ntiles x R CTAs
-// runs in ceil(ntiles R / (FQSB_BK_CTAS SMs)) waves: pick the (B, ntiles) with the cheapest
-// waves x B, ties broken towards fewer tiles (less halo). `own_hint` > 0 fixes the tile size
-// (tests), `ksteps_hint` > 0 the steps per launch.
+// blocks and costs ~B time units per step whatever its fill. The tiles resident on one SM share
+// its FP64 issue slots (two tiles per SM only overlap each other's load / store phases and
+// latencies), so the grid of ntiles x R CTAs costs ceil(ntiles R / SMs) x B per step: pick the
+// (B, ntiles) with the cheapest, ties broken towards fewer tiles (less halo). [Counting
+// FQSB_BK_CTAS x SMs slots instead gave the members of an 8-GPU slab 205 tiles of B = 3 -- two
+// tiles on 57 SMs, one on the others -- where 147 tiles of B = 4 do one tile per SM.]
+// `own_hint` > 0 fixes the tile size (tests), `ksteps_hint` > 0 the steps per launch.
 BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
 {
     BlockedPlan best;
@@ -153,7 +156,6 @@ BlockedPlan blocked_plan(const Par& P, int ksteps_hint, int own_hint)
             sms = n;
         }
     }
-    sms *= FQSB_BK_CTAS; // tiles resident at a time
     if (own_hint > 0) {
         i64 own = own_hint < N ? own_hint : N;
         int B = (int)((own + 2 * H + FQSB_BK_T - 1) / FQSB_BK_T);

@@ -1,5 +1,6 @@
 """Config #3 (N = 2^20, Cuspy_Quartic): temporally blocked kernel for several tile geometries
 (kernel bits 8..15 = steps per launch, bits 16..31 = owned blocks per tile, 0 = planner)."""
+import os
 import sys
 
 import numpy as np
@@ -7,7 +8,7 @@ import numpy as np
 sys.path.insert(0, ".")
 import frictionqpotspringblock_b200 as F  # noqa: E402
 
-N = 1 << 20
+N = int(os.environ.get("FQSB_N", 1 << 20))
 kw = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, a1=1.0, a2=1.0, k_frame=1.0 / N,
           dt=0.1, shape=[N], distribution="random", parameters=[2.0], offset=-50, seed=0)
 T = 2048
