@@ -72,6 +72,10 @@ cudaError_t FQSB_BK_LAUNCH_NAME(FQSB_COMBO)(const BlockedPlan& plan, const Par& 
     const bool stop = A.mode != MODE_FIXED;
 #define FQSB_BK_CFG(b) \
     if (plan.B == b) { \
+        if (!stop && K.fuse.on) { /* a slab member's fixed-step batch with the exchange on board */ \
+            return unit ? launch(k_blocked<C_POT, C_INT, b, true, false, C_FMA, true>, plan, P, S, A, K, stream) \
+                        : launch(k_blocked<C_POT, C_INT, b, false, false, C_FMA, true>, plan, P, S, A, K, stream); \
+        } \
         if (unit) { \
             return stop ? launch(k_blocked<C_POT, C_INT, b, true, true, C_FMA>, plan, P, S, A, K, stream) \
                         : launch(k_blocked<C_POT, C_INT, b, true, false, C_FMA>, plan, P, S, A, K, stream); \

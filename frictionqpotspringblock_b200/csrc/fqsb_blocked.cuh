@@ -43,7 +43,8 @@ static __device__ __noinline__ int hop_blocked(const Par& P, double un, double* 
 
 // FMA only names the instantiations of the translation units built with FMA contraction
 // (-fmad=true, FQSB_FMA_BUILD; fqsb_params.kernel bit 7): same source, contracted by the compiler.
-template <int POT, int INT, int B, bool UNIT, bool STOP, bool FMA = false>
+// FUSE: the instantiation whose tiles carry a slab member's halo exchange (BlockedFuse; fixed steps)
+template <int POT, int INT, int B, bool UNIT, bool STOP, bool FMA = false, bool FUSE = false>
 __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     k_blocked(const __grid_constant__ Par P, const __grid_constant__ State S,
               const __grid_constant__ RunArgs A, const __grid_constant__ BlockedArgs K)
@@ -94,9 +95,57 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     const double* __restrict__ ai = (flip ? S.a2 : S.a) + base;
     const double* __restrict__ yli = (flip ? K.yl2 : S.yl) + base;
     const double* __restrict__ yri = (flip ? K.yr2 : S.yr) + base;
-    const i64* __restrict__ idxi = (flip ? K.idx2 : S.idx) + base;
+    const i64* idxi = (flip ? K.idx2 : S.idx) + base; // (no __restrict__: fused readers patch its halo cells)
     const u64* __restrict__ rngi = (flip ? K.rng2 : S.rng) + base;
     double uf = (flip ? K.uf2 : S.u_frame)[r];
+
+    // ---- fused halo exchange of a slab member (BlockedFuse): roles of this tile, wait for the
+    //      neighbours' previous push (also before WRITING into their mailboxes: the slot this
+    //      batch fills was last read by their batch before)
+    const BlockedFuse& Fz = K.fuse;
+    bool fz_reader = false, fz_pusher = false;
+    const u64 *fz_in0 = nullptr, *fz_in1 = nullptr; // mail "from prev" -> [0, hc), "from next" -> [N - hc, N)
+    if (FUSE && Fz.on) {
+        blocked_tile_roles(P.N, Fz.hc, K.own, H, c, &fz_reader, &fz_pusher);
+        fz_reader = fz_reader && Fz.pull;
+        if (fz_reader || fz_pusher) {
+            const u64 e_in = *Fz.epoch + (u64)Fz.batch;
+            if (t == 0) {
+                const unsigned long long t0 = global_ns();
+                while (ld_acquire_sys(Fz.self) < e_in || ld_acquire_sys(Fz.self + 1) < e_in) {
+                    if (global_ns() - t0 > Fz.timeout_ns) {
+                        Fz.h_status[0] = 1;
+                        __threadfence_system();
+                        break;
+                    }
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+            fz_in0 = slab_mail(Fz.self, (int)(e_in & 1ULL), 0, Fz.hc);
+            fz_in1 = slab_mail(Fz.self, (int)(e_in & 1ULL), 1, Fz.hc);
+        }
+    }
+    // plane q (u, v, a, y_l, y_r, idx, rng) of local block gp: the state arrays, or -- halo
+    // regions of a fused reader -- the mailbox
+    const u64* const planes[7] = {reinterpret_cast<const u64*>(ui),  reinterpret_cast<const u64*>(vi),
+                                  reinterpret_cast<const u64*>(ai),  reinterpret_cast<const u64*>(yli),
+                                  reinterpret_cast<const u64*>(yri), reinterpret_cast<const u64*>(idxi),
+                                  rngi};
+    auto SRC = [&](const int q, const int gp) -> const u64* {
+        if (FUSE && fz_reader) {
+            if (gp < Fz.hc) {
+                return fz_in0 + (i64)q * Fz.hc + gp;
+            }
+            if (gp >= N - Fz.hc) {
+                return fz_in1 + (i64)q * Fz.hc + (gp - (N - Fz.hc));
+            }
+        }
+        return planes[q] + gp;
+    };
+    auto LDD = [&](const int q, const int gp) {
+        return __longlong_as_double((i64)(FUSE ? __ldcg(SRC(q, gp)) : *SRC(q, gp)));
+    };
 
     double u[B], v[B], a[B], yl[B], yr[B];
     // ownmask: blocks this tile writes back; summask: those of them that enter the sums (a member
@@ -108,14 +157,20 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
         const int q = t * B + j;
         const int qc = q < L ? q : L - 1;
         const int gp = GP(qc);
-        u[j] = ui[gp];
-        v[j] = vi[gp];
-        a[j] = ai[gp];
-        yl[j] = yli[gp];
-        yr[j] = yri[gp];
+        u[j] = LDD(0, gp);
+        v[j] = LDD(1, gp);
+        a[j] = LDD(2, gp);
+        yl[j] = LDD(3, gp);
+        yr[j] = LDD(4, gp);
         if (q < L) {
-            sst[q] = rngi[gp];
+            sst[q] = FUSE ? __ldcg(SRC(6, gp)) : *SRC(6, gp);
             sdidx[q] = 0;
+            if (FUSE && fz_reader && (gp < Fz.hc || gp >= N - Fz.hc)) {
+                // the well index is only read on the rare path, long after this tile has released
+                // the mailbox: park it in the (stale) halo cell of the input set, which nothing
+                // else reads in a fused batch
+                __stcg(const_cast<i64*>(idxi) + gp, (i64)__ldcg(SRC(5, gp)));
+            }
         }
         else { // padding (never stored): a copy of the last block in one unbounded well
             yl[j] = -1e300;
@@ -133,7 +188,14 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     }
     // the cells just outside the tile stay frozen at their input value: the error this makes
     // enters at the outermost halo block and moves inwards one block per step
-    const double ghost_l = ui[GP(-1)], ghost_r = ui[GP(L)];
+    const double ghost_l = LDD(0, GP(-1)), ghost_r = LDD(0, GP(L));
+    if (FUSE && fz_reader) { // this tile is done with the mailbox
+        __threadfence();
+        __syncthreads();
+        if (t == 0) {
+            atomicAdd(Fz.count, 1u);
+        }
+    }
 
     const double c2 = P.c2; // (0.5*dt)*dt, detail.h:1549
     int underflow = 0;
@@ -320,8 +382,31 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
                 ylo[gp] = yl[j];
                 yro[gp] = yr[j];
                 rngo[gp] = sst[q];
-                idxo[gp] = idxi[gp] + sdidx[q];
+                const i64 inew = (FUSE ? __ldcg(idxi + gp) : idxi[gp]) + sdidx[q];
+                idxo[gp] = inew;
                 nan |= uu != uu;
+                if (FUSE && fz_pusher) {
+                    // the member's outermost owned blocks -> the neighbours' mailboxes (NVLink
+                    // peer stores): [hc, 2 hc) becomes prev's "from next", [N - 2 hc, N - hc)
+                    // next's "from prev"
+                    const int par = (int)((*Fz.epoch + (u64)Fz.batch + 1ULL) & 1ULL);
+                    u64* dst = nullptr;
+                    if (gp >= Fz.hc && gp < 2 * Fz.hc) {
+                        dst = slab_mail(Fz.prev, par, 1, Fz.hc) + (gp - Fz.hc);
+                    }
+                    else if (gp >= N - 2 * Fz.hc && gp < N - Fz.hc) {
+                        dst = slab_mail(Fz.next, par, 0, Fz.hc) + (gp - (N - 2 * Fz.hc));
+                    }
+                    if (dst) {
+                        dst[0] = (u64)__double_as_longlong(uu);
+                        dst[Fz.hc] = (u64)__double_as_longlong(v[j]);
+                        dst[2 * Fz.hc] = (u64)__double_as_longlong(a[j]);
+                        dst[3 * Fz.hc] = (u64)__double_as_longlong(yl[j]);
+                        dst[4 * Fz.hc] = (u64)__double_as_longlong(yr[j]);
+                        dst[5 * Fz.hc] = (u64)inew;
+                        dst[6 * Fz.hc] = sst[q];
+                    }
+                }
             }
         }
         if (nan) {
@@ -335,6 +420,29 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
         }
     }
     if (!STOP) {
+        if (FUSE && fz_pusher) {
+            // the last pusher to finish publishes the epoch -- once every reader of THIS launch is
+            // done with the mailbox, so that a neighbour that sees the epoch may refill the slot
+            // this launch read from (it does so two batches on)
+            __threadfence_system();
+            __syncthreads();
+            if (t == 0 && atomicAdd(Fz.count + 1, 1u) == (unsigned)Fz.n_pushers - 1u) {
+                const unsigned long long t0 = global_ns();
+                while (*reinterpret_cast<volatile unsigned int*>(Fz.count) < (unsigned)Fz.n_readers) {
+                    if (global_ns() - t0 > Fz.timeout_ns) {
+                        Fz.h_status[0] = 1;
+                        break;
+                    }
+                    __nanosleep(100);
+                }
+                Fz.count[0] = 0u;
+                Fz.count[1] = 0u;
+                __threadfence_system();
+                const u64 e_out = *Fz.epoch + (u64)Fz.batch + 1ULL;
+                st_release_sys(Fz.prev + 1, e_out); // prev's flag "from next"
+                st_release_sys(Fz.next + 0, e_out); // next's flag "from prev"
+            }
+        }
         return;
     }
 

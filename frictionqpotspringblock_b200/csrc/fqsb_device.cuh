@@ -138,6 +138,27 @@ struct Thermal {
 #define FQSB_BK_PARK 8      // stop modes: steps whose per-thread sums are parked before a reduction (power of 2)
 #define FQSB_BK_GROUP 32    // tiles per group of the two-level reduction of the per-step logs
 
+// Slab member whose halo exchange rides on the tile kernel (fixed-step batches of a
+// slab-decomposed line, fqsb_slab.inl): the tiles next to the member's halo regions READ them
+// from the member's mailbox (filled by the neighbours' previous batch over NVLink) instead of from
+// the state arrays, and the tiles that own the member's outermost blocks WRITE them straight into
+// the neighbours' mailboxes in their write-back -- no push / import launches between batches.
+struct BlockedFuse {
+    int on;        // 0: plain launch
+    int pull;      // read the halo regions from the mailbox (every batch of a call but the first)
+    int batch;     // index of this batch within the call
+    int n_readers; // tiles that pull (0 when !pull)
+    int n_pushers; // tiles that push
+    i64 hc;        // blocks per halo region (one side)
+    u64* self;     // own mailbox (epoch flags "from prev" / "from next" at words 0 / 1)
+    u64* prev;     // the neighbours' mailboxes (peer-mapped)
+    u64* next;
+    const u64* epoch;    // device: halo exchanges completed before this call
+    unsigned int* count; // device [2]: readers done, pushers done (0 between launches)
+    volatile int* h_status; // host-mapped: [0] peer timeout
+    unsigned long long timeout_ns;
+};
+
 struct BlockedArgs {
     int own;    // owned blocks per tile (the last tile may own fewer)
     int H;      // halo blocks on each side (>= ksteps unless the system has no interactions)
@@ -153,7 +174,58 @@ struct BlockedArgs {
     double* log;  // [R][ntiles][FQSB_BK_MAXSTEPS][FQSB_NLOG] per-step sums of every tile
     double* glog; // [R][ngroups][FQSB_BK_MAXSTEPS][FQSB_NLOG] ... of every group of tiles
     unsigned int* gcount; // [R][ngroups] tiles of a group that have finished (0 between launches)
+    BlockedFuse fuse;
 };
+
+// ---- slab mailboxes (fqsb_slab.inl; also read / written by k_blocked in fused mode) -----------
+#define FQSB_SLAB_FLAGS 32 // 8-byte words reserved for the epoch flags at the head of a mailbox
+
+// mailbox layout (8-byte words): flags | halo mail [2 parity][2 side][7 planes][hc] |
+// gather [2 parity][world][gcap]
+__host__ __device__ __forceinline__ u64* slab_mail(u64* base, int parity, int side, i64 hc)
+{
+    return base + FQSB_SLAB_FLAGS + (i64)((parity * 2 + side) * 7) * hc;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 ld_acquire_sys(const u64* p)
+{
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(u64* p, u64 v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+// which tiles of a fused launch touch the exchange: `reader` = its load range (owned blocks, H
+// halo blocks and the frozen cell per side, periodic in the n local blocks) meets a halo region
+// [0, hc) / [n - hc, n); `pusher` = it owns blocks of [hc, 2 hc) / [n - 2 hc, n - hc)
+__host__ __device__ inline void blocked_tile_roles(i64 n, i64 hc, i64 own, i64 H, i64 c,
+                                                   bool* reader, bool* pusher)
+{
+    const i64 own0 = c * own;
+    const i64 cnt = n - own0 < own ? n - own0 : own;
+    const i64 a0 = own0, a1 = own0 + cnt;
+    *pusher = (a0 < 2 * hc && hc < a1) || (a0 < n - hc && n - 2 * hc < a1);
+    bool r = false;
+    for (int k = -1; k <= 1; ++k) {
+        const i64 l0 = own0 - H - 1 + k * n, l1 = own0 + cnt + H + 1 + k * n;
+        r = r || (l0 < hc && 0 < l1) || (l0 < n && n - hc < l1);
+    }
+    *reader = r;
+}
+
 
 // ---- prrng::pcg32 ------------------------------------------------------
 #define FQSB_PCG_MULT 0x5851f42d4c957f2dULL

@@ -21,8 +21,6 @@
 // s* < k of a batch -> every member rolls back to its snapshot and redoes exactly s* steps.
 
 #define FQSB_SLAB_MAXW 16
-#define FQSB_SLAB_FLAGS 32 // 8-byte words reserved for the epoch flags at the head of a mailbox
-
 namespace fqsb {
 
 struct SlabDev {
@@ -38,13 +36,6 @@ struct SlabDev {
     unsigned long long timeout_ns;
 };
 
-// mailbox layout (8-byte words): flags | halo mail [2 parity][2 side][7 planes][hc] |
-// gather [2 parity][world][gcap]
-__host__ __device__ __forceinline__ u64* slab_mail(u64* base, int parity, int side, i64 hc)
-{
-    return base + FQSB_SLAB_FLAGS + (i64)((parity * 2 + side) * 7) * hc;
-}
-
 __host__ __device__ __forceinline__ double* slab_gather(u64* base, int parity, int member, i64 hc,
                                                         int world, int gcap)
 {
@@ -55,25 +46,6 @@ __host__ __device__ __forceinline__ double* slab_gather(u64* base, int parity, i
 inline size_t slab_mailbox_words(i64 hc, int world, int gcap)
 {
     return (size_t)FQSB_SLAB_FLAGS + 28 * (size_t)hc + 2 * (size_t)world * (size_t)gcap;
-}
-
-__device__ __forceinline__ u64 ld_acquire_sys(const u64* p)
-{
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release_sys(u64* p, u64 v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
 }
 
 // spin until *flag >= epoch (published by a peer with st.release.sys); gives up after timeout_ns
@@ -341,7 +313,8 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_slab_import_blocked(const State S, const SlabDev D, const SlabPlanes PL, const int set_arg,
-                          const int logged, const RunArgs A, const int ksteps)
+                          const int logged, const RunArgs A, const int ksteps,
+                          const int advance = 1)
 {
     __shared__ int s_ok, s_last;
     __shared__ double tot[FQSB_BK_MAXSTEPS * FQSB_NLOG];
@@ -350,7 +323,8 @@ __global__ void __launch_bounds__(256)
     const int set = set_arg < 2 ? set_arg : (flip ^ 1);
     const int nsteps = logged ? ctl.batch : 0;
     const bool running = ctl.status == ST_RUNNING;
-    const u64 e = D.epoch[0] + 1;
+    // (advance > 1: the halo exchanges in between rode on the tile kernel, BlockedFuse)
+    const u64 e = D.epoch[0] + (u64)advance;
     const u64 ge = D.epoch[1] + 1;
     u64* self = D.peer[D.rank];
     const int par = (int)(e & 1ULL);
@@ -922,8 +896,18 @@ static int slab_blocked_run(fqsb_system** m, int nm, RunArgs A, i64 batch)
     A.own_lo = (int)m[0]->own_lo;
     A.own_hi = (int)m[0]->own_hi;
     if (A.mode == MODE_FIXED) {
+        // Fixed steps need no decision between batches, so the halo exchange rides on the tile
+        // kernel (BlockedFuse): the tiles at the member's ends read the halo regions from the
+        // mailbox and write the member's outermost owned blocks into the neighbours' mailboxes
+        // from their write-back. ONE launch per batch; one import at the end of the call brings
+        // the last mail into the state arrays. FQSB_SLAB_FUSE=0: push / import launches instead.
+        static const bool fuse = [] {
+            const char* e = getenv("FQSB_SLAB_FUSE");
+            return !(e && e[0] == '0');
+        }();
         int parity = 0;
         i64 left = A.max_steps;
+        int nb = 0;
         while (left > 0) {
             const i64 k = left < batch ? left : batch;
             for (int g = 0; g < nm; ++g) {
@@ -935,26 +919,65 @@ static int slab_blocked_run(fqsb_system** m, int nm, RunArgs A, i64 batch)
                 BlockedArgs K = s->bk;
                 K.nsteps = (int)k;
                 K.flip = parity;
+                if (fuse) {
+                    const SlabDev& D = s->slab->dev;
+                    const BlockedPlan& pl = plan[(size_t)g];
+                    BlockedFuse& F = K.fuse;
+                    F.on = 1;
+                    F.pull = nb > 0;
+                    F.batch = nb;
+                    F.hc = D.hc;
+                    F.self = D.peer[D.rank];
+                    F.prev = D.peer[(D.rank + D.world - 1) % D.world];
+                    F.next = D.peer[(D.rank + 1) % D.world];
+                    F.epoch = D.epoch;
+                    F.count = D.ticket + 2;
+                    F.h_status = D.h_status;
+                    F.timeout_ns = D.timeout_ns;
+                    F.n_readers = F.n_pushers = 0;
+                    for (int c = 0; c < pl.ntiles; ++c) {
+                        bool rd, pu;
+                        blocked_tile_roles(s->P.N, D.hc, pl.own, pl.H, c, &rd, &pu);
+                        F.n_readers += rd && F.pull;
+                        F.n_pushers += pu;
+                    }
+                }
                 cudaError_t e = launch_blocked(plan[(size_t)g], s->P, s->S, Ag, K, s->stream);
                 if (e != cudaSuccess) {
                     return cuda_fail(e, "blocked kernel launch");
                 }
-                k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
-                    s->S, s->slab->dev, slab_planes(s), parity ^ 1, nullptr, 0);
-                CU(cudaGetLastError());
-                s->launches += 2;
+                s->launches++;
+                if (!fuse) {
+                    k_slab_push_blocked<<<slab_copy_grid(s->slab, 64u), 256, 0, s->stream>>>(
+                        s->S, s->slab->dev, slab_planes(s), parity ^ 1, nullptr, 0);
+                    CU(cudaGetLastError());
+                    s->launches++;
+                }
                 s->steps += k;
             }
+            if (!fuse) {
+                for (int g = 0; g < nm; ++g) {
+                    fqsb_system* s = m[g];
+                    CU(cudaSetDevice(s->device));
+                    k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
+                        s->S, s->slab->dev, slab_planes(s), parity ^ 1, 0, A, (int)batch);
+                    CU(cudaGetLastError());
+                    s->launches++;
+                }
+            }
+            parity ^= 1;
+            left -= k;
+            nb++;
+        }
+        if (fuse && nb > 0) {
             for (int g = 0; g < nm; ++g) {
                 fqsb_system* s = m[g];
                 CU(cudaSetDevice(s->device));
                 k_slab_import_blocked<<<slab_copy_grid(s->slab, 32u), 256, 0, s->stream>>>(
-                    s->S, s->slab->dev, slab_planes(s), parity ^ 1, 0, A, (int)batch);
+                    s->S, s->slab->dev, slab_planes(s), parity, 0, A, (int)batch, nb);
                 CU(cudaGetLastError());
                 s->launches++;
             }
-            parity ^= 1;
-            left -= k;
         }
         for (int g = 0; g < nm; ++g) {
             fqsb_system* s = m[g];
@@ -1328,8 +1351,9 @@ int fqsb_slab_init(fqsb_system* s, int rank, int world, int64_t halo_cells, int 
         CU(cudaMemset(L->mailbox, 0, L->mailbox_bytes));
         CU(cudaMalloc((void**)&L->d_epoch, 2 * sizeof(u64)));
         CU(cudaMemset(L->d_epoch, 0, 2 * sizeof(u64)));
-        CU(cudaMalloc((void**)&L->d_ticket, 2 * sizeof(unsigned int)));
-        CU(cudaMemset(L->d_ticket, 0, 2 * sizeof(unsigned int)));
+        // [0], [1]: push / import tickets; [2], [3]: readers / pushers done of a fused tile launch
+        CU(cudaMalloc((void**)&L->d_ticket, 4 * sizeof(unsigned int)));
+        CU(cudaMemset(L->d_ticket, 0, 4 * sizeof(unsigned int)));
         const size_t res = 2 * (size_t)world * (size_t)L->gcap;
         CU(cudaHostAlloc((void**)&L->h_res, res * sizeof(double), cudaHostAllocMapped));
         CU(cudaHostAlloc((void**)&L->h_status, 4 * sizeof(int), cudaHostAllocMapped));
