@@ -132,6 +132,47 @@ def test_slab_flow_steps_and_batch_redo(kernel):
     assert np.all(s.owned("v") == 0.0)  # quench() on convergence (detail.h:1781)
 
 
+_FIXED_STEPS_SCRIPT = r"""
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import frictionqpotspringblock_b200 as F
+from frictionqpotspringblock_b200.slab import SlabSystem
+N = 6000
+kw = dict(m=1.0, eta=2.0 * np.sqrt(3.0) / 10.0, mu=1.0, a1=1.0, a2=0.5, k_frame=1.0 / N, dt=0.1,
+          shape=[N], seed=11, distribution="random", parameters=[2.0], offset=-50)
+ref = F.Line1d.System_Cuspy_Quartic(kernel=2, **kw)
+s = SlabSystem("Line1d", "System_Cuspy_Quartic", halo=8, devices=[0, 0, 0],
+               kernel=3 | (700 << 16), **kw)
+for x in (ref, s):
+    x.u_frame = 2.0
+    x.timeSteps(8 * 13 + 3)   # 14 batches: every slot of the two-slot mailbox is reused 6 times
+    x.flowSteps(21, 0.1)
+    x.timeSteps(5)
+assert s.members[0].last_kernel == "slab_blocked_1d"
+assert np.array_equal(s.owned("u"), ref.u) and np.array_equal(s.owned("v"), ref.v)
+assert np.array_equal(s.owned("index_at_align"), ref.chunk.index_at_align)
+assert ref.minimise() == 0 and s.minimise() == 0 and s.inc == ref.inc
+assert np.array_equal(s.owned("index_at_align"), ref.chunk.index_at_align)
+print("ok", s.launch_count if hasattr(s, "launch_count") else "")
+"""
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_fixed_step_batches_fused_and_unfused_exchange(fuse):
+    """timeSteps / flowSteps of a three-member line: the halo exchange inside the tile kernel
+    (default) and the push / import launches (FQSB_SLAB_FUSE=0) give the single handle's bits,
+    and a stop-mode call afterwards finds the epochs where it expects them."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FQSB_SLAB_FUSE=fuse)
+    r = subprocess.run([sys.executable, "-c", _FIXED_STEPS_SCRIPT, root], env=env,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("ok")
+
+
 def test_slab_refuses_what_a_halo_cannot_reproduce():
     from frictionqpotspringblock_b200.slab import SlabSystem
 
