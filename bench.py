@@ -35,9 +35,9 @@ if str(ROOT) not in sys.path:
 N_BLOCKS = 4096
 R_CONFIG = 16384  # realisations of BASELINE configs[1]
 ALGO_BYTES_PER_UPDATE = 64.0  # u,v,a read + write (48) + y_left,y_right read (16); SURVEY 8(d)
-# FP64-pipe instructions per block-update of k_resident<Cuspy,Laplace1d,unit>, counted by ncu
-# (profiles/r2d_ncu_resident_fixed.txt: 145 DADD + 84 DMUL + 16 DSETP per warp-step of 8 blocks;
-# the reference's evaluation order, no FMA contraction)
+# FP64-pipe instructions per block-update of k_resident<Cuspy,Laplace1d,unit> (SASS of the loop,
+# cross-checked with ncu's instruction counts, profiles/r2g_ncu_resident_fixed.txt: 144 DADD +
+# 81 DMUL + 20 DSETP per warp-step of 8 blocks; the reference's evaluation order, no FMA contraction)
 FP64_INSTR_PER_UPDATE = 245.0 / 8.0
 # DADD/DMUL issue rate a B200 SM sustains in a register-only loop (tools/fp64_peak.cu, measured:
 # 1.934 of the nominal 2.0 warp-instructions per SM per clock)
@@ -619,7 +619,7 @@ def main():
                       "ms_per_step": 1e3 * csec / 3,
                       "minimise_block_updates_per_s": world * msteps * N / msec,
                       "how": "the same ensemble, protocol and timeSteps(T) calls with "
-                             "contracted=True (resident kernel compiled with -fmad=true: ~21.6 "
+                             "contracted=True (resident kernel compiled with -fmad=true: 20.6 "
                              "instead of 30.6 FP64-pipe instructions per block-update); "
                              "device-timed; results equal to rounding, not bit for bit"}
         del ensc

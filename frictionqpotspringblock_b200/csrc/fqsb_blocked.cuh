@@ -8,23 +8,35 @@
 // steps only the outermost s blocks of each side have been contaminated by the missing
 // neighbours, and those are halo copies whose owner tile computes them exactly. One launch
 // therefore advances the whole line by k steps with ONE pass over HBM / L2 (all seven per-block
-// arrays in, all seven out: 112 B per block per launch = 3.5 B per block-update at k = 32), and
-// the inner loop is the on-chip loop of k_resident (slips in shared memory, v, a, wells in
-// registers, pcg32 states in shared memory), bound by the FP64 pipe instead of by memory.
+// arrays in, all seven out: 112 B per block per launch = 1.75 B per block-update at k = 64), and
+// the inner loop is the on-chip loop of k_resident (all state of a thread's B consecutive blocks
+// in registers, one slip per neighbouring thread through shared memory, pcg32 states in shared
+// memory), bound by the FP64 issue rate instead of by memory. Two tiles of 256 threads share an
+// SM: the load / store phase of one overlaps the steps of the other.
 //
 // grid = (tiles, R). The new state goes to the other buffer set (neighbouring tiles still read
 // the old one as their halo), which also makes a launch revocable: in the stop modes every tile
-// logs its per-step partial sums (owned blocks only), the last tile to finish adds them up in
-// tile order, replays the per-step decisions of timeStepsUntilEvent / minimise /
-// minimise_truncate (detail.h:1605-1619, 1764-1784, 1858-1886) and either commits the batch
-// (flips the buffer set) or -- the criterion fired at step s* < k -- leaves the input set
-// current and asks for a batch of exactly s* steps. No host round trip is involved; the host
-// only polls the status every few batches.
+// logs its per-step partial sums (owned blocks only; per-thread sums are parked in shared memory
+// and reduced every FQSB_BK_PARK steps), the tiles' logs are added up in two levels (groups of
+// FQSB_BK_GROUP tiles, then the groups; fixed order), and the last tile to finish replays the
+// per-step decisions of timeStepsUntilEvent / minimise / minimise_truncate (detail.h:1605-1619,
+// 1764-1784, 1858-1886) and either commits the batch (flips the buffer set) or -- the criterion
+// fired at step s* < k -- leaves the input set current and asks for a batch of exactly s* steps.
+// No host round trip is involved; the host only polls the status every few batches.
+//
+// FUSE (members of a slab-decomposed line, fixed-step batches; BlockedFuse in fqsb_device.cuh):
+// the halo exchange with the neighbouring GPUs rides on the launch -- boundary tiles read the
+// member's halo regions from its mailbox and write the outermost owned blocks straight into the
+// neighbours' mailboxes over NVLink.
 #pragma once
 
 #include "fqsb_kernels.cuh"
 
 namespace fqsb {
+
+#ifndef FQSB_BK_YMID
+#define FQSB_BK_YMID 1
+#endif
 
 // rare path: a block of the tile left its well. The global index is idx_in + sdidx (the delta
 // accumulated during this launch); the input set is never written.
@@ -148,6 +160,10 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
     };
 
     double u[B], v[B], a[B], yl[B], yr[B];
+    // Cuspy: midpoint of the current well beside it (force = ym - u: 1 FP64 instruction instead
+    // of 3, same bits; detail.h:164-169)
+    constexpr bool YMID = FQSB_BK_YMID && POT == POT_CUSPY && B <= 5; // (B > 5: the registers are worth more)
+    double ym[YMID ? B : 1];
     // ownmask: blocks this tile writes back; summask: those of them that enter the sums (a member
     // of a slab-decomposed line leaves out the halo copies of its neighbours' blocks);
     // ghostmask: blocks whose right neighbour is the frozen cell just outside the tile
@@ -175,6 +191,9 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
         else { // padding (never stored): a copy of the last block in one unbounded well
             yl[j] = -1e300;
             yr[j] = 1e300;
+        }
+        if (YMID) {
+            ym[j] = 0.5 * (yl[j] + yr[j]);
         }
         if (q + 1 >= L) {
             ghostmask |= 1u << j;
@@ -248,6 +267,9 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
                     }
                     yl[j] = l;
                     yr[j] = rr;
+                    if (YMID) {
+                        ym[j] = 0.5 * (l + rr);
+                    }
                     sdidx[q] += moved;
                     if ((ownmask >> j) & 1u) { // halo copies are accounted for by their owner
                         underflow |= uflag;
@@ -273,7 +295,13 @@ __global__ void __launch_bounds__(FQSB_BK_T, FQSB_BK_CTAS)
                                                       : (j < B - 1 ? u[j < B - 1 ? j + 1 : 0] : from_right);
             auto UE = [&](int qq) { return qq < q ? ul : ur; };
             double fi = f_interactions<INT, false, UNIT>(P, UE, nullptr, q, 0, 0, u[j]);
-            double fp = f_potential<POT, UNIT>(P, u[j], yl[j], yr[j]);
+            double fp;
+            if (YMID) {
+                fp = UNIT ? (ym[j] - u[j]) : (ym[j] - u[j]) * P.mu;
+            }
+            else {
+                fp = f_potential<POT, UNIT>(P, u[j], yl[j], yr[j]);
+            }
             double ff = P.k_frame * (uf - u[j]);
             double F = ff + fp + fi;
             double f = verlet_tail<UNIT>(P, F, v[j], a[j]);

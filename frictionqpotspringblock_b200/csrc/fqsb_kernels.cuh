@@ -182,6 +182,9 @@ static __device__ __noinline__ int hop_global(const Par& P, double un, double* y
 #ifndef FQSB_YMID
 #define FQSB_YMID 1
 #endif
+#ifndef FQSB_YMID_FIXED
+#define FQSB_YMID_FIXED 0 // ... in the fixed-step loops too: measured slower (see YMID below)
+#endif
 #ifndef FQSB_UREG
 #define FQSB_UREG 1
 #endif
@@ -241,8 +244,12 @@ __global__ void __launch_bounds__(T)
     double yl[YSMEM ? 1 : B], yr[YSMEM ? 1 : B];
     // Cuspy potential: the midpoint of the well, 0.5 * (y_l + y_r), only changes with the well;
     // kept beside it, the force costs one subtraction instead of three operations (same bits).
-    // Measured: +2.6 % in the stop modes, -0.7 % in the fixed-step loop (register pressure), hence STOP
-    constexpr bool YMID = FQSB_YMID && POT == POT_CUSPY && !YSMEM && STOP;
+    // In the fixed-step loop of this kernel it costs more in spills than it saves: 229 instead of
+    // 245 FP64 instructions per warp-step but 10 instead of 4 local loads -- 5.57e11 -> 5.48e11
+    // block-updates/s (flowSteps -10 %, contracted build -3 %), measured twice (round 2: -0.7 %
+    // before the loop was trimmed). Hence STOP only (FQSB_YMID_FIXED = 0). k_blocked, with 4
+    // blocks per thread and registers to spare, keeps the midpoint in every variant.
+    constexpr bool YMID = FQSB_YMID && POT == POT_CUSPY && !YSMEM && (STOP || FQSB_YMID_FIXED);
     double ym[YMID ? B : 1];
     int ij[ONE_D ? 1 : B];
 
