@@ -133,6 +133,7 @@ SIGNATURES = {
     "fqsb_slab_ipc_handle": (C.c_int, [_P, _P]),
     "fqsb_slab_connect": (C.c_int, [_P, _P, _P]),
     "fqsb_slab_info": (C.c_int, [_P, _P]),
+    "fqsb_plan_blocked": (C.c_int, [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "fqsb_slab_exchange": (C.c_int, [_P, C.c_int]),
     "fqsb_slab_time_steps": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_double]),
     "fqsb_slab_minimise": (C.c_int, [_P, C.c_int, C.c_double, C.c_int64, C.c_int64, C.c_int64,

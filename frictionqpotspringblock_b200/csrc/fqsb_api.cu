@@ -970,6 +970,49 @@ static bool use_blocked(const fqsb_system* s, int mode, bool overdamped)
 static int ensure_stream_buffers(fqsb_system* s);
 static int run_host_ring(fqsb_system* s, RunArgs A, bool overdamped, bool track_user);
 
+// host-only view of the tile planner (tests, tools)
+extern "C" int fqsb_plan_blocked(int64_t n_blocks, int64_t n_realisations, int has_interactions,
+                                 int steps_per_launch, int own_hint, int64_t halo_cells,
+                                 int64_t* out)
+{
+    if (!out || n_blocks < 2 || n_realisations < 1) {
+        return fail(FQSB_EASSERT, "fqsb_plan_blocked: n_blocks >= 2, n_realisations >= 1, out != NULL");
+    }
+    Par P;
+    memset(&P, 0, sizeof P);
+    P.rank = 1;
+    P.N = n_blocks;
+    P.R = n_realisations;
+    P.pot = POT_CUSPY;
+    P.inter = has_interactions ? INT_LAPLACE1D : INT_NONE;
+    const BlockedPlan pl = blocked_plan(P, steps_per_launch, own_hint);
+    if (pl.B < 2 || pl.B > 8) {
+        return fail(FQSB_EUNSUPPORTED, "no tile geometry for the blocked kernel");
+    }
+    int sms = 148, dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+        sms = n;
+    }
+    cudaGetLastError(); // (no device: the planner falls back to 148 SMs, nothing to report)
+    out[0] = pl.B;
+    out[1] = pl.own;
+    out[2] = pl.H;
+    out[3] = pl.ksteps;
+    out[4] = pl.ntiles;
+    out[5] = ((int64_t)pl.ntiles * n_realisations + sms - 1) / sms;
+    out[6] = out[7] = 0;
+    if (halo_cells > 0) {
+        for (int c = 0; c < pl.ntiles; ++c) {
+            bool rd, pu;
+            blocked_tile_roles(n_blocks, halo_cells, pl.own, pl.H, c, &rd, &pu);
+            out[6] += rd;
+            out[7] += pu;
+        }
+    }
+    return FQSB_OK;
+}
+
 static int ensure_blocked_buffers(fqsb_system* s, const BlockedPlan& plan)
 {
     TRY(ensure_stream_buffers(s));

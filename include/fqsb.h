@@ -315,6 +315,17 @@ int fqsb_slab_event_driven_step(fqsb_system** members, int nmembers, double eps,
 int64_t fqsb_slab_first_stop(const double* log, int64_t k, double tol, int64_t niter_tol,
                              double* ring_num, double* ring_den);
 
+/* host-only: geometry the temporally blocked kernel (1-D nearest-neighbour lines beyond one CTA,
+ * BASELINE config #3) would use for a line of n_blocks x n_realisations; no reference counterpart
+ * (the reference steps one block at a time, ref: detail.h:1539-1569). steps_per_launch / own_hint
+ * 0 = planner's choice. halo_cells > 0: the line is a slab member with that many halo blocks per
+ * side, and out[6], out[7] count the tiles that read / write the neighbours' mailboxes when the
+ * exchange rides on the tile kernel.
+ * out [8]: blocks per thread, owned blocks per tile, tile halo, steps per launch, tiles,
+ * tiles per SM (ceil), reader tiles, pusher tiles */
+int fqsb_plan_blocked(int64_t n_blocks, int64_t n_realisations, int has_interactions,
+                      int steps_per_launch, int own_hint, int64_t halo_cells, int64_t* out);
+
 /* host staging helpers (pinned memory for the e2e path) ---------------------------------- */
 void* fqsb_host_alloc(size_t bytes);
 void fqsb_host_free(void* p);

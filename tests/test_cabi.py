@@ -72,3 +72,45 @@ def test_product_does_not_import_the_oracle():
         text = path.read_text()
         assert "oracle" not in text.replace("CPU oracle", "").replace("the oracle", "") \
             .replace("oracle/fqsb_oracle.c", ""), path
+
+
+def _plan(n, r=1, inter=1, k=0, own=0, halo=0):
+    from frictionqpotspringblock_b200 import _capi
+
+    out = (C.c_int64 * 8)()
+    assert _capi.lib.fqsb_plan_blocked(n, r, inter, k, own, halo, out) == 0
+    return dict(zip(("B", "own", "H", "ksteps", "ntiles", "rounds", "readers", "pushers"), out))
+
+
+def test_blocked_tile_planner_is_host_only_and_sane():
+    """geometry of the temporally blocked kernel (no device needed: 148 SMs assumed): tiles cover
+    the line, fit a CTA of 256 threads x B blocks, and the grid is costed per SM (tiles on one SM
+    share its FP64 issue slots)."""
+    for n in (4097, 20000, 131200, 1 << 19, 1 << 20, 3_000_001):
+        p = _plan(n)
+        assert 2 <= p["B"] <= 8 and p["H"] == p["ksteps"] == 64
+        assert p["own"] + 2 * p["H"] <= 256 * p["B"]
+        assert (p["ntiles"] - 1) * p["own"] < n <= p["ntiles"] * p["own"]
+        assert p["rounds"] == -(-p["ntiles"] // 148)
+    # config #3: 1171 tiles of 896 + 2 x 64 blocks, 8 tiles per SM
+    p = _plan(1 << 20)
+    assert (p["B"], p["own"], p["ntiles"], p["rounds"]) == (4, 896, 1171, 8)
+    # a member of an 8-GPU slab of that line: ONE tile per SM (205 tiles of B = 3 would put two
+    # tiles on 57 SMs and cost 6 units per step instead of 4)
+    p = _plan((1 << 17) + 128)
+    assert p["B"] == 4 and p["ntiles"] <= 148 and p["rounds"] == 1
+    # no interactions (Particles): no halo at all
+    assert _plan(100000, inter=0)["H"] == 0
+    # short batches (timeStepsUntilEvent) and a forced tile size (tests)
+    p = _plan(20000, k=8, own=101)
+    assert (p["ksteps"], p["H"], p["own"], p["ntiles"]) == (8, 8, 101, 199)
+
+
+def test_blocked_tile_roles_of_a_slab_member():
+    """exchange fused into the tile kernel: every halo cell of the member is read by some tile, the
+    pushed regions are owned by some tile, and only the tiles at the member's ends take part."""
+    for n, halo, own in ((131200, 64, 0), (6000 // 3 + 16, 8, 700), (4096 // 2 + 32, 16, 0),
+                         (524416, 64, 0)):
+        p = _plan(n, halo=halo, own=own, k=halo)
+        assert 1 <= p["pushers"] <= 4 and 1 <= p["readers"] <= 4
+        assert p["readers"] <= p["ntiles"] and p["pushers"] <= p["ntiles"]
